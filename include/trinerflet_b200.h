@@ -1,0 +1,165 @@
+/* trinerflet_b200 -- C ABI of the B200-native (sm_100a) TriNeRFLet reconstruction hot path.
+ *
+ * Drop-in boundary for the native layer the reference reaches through pybind11/torch:
+ *   aux_libs/raymarching/src/raymarching.h:7-18  (10 functions, at::Tensor args, outputs pre-allocated)
+ *   aux_libs/shencoder/src/shencoder.h:9-10      (sh_encode_forward / backward)
+ * plus the library calls the reference makes for the encoder and MLP heads
+ *   pytorch_wavelets DWTInverse      (reconstruction/triplaneencoder/triplane_encoder.py:394)
+ *   F.grid_sample                    (triplane_encoder.py:329)
+ *   nn.Linear x5 / trunc_exp / sigmoid (reconstruction/nerf/network.py:118-147)
+ *
+ * Conventions (all entry points):
+ *   - plain device pointers + explicit element counts, no torch types; every output buffer is
+ *     allocated by the caller (same ownership rule as the reference);
+ *   - `stream` is the caller's CUDA stream (cudaStream_t passed as void*); kernels never allocate,
+ *     never synchronise, keep no state between calls;
+ *   - return value: 0 = launched ok, >0 = cudaError_t, <0 = TNL_ERR_*; tnl_last_error() gives text;
+ *   - fp32 everywhere unless the name says otherwise; int32 index tensors as in the reference.
+ *
+ * Memory layouts of the encoder ("channels-last"):
+ *   plane tensor   x   [3][n][n][C]        (logical reference shape [3,C,n,n], C fastest)
+ *   detail coefs   yh  [3][3][n][n][C]     (logical reference shape [3,C,3,n,n])
+ */
+#ifndef TRINERFLET_B200_H
+#define TRINERFLET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TNL_ABI_VERSION 1
+#define TNL_ERR_INVALID_ARGUMENT (-1)
+#define TNL_ERR_UNSUPPORTED (-2)
+#define TNL_ERR_WORKSPACE (-3)
+
+typedef void* tnl_stream_t; /* cudaStream_t */
+
+int tnl_abi_version(void);
+const char* tnl_last_error(void);
+
+/* ------------------------------------------------------------------ ray utilities ---------- */
+/* replaces near_far_from_aabb  (raymarching.h:7, raymarching.cu:148-156) */
+int tnl_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N,
+                           float min_near, float* nears, float* fars, tnl_stream_t stream);
+/* replaces sph_from_ray        (raymarching.h:8, raymarching.cu:201-209) */
+int tnl_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords,
+                     tnl_stream_t stream);
+/* replaces morton3D / morton3D_invert (raymarching.h:9-10, raymarching.cu:229-260) */
+int tnl_morton3d(const int32_t* coords, uint32_t N, int32_t* indices, tnl_stream_t stream);
+int tnl_morton3d_invert(const int32_t* indices, uint32_t N, int32_t* coords, tnl_stream_t stream);
+/* replaces packbits            (raymarching.h:11, raymarching.cu:292-300); N = number of output bytes */
+int tnl_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield, tnl_stream_t stream);
+
+/* ------------------------------------------------------------------ training march ---------- */
+/* replaces march_rays_train    (raymarching.h:13, raymarching.cu:482-490).
+ * Same outputs; sample slots are allocated by a deterministic exclusive scan in ray order instead
+ * of the reference's atomicAdd race (raymarching.cu:405-406), so rays[n] = (n, offset_n, count_n).
+ * counter[0] += total samples, counter[1] += N (as the reference's atomics leave them).
+ * xyzs/dirs/deltas must be zero-initialised by the caller (reference: torch.zeros).
+ * workspace: >= tnl_march_rays_train_workspace(N) bytes of device scratch. */
+size_t tnl_march_rays_train_workspace(uint32_t N);
+int tnl_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                         float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                         const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                         int32_t* rays, int32_t* counter, const float* noises, void* workspace,
+                         size_t workspace_bytes, tnl_stream_t stream);
+/* replaces composite_rays_train_forward / _backward (raymarching.h:14-15, raymarching.cu:580-693) */
+int tnl_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas,
+                                     const int32_t* rays, uint32_t M, uint32_t N, float T_thresh,
+                                     float* weights_sum, float* depth, float* image, tnl_stream_t stream);
+int tnl_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image,
+                                      const float* sigmas, const float* rgbs, const float* deltas,
+                                      const int32_t* rays, const float* weights_sum, const float* image,
+                                      uint32_t M, uint32_t N, float T_thresh, float* grad_sigmas,
+                                      float* grad_rgbs, tnl_stream_t stream);
+
+/* ------------------------------------------------------------------ inference march ---------- */
+/* replaces march_rays / composite_rays (raymarching.h:17-18, raymarching.cu:808-914) */
+int tnl_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* rays_alive, const float* rays_t,
+                   const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                   uint32_t C, uint32_t H, const uint8_t* grid, const float* nears, const float* fars,
+                   float* xyzs, float* dirs, float* deltas, const float* noises, tnl_stream_t stream);
+int tnl_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* rays_alive, float* rays_t,
+                       const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum,
+                       float* depth, float* image, tnl_stream_t stream);
+/* on-device stream compaction of rays_alive (replaces the boolean-index + D2H sync at
+ * reconstruction/nerf/renderer.py:364): out[0..n_out) = alive[i] for alive[i] >= 0, order kept;
+ * *n_out_dev receives the count.  workspace >= tnl_compact_alive_workspace(n) bytes. */
+size_t tnl_compact_alive_workspace(uint32_t n);
+int tnl_compact_alive(const int32_t* alive, uint32_t n, int32_t* out, int32_t* n_out_dev, void* workspace,
+                      size_t workspace_bytes, tnl_stream_t stream);
+
+/* ------------------------------------------------------------------ SH direction encoder ----- */
+/* replaces sh_encode_forward (shencoder.h:9, shencoder.cu:387-398) for degree <= 4, dy_dx = NULL */
+int tnl_sh_encode_forward(const float* inputs, float* outputs, uint32_t B, uint32_t degree, tnl_stream_t stream);
+
+/* ------------------------------------------------------------------ wavelet planes ----------- */
+/* One level of the inverse 2-D DWT (bior6.8, zero mode) exactly as TriPlaneVolume.build_planes chains
+ * it (triplane_encoder.py:379-394):  out = IDWT(pad4(2*x), pad4(yh)),  n -> 2n.
+ * x [3][n][n][C], yh [3][3][n][n][C] (yh[.,0]=high-pass along H, [.,1]=along W, [.,2]=both),
+ * out [3][2n][2n][C].  C % 8 == 0, n % 8 == 0. */
+int tnl_idwt_level_forward(const float* x, const float* yh, float* out, uint32_t n, uint32_t C,
+                           tnl_stream_t stream);
+/* Exact adjoint of the above: g_out [3][2n][2n][C] -> g_x [3][n][n][C], g_yh [3][3][n][n][C]
+ * (what SFB2D.backward + pad backward + the 2*x factor produce in the reference's autograd graph). */
+int tnl_idwt_level_backward(const float* g_out, float* g_x, float* g_yh, uint32_t n, uint32_t C,
+                            tnl_stream_t stream);
+
+/* Bilinear tri-plane sampling: replaces F.grid_sample(bilinear, border, align_corners=True) +
+ * permute/concat of TriPlaneVolume.forward (triplane_encoder.py:314-332, 523-530).
+ * planes [3][R][R][C]; xyz [M][3]; feat [M][3C] with feature index p*C + c.
+ * u = xyz * inv_bound (inv_bound = 1/bound in fp32, CUDA's tensor/scalar rule); if fp16_coords != 0,
+ * u is rounded to fp16 first (the autocast quirk of triplane_encoder.py:299).
+ * n_valid (device int32*, may be NULL): rows >= *n_valid are skipped (feat rows written as zeros). */
+int tnl_sample_planes_forward(const float* planes, const float* xyz, uint32_t M, uint32_t R, uint32_t C,
+                              float inv_bound, int fp16_coords, const int32_t* n_valid, float* feat,
+                              tnl_stream_t stream);
+/* Adjoint scatter (grid_sampler_2d_backward w.r.t. input): g_planes += ...; caller zero-fills g_planes. */
+int tnl_sample_planes_backward(const float* g_feat, const float* xyz, uint32_t M, uint32_t R, uint32_t C,
+                               float inv_bound, int fp16_coords, const int32_t* n_valid, float* g_planes,
+                               tnl_stream_t stream);
+
+/* ------------------------------------------------------------------ sigma / color MLP heads -- */
+/* NeRFNetwork.forward / .density (network.py:118-166) with the fp16-autocast arithmetic the reference
+ * trains with: fp16 operands, fp32 accumulation, fp16 rounding of every layer output, fp32 exp/SH.
+ * Weight masters are fp32 row-major [out][in] exactly as nn.Linear stores them:
+ *   W1 [H][3C]  W2 [16][H]  W3 [Hc][31]  W4 [Hc][Hc]  W5 [3][Hc];  H, Hc in {64, 128}; 3C % 16 == 0.
+ * `packed` (device, >= tnl_mlp_packed_bytes) receives the tensor-core fragment-ordered fp16 copy;
+ * re-pack after every optimizer step. */
+typedef struct tnl_mlp_dims {
+    uint32_t in_dim;   /* 3C */
+    uint32_t hidden;   /* H  */
+    uint32_t hidden_c; /* Hc */
+} tnl_mlp_dims;
+size_t tnl_mlp_packed_bytes(const tnl_mlp_dims* dims);
+int tnl_mlp_pack_weights(const tnl_mlp_dims* dims, const float* W1, const float* W2, const float* W3,
+                         const float* W4, const float* W5, void* packed, tnl_stream_t stream);
+/* feat [M][3C] fp32, dirs [M][3] fp32 (NULL => density only) -> sigma [M] fp32, rgb [M][3] fp32
+ * (fp16-representable), geo [M][15] fp32 (may be NULL).  n_valid as above (skipped rows -> zeros). */
+int tnl_mlp_forward(const tnl_mlp_dims* dims, const void* packed, const float* feat, const float* dirs,
+                    uint32_t M, const int32_t* n_valid, float* sigma, float* rgb, float* geo,
+                    tnl_stream_t stream);
+/* Backward of tnl_mlp_forward: recomputes activations from feat; g_sigma [M], g_rgb [M][3] in;
+ * g_feat [M][3C] out (may be NULL); g_W1..g_W5 fp32 accumulated with atomics (caller zero-fills). */
+int tnl_mlp_backward(const tnl_mlp_dims* dims, const void* packed, const float* feat, const float* dirs,
+                     uint32_t M, const int32_t* n_valid, const float* g_sigma, const float* g_rgb,
+                     float* g_feat, float* g_W1, float* g_W2, float* g_W3, float* g_W4, float* g_W5,
+                     tnl_stream_t stream);
+
+/* ------------------------------------------------------------------ density grid ------------- */
+/* Fused pieces of NeRFRenderer.update_extra_state (reconstruction/nerf/renderer.py:448-542). */
+/* cell-centre sample positions for a list of Morton cells of one cascade (renderer.py:474-483):
+ *   xyz = (2*coord/(H-1) - 1) * (bound_c - hgs) + (2*noise - 1) * hgs,  hgs = bound_c / H
+ * indices [n] int32 Morton codes, noise [n][3] uniform [0,1) -> xyz [n][3] */
+int tnl_grid_cell_positions(const int32_t* indices, uint32_t n, uint32_t H, float bound_c, const float* noise,
+                            float* xyz, tnl_stream_t stream);
+/* grid[idx] = max(grid[idx]*decay, sigma*density_scale) where both >= 0 (renderer.py:526-527) for the
+ * full sweep (indices == NULL => idx = i) or scattered cells; see DESIGN.md for the tmp_grid semantics. */
+int tnl_grid_ema_update(float* grid, const float* tmp_grid, uint32_t n, float decay, tnl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRINERFLET_B200_H */

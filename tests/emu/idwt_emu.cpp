@@ -1,0 +1,91 @@
+// TEST-ONLY host emulator of the IDWT kernels: runs the per-thread phase functions of
+// trinerflet_b200/csrc/idwt_core.cuh in lock-step (all threads phase A, barrier, all threads phase B),
+// so the CPU test-suite can check the kernels' index arithmetic against the oracle without a GPU.
+// Never linked into the product library.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include "../../trinerflet_b200/csrc/idwt_core.cuh"
+
+using namespace tnl;
+
+template <typename Cfg>
+static void emu_fwd(const float* x, const float* yh, float* out, unsigned n, unsigned C) {
+    unsigned gx, gy, gz, rows;
+    idwt_grid<Cfg>(n, C, 148, gx, gy, gz, rows);
+    std::vector<float> smem(2 * Cfg::MID_F + 2 * Cfg::STAGE);
+    std::vector<FwdState> st(Cfg::NT);
+    std::vector<IdwtGeom> geo(Cfg::NT);
+    for (unsigned bz = 0; bz < gz; ++bz) for (unsigned by = 0; by < gy; ++by) for (unsigned bx = 0; bx < gx; ++bx) {
+        float* mid0 = smem.data();
+        float* stage0 = smem.data() + 2 * Cfg::MID_F;
+        for (int t = 0; t < Cfg::NT; ++t) {
+            geo[t] = idwt_geom<Cfg>(t, IdwtBlock{(int)bx, (int)by, (int)bz}, (int)n, (int)C, (int)rows);
+            fwd_state_init(st[t]);
+            fwd_issue_stage<Cfg>(geo[t], stage0, x, yh, t, 0);
+        }
+        const int nsteps = geo[0].nsteps;
+        for (int ss = 0; ss < nsteps; ++ss) {
+            float* mid = mid0 + (ss & 1) * Cfg::MID_F;
+            const float* stage = stage0 + (ss & 1) * Cfg::STAGE;
+            for (int t = 0; t < Cfg::NT; ++t) {
+                fwd_issue_stage<Cfg>(geo[t], stage0 + ((ss + 1) & 1) * Cfg::STAGE, x, yh, t, ss + 1);
+                switch (ss % 3) {
+                    case 0: fwd_phase_a<Cfg, 0>(st[t], stage, mid, t); break;
+                    case 1: fwd_phase_a<Cfg, 1>(st[t], stage, mid, t); break;
+                    default: fwd_phase_a<Cfg, 2>(st[t], stage, mid, t); break;
+                }
+            }
+            for (int t = 0; t < Cfg::NT; ++t) fwd_phase_b<Cfg>(geo[t], mid, out, t, ss);
+        }
+    }
+}
+
+template <typename Cfg>
+static void emu_bwd(const float* g, float* g_x, float* g_yh, unsigned n, unsigned C) {
+    unsigned gx, gy, gz, rows;
+    idwt_grid<Cfg>(n, C, 148, gx, gy, gz, rows);
+    std::vector<float> smem(2 * Cfg::MID_B + 2 * Cfg::STAGE);
+    std::vector<BwdState> st(Cfg::NT);
+    std::vector<IdwtGeom> geo(Cfg::NT);
+    for (unsigned bz = 0; bz < gz; ++bz) for (unsigned by = 0; by < gy; ++by) for (unsigned bx = 0; bx < gx; ++bx) {
+        float* mid0 = smem.data();
+        float* stage0 = smem.data() + 2 * Cfg::MID_B;
+        for (int t = 0; t < Cfg::NT; ++t) {
+            geo[t] = idwt_geom<Cfg>(t, IdwtBlock{(int)bx, (int)by, (int)bz}, (int)n, (int)C, (int)rows);
+            bwd_state_init(st[t]);
+            bwd_issue_stage<Cfg>(geo[t], stage0, g, t, 0);
+        }
+        const int nsteps = geo[0].nsteps;
+        for (int ss = 0; ss < nsteps; ++ss) {
+            float* mid = mid0 + (ss & 1) * Cfg::MID_B;
+            const float* stage = stage0 + (ss & 1) * Cfg::STAGE;
+            for (int t = 0; t < Cfg::NT; ++t) {
+                bwd_issue_stage<Cfg>(geo[t], stage0 + ((ss + 1) & 1) * Cfg::STAGE, g, t, ss + 1);
+                switch (ss % 3) {
+                    case 0: bwd_phase_a<Cfg, 0>(st[t], stage, mid, t); break;
+                    case 1: bwd_phase_a<Cfg, 1>(st[t], stage, mid, t); break;
+                    default: bwd_phase_a<Cfg, 2>(st[t], stage, mid, t); break;
+                }
+            }
+            for (int t = 0; t < Cfg::NT; ++t) bwd_phase_b<Cfg>(geo[t], mid, g_x, g_yh, t, ss);
+        }
+    }
+}
+
+extern "C" {
+int emu_idwt_level_forward(const float* x, const float* yh, float* out, uint32_t n, uint32_t C) {
+    if (C % 32 == 0) emu_fwd<IdwtCfg<32, 32>>(x, yh, out, n, C);
+    else if (C % 24 == 0) emu_fwd<IdwtCfg<24, 32>>(x, yh, out, n, C);
+    else if (C % 16 == 0) emu_fwd<IdwtCfg<16, 32>>(x, yh, out, n, C);
+    else emu_fwd<IdwtCfg<8, 32>>(x, yh, out, n, C);
+    return 0;
+}
+int emu_idwt_level_backward(const float* g, float* g_x, float* g_yh, uint32_t n, uint32_t C) {
+    if (C % 32 == 0) emu_bwd<IdwtCfg<32, 32>>(g, g_x, g_yh, n, C);
+    else if (C % 24 == 0) emu_bwd<IdwtCfg<24, 32>>(g, g_x, g_yh, n, C);
+    else if (C % 16 == 0) emu_bwd<IdwtCfg<16, 32>>(g, g_x, g_yh, n, C);
+    else emu_bwd<IdwtCfg<8, 32>>(g, g_x, g_yh, n, C);
+    return 0;
+}
+}

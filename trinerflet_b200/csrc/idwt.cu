@@ -1,0 +1,138 @@
+// Inverse 2-D DWT level (bior6.8, zero mode) and its exact adjoint -- sm_100a, channels-last.
+//
+// The reference spends ~7 full-size passes per level (2 F.pad, 6 conv_transpose2d, 3 adds, see
+// triplane_encoder.py:391-394 + pytorch_wavelets sfb1d); here one kernel per level reads each
+// coefficient once and writes each plane element once.
+//
+// Layout: x [3][n][n][C], yh [3][3][n][n][C], out [3][2n][2n][C] (C fastest).  A row of pixels is one
+// contiguous run of n*C floats, so "thread <-> one float of the row" is fully coalesced for any C.
+//
+// Kernel structure (forward; the backward kernel mirrors it), per-thread code in idwt_core.cuh:
+//   CTA = one column strip (32 fine columns) x one row chunk x CG channels, NT = 24*CG threads.
+//   phase A  thread <-> input column (pixel column, channel): streams rows top to bottom with 9-deep
+//            register windows per sub-band (static ring indices, no register moves), emits two
+//            H-synthesised rows per input row into a double-buffered shared-memory ring.  Inputs are
+//            staged global->shared one step ahead with cp.async (thread-private slots; src-size 0
+//            zero-fill implements the zero padding of mode='zero').
+//   phase B  thread <-> (mid row, strip of 8 output columns, channel): W-axis synthesis from the mid
+//            rows with a register sliding window; lanes <-> channels => 128-byte coalesced stores.
+//   One __syncthreads per step (3 coarse rows).  ~35 FMA per output element => FMA-pipe / HBM
+//   co-limited ("IDWT roofline").
+#include "common.cuh"
+#include "idwt_core.cuh"
+
+namespace tnl {
+
+template <typename Cfg>
+__global__ void __launch_bounds__(Cfg::NT, (768 / Cfg::NT) > 0 ? (768 / Cfg::NT) : 1)
+k_idwt_fwd(const float* __restrict__ x, const float* __restrict__ yh, float* __restrict__ out, int n, int C,
+           int rows_per_cta) {
+    extern __shared__ __align__(16) float smem[];
+    float* mid0 = smem;
+    float* stage0 = smem + 2 * Cfg::MID_F;
+    const int tid = threadIdx.x;
+    const IdwtGeom g = idwt_geom<Cfg>(tid, IdwtBlock{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z}, n, C, rows_per_cta);
+    FwdState st;
+    fwd_state_init(st);
+    fwd_issue_stage<Cfg>(g, stage0, x, yh, tid, 0);
+    for (int s = 0; s < g.nsteps; s += 3) {
+#define TNL_STEP(PH)                                                                          \
+    if (s + PH < g.nsteps) {                                                                  \
+        const int ss = s + PH;                                                                \
+        fwd_issue_stage<Cfg>(g, stage0 + ((ss + 1) & 1) * Cfg::STAGE, x, yh, tid, ss + 1);    \
+        cp_async_wait<1>();                                                                   \
+        float* mid = mid0 + (ss & 1) * Cfg::MID_F;                                            \
+        fwd_phase_a<Cfg, PH>(st, stage0 + (ss & 1) * Cfg::STAGE, mid, tid);                   \
+        __syncthreads();                                                                      \
+        fwd_phase_b<Cfg>(g, mid, out, tid, ss);                                               \
+    }
+        TNL_STEP(0) TNL_STEP(1) TNL_STEP(2)
+#undef TNL_STEP
+    }
+    cp_async_wait<0>();
+}
+
+template <typename Cfg>
+__global__ void __launch_bounds__(Cfg::NT, (768 / Cfg::NT) > 0 ? (768 / Cfg::NT) : 1)
+k_idwt_bwd(const float* __restrict__ gout, float* __restrict__ g_x, float* __restrict__ g_yh, int n, int C,
+           int rows_per_cta) {
+    extern __shared__ __align__(16) float smem[];
+    float* mid0 = smem;
+    float* stage0 = smem + 2 * Cfg::MID_B;
+    const int tid = threadIdx.x;
+    const IdwtGeom g = idwt_geom<Cfg>(tid, IdwtBlock{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z}, n, C, rows_per_cta);
+    BwdState st;
+    bwd_state_init(st);
+    bwd_issue_stage<Cfg>(g, stage0, gout, tid, 0);
+    for (int s = 0; s < g.nsteps; s += 3) {
+#define TNL_STEP(PH)                                                                          \
+    if (s + PH < g.nsteps) {                                                                  \
+        const int ss = s + PH;                                                                \
+        bwd_issue_stage<Cfg>(g, stage0 + ((ss + 1) & 1) * Cfg::STAGE, gout, tid, ss + 1);     \
+        cp_async_wait<1>();                                                                   \
+        float* mid = mid0 + (ss & 1) * Cfg::MID_B;                                            \
+        bwd_phase_a<Cfg, PH>(st, stage0 + (ss & 1) * Cfg::STAGE, mid, tid);                   \
+        __syncthreads();                                                                      \
+        bwd_phase_b<Cfg>(g, mid, g_x, g_yh, tid, ss);                                         \
+    }
+        TNL_STEP(0) TNL_STEP(1) TNL_STEP(2)
+#undef TNL_STEP
+    }
+    cp_async_wait<0>();
+}
+
+template <typename Cfg>
+static int launch_fwd(const float* x, const float* yh, float* out, uint32_t n, uint32_t C, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_idwt_fwd<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_F);
+        attr_set = true;
+    }
+    unsigned gx, gy, gz, rows;
+    idwt_grid<Cfg>(n, C, kNumSM, gx, gy, gz, rows);
+    k_idwt_fwd<Cfg><<<dim3(gx, gy, gz), Cfg::NT, Cfg::SMEM_F, stream>>>(x, yh, out, (int)n, (int)C, (int)rows);
+    return finish_launch("idwt_level_forward");
+}
+
+template <typename Cfg>
+static int launch_bwd(const float* g, float* g_x, float* g_yh, uint32_t n, uint32_t C, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_idwt_bwd<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_B);
+        attr_set = true;
+    }
+    unsigned gx, gy, gz, rows;
+    idwt_grid<Cfg>(n, C, kNumSM, gx, gy, gz, rows);
+    k_idwt_bwd<Cfg><<<dim3(gx, gy, gz), Cfg::NT, Cfg::SMEM_B, stream>>>(g, g_x, g_yh, (int)n, (int)C, (int)rows);
+    return finish_launch("idwt_level_backward");
+}
+
+}  // namespace tnl
+
+using namespace tnl;
+
+extern "C" {
+
+int tnl_idwt_level_forward(const float* x, const float* yh, float* out, uint32_t n, uint32_t C, tnl_stream_t stream) {
+    TNL_ARG_CHECK(x && yh && out, "null pointer");
+    TNL_ARG_CHECK(n >= 8 && n % 8 == 0 && n <= 16384, "n must be a multiple of 8 in [8, 16384]");
+    TNL_ARG_CHECK(C >= 8 && C % 8 == 0, "C must be a multiple of 8");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (C % 32 == 0) return launch_fwd<IdwtCfg<32, 32>>(x, yh, out, n, C, s);
+    if (C % 24 == 0) return launch_fwd<IdwtCfg<24, 32>>(x, yh, out, n, C, s);
+    if (C % 16 == 0) return launch_fwd<IdwtCfg<16, 32>>(x, yh, out, n, C, s);
+    return launch_fwd<IdwtCfg<8, 32>>(x, yh, out, n, C, s);
+}
+
+int tnl_idwt_level_backward(const float* g_out, float* g_x, float* g_yh, uint32_t n, uint32_t C, tnl_stream_t stream) {
+    TNL_ARG_CHECK(g_out && g_x && g_yh, "null pointer");
+    TNL_ARG_CHECK(n >= 8 && n % 8 == 0 && n <= 16384, "n must be a multiple of 8 in [8, 16384]");
+    TNL_ARG_CHECK(C >= 8 && C % 8 == 0, "C must be a multiple of 8");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (C % 32 == 0) return launch_bwd<IdwtCfg<32, 32>>(g_out, g_x, g_yh, n, C, s);
+    if (C % 24 == 0) return launch_bwd<IdwtCfg<24, 32>>(g_out, g_x, g_yh, n, C, s);
+    if (C % 16 == 0) return launch_bwd<IdwtCfg<16, 32>>(g_out, g_x, g_yh, n, C, s);
+    return launch_bwd<IdwtCfg<8, 32>>(g_out, g_x, g_yh, n, C, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,161 @@
+// Tri-plane bilinear sampling (gather) and its adjoint (scatter) -- sm_100a, channels-last planes.
+//
+// Behavioural contract: TriPlaneVolume.forward -> sample_from_planes_aux
+// (/root/reference/reconstruction/triplaneencoder/triplane_encoder.py:314-332, 523-530):
+//   u = coords / bound ; plane 0 samples (u_x,u_z), plane 1 (u_x,u_y), plane 2 (u_y,u_z) (:250-289);
+//   F.grid_sample(bilinear, padding_mode='border', align_corners=True); concat -> feat[m][p*C + c].
+// Arithmetic follows ATen's grid_sampler_2d (unnormalise ((g+1)/2)*(R-1), clip to [0,R-1], weights
+// nw/ne/sw/se as products of differences, accumulate in that order, out-of-range corners skipped).
+//
+// Why channels-last: with planes [3][R][R][C] a texel's C features are one contiguous 4*C-byte run, so
+// a bilinear tap is 2 x (two adjacent texels) = two contiguous 8*C-byte reads; every 32-byte sector
+// fetched is fully used.  The reference's NCHW layout fetches 2 sectors per (plane, channel) for 16
+// useful bytes.
+//
+// Mapping: one thread per (point, plane, 4-channel group): four 128-bit loads (one per corner),
+// lerp in registers, one 128-bit store into the contiguous feature row.  Backward: one 128-bit
+// load of the feature gradient and four vector atomic adds (red.global.add.v4.f32).
+#include "common.cuh"
+
+namespace tnl {
+
+struct Tap {
+    int x0, y0;       // north-west texel
+    float nw, ne, sw, se;
+    bool x1ok, y1ok;  // south / east neighbours inside the plane
+};
+
+__device__ __forceinline__ float to_pixel(float g, int R) {
+    float v = ((g + 1.0f) * 0.5f) * (float)(R - 1);
+    return fminf((float)(R - 1), fmaxf(v, 0.0f));
+}
+
+__device__ __forceinline__ Tap make_tap(float gx, float gy, int R) {
+    const float ix = to_pixel(gx, R), iy = to_pixel(gy, R);
+    const float fx = floorf(ix), fy = floorf(iy);
+    Tap t;
+    t.x0 = (int)fx;
+    t.y0 = (int)fy;
+    const float ex = fx + 1.0f, ey = fy + 1.0f;  // south-east corner coordinates
+    t.nw = (ex - ix) * (ey - iy);
+    t.ne = (ix - fx) * (ey - iy);
+    t.sw = (ex - ix) * (iy - fy);
+    t.se = (ix - fx) * (iy - fy);
+    t.x1ok = t.x0 + 1 <= R - 1;
+    t.y1ok = t.y0 + 1 <= R - 1;
+    return t;
+}
+
+__device__ __forceinline__ void plane_coords(const float* __restrict__ xyz, uint32_t m, int p, float inv_bound,
+                                             int fp16_coords, float& gx, float& gy) {
+    const int a = (p == 2) ? 1 : 0;
+    const int b = (p == 1) ? 1 : 2;
+    gx = __fmul_rn(__ldg(xyz + 3 * (size_t)m + a), inv_bound);
+    gy = __fmul_rn(__ldg(xyz + 3 * (size_t)m + b), inv_bound);
+    if (fp16_coords) {  // autocast rounds the projected coordinates to fp16 (triplane_encoder.py:299)
+        gx = __half2float(__float2half_rn(gx));
+        gy = __half2float(__float2half_rn(gy));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_sample_fwd(const float* __restrict__ planes, const float* __restrict__ xyz, uint32_t M, int R, int C, float inv_bound,
+             int fp16_coords, const int32_t* __restrict__ n_valid, float* __restrict__ feat) {
+    const int cq_per = C >> 2;
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t total = (uint64_t)M * 3 * cq_per;
+    if (idx >= total) return;
+    const int cq = (int)(idx % cq_per);
+    const int p = (int)((idx / cq_per) % 3);
+    const uint32_t m = (uint32_t)(idx / ((uint64_t)3 * cq_per));
+    float4* dst = reinterpret_cast<float4*>(feat + (size_t)m * 3 * C + (size_t)p * C) + cq;
+    if (n_valid && (int32_t)m >= *n_valid) {
+        *dst = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    float gx, gy;
+    plane_coords(xyz, m, p, inv_bound, fp16_coords, gx, gy);
+    const Tap t = make_tap(gx, gy, R);
+    const float4* base = reinterpret_cast<const float4*>(planes + (((size_t)p * R + t.y0) * R + t.x0) * C) + cq;
+    const size_t dx = (size_t)cq_per, dy = (size_t)R * cq_per;
+    float4 acc;
+    {
+        const float4 v = __ldg(base);
+        acc.x = v.x * t.nw; acc.y = v.y * t.nw; acc.z = v.z * t.nw; acc.w = v.w * t.nw;
+    }
+    if (t.x1ok) {
+        const float4 v = __ldg(base + dx);
+        acc.x = fmaf(v.x, t.ne, acc.x); acc.y = fmaf(v.y, t.ne, acc.y); acc.z = fmaf(v.z, t.ne, acc.z); acc.w = fmaf(v.w, t.ne, acc.w);
+    }
+    if (t.y1ok) {
+        const float4 v = __ldg(base + dy);
+        acc.x = fmaf(v.x, t.sw, acc.x); acc.y = fmaf(v.y, t.sw, acc.y); acc.z = fmaf(v.z, t.sw, acc.z); acc.w = fmaf(v.w, t.sw, acc.w);
+    }
+    if (t.x1ok && t.y1ok) {
+        const float4 v = __ldg(base + dy + dx);
+        acc.x = fmaf(v.x, t.se, acc.x); acc.y = fmaf(v.y, t.se, acc.y); acc.z = fmaf(v.z, t.se, acc.z); acc.w = fmaf(v.w, t.se, acc.w);
+    }
+    *dst = acc;
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v, float w) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(v.x * w), "f"(v.y * w), "f"(v.z * w),
+                 "f"(v.w * w)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+k_sample_bwd(const float* __restrict__ g_feat, const float* __restrict__ xyz, uint32_t M, int R, int C, float inv_bound,
+             int fp16_coords, const int32_t* __restrict__ n_valid, float* __restrict__ g_planes) {
+    const int cq_per = C >> 2;
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t total = (uint64_t)M * 3 * cq_per;
+    if (idx >= total) return;
+    const int cq = (int)(idx % cq_per);
+    const int p = (int)((idx / cq_per) % 3);
+    const uint32_t m = (uint32_t)(idx / ((uint64_t)3 * cq_per));
+    if (n_valid && (int32_t)m >= *n_valid) return;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(g_feat + (size_t)m * 3 * C + (size_t)p * C) + cq);
+    if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) return;  // adding zeros is a no-op
+    float gx, gy;
+    plane_coords(xyz, m, p, inv_bound, fp16_coords, gx, gy);
+    const Tap t = make_tap(gx, gy, R);
+    float* base = g_planes + (((size_t)p * R + t.y0) * R + t.x0) * C + 4 * cq;
+    const size_t dx = (size_t)C, dy = (size_t)R * C;
+    red_add_v4(base, g, t.nw);
+    if (t.x1ok) red_add_v4(base + dx, g, t.ne);
+    if (t.y1ok) red_add_v4(base + dy, g, t.sw);
+    if (t.x1ok && t.y1ok) red_add_v4(base + dy + dx, g, t.se);
+}
+
+}  // namespace tnl
+
+using namespace tnl;
+
+extern "C" {
+
+int tnl_sample_planes_forward(const float* planes, const float* xyz, uint32_t M, uint32_t R, uint32_t C, float inv_bound,
+                              int fp16_coords, const int32_t* n_valid, float* feat, tnl_stream_t stream) {
+    if (M == 0) return 0;
+    TNL_ARG_CHECK(planes && xyz && feat, "null pointer");
+    TNL_ARG_CHECK(C >= 4 && C % 4 == 0 && R >= 2, "C must be a multiple of 4, R >= 2");
+    TNL_ARG_CHECK(((uintptr_t)planes & 15) == 0 && ((uintptr_t)feat & 15) == 0, "planes/feat must be 16-byte aligned");
+    const uint64_t total = (uint64_t)M * 3 * (C / 4);
+    k_sample_fwd<<<(unsigned)ceil_div(total, (uint64_t)256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        planes, xyz, M, (int)R, (int)C, inv_bound, fp16_coords, n_valid, feat);
+    return finish_launch("sample_planes_forward");
+}
+
+int tnl_sample_planes_backward(const float* g_feat, const float* xyz, uint32_t M, uint32_t R, uint32_t C, float inv_bound,
+                               int fp16_coords, const int32_t* n_valid, float* g_planes, tnl_stream_t stream) {
+    if (M == 0) return 0;
+    TNL_ARG_CHECK(g_feat && xyz && g_planes, "null pointer");
+    TNL_ARG_CHECK(C >= 4 && C % 4 == 0 && R >= 2, "C must be a multiple of 4, R >= 2");
+    TNL_ARG_CHECK(((uintptr_t)g_planes & 15) == 0 && ((uintptr_t)g_feat & 15) == 0, "g_planes/g_feat must be 16-byte aligned");
+    const uint64_t total = (uint64_t)M * 3 * (C / 4);
+    k_sample_bwd<<<(unsigned)ceil_div(total, (uint64_t)256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        g_feat, xyz, M, (int)R, (int)C, inv_bound, fp16_coords, n_valid, g_planes);
+    return finish_launch("sample_planes_backward");
+}
+
+}  // extern "C"

@@ -1,0 +1,90 @@
+"""One training step of the reconstruction loop, in the reference's order of operations
+(Trainer.train_one_epoch2, reconstruction/nerf/utils.py:1116-1175 and train_step :532-679):
+
+    encoder.reset_cahce(); encoder.get_planes()                # OUTSIDE autocast => fp32 IDWT, graph kept (:1138-1140)
+    every `update_extra_interval` steps: model.update_extra_state() under autocast                      (:1144-1146)
+    with autocast(fp16): render -> MSE(pred, gt).mean(-1).mean() + wavelet L1 regulariser               (:1158-1160)
+    encoder.reset_cahce(); scaler.scale(loss).backward()                                                (:1161-1166)
+    scaler.step(optimizer); scaler.update()                                                             (:1170-1173)
+
+The Trainer class of the reference (datasets, checkpoints, logging, LR schedule) stays the host's business; this
+module is the thin per-step driver the benchmark and the tests use, plus the ray-sharded multi-GPU variant.
+"""
+from types import SimpleNamespace
+
+import torch
+
+from . import parallel
+
+
+def default_opt(**over):
+    opt = dict(fp16=True, max_steps=1024, dt_gamma=0.0, background_color=0.0, wavelet_regularization=0.2,
+               update_extra_interval=16, lr=1e-2)
+    opt.update(over)
+    return SimpleNamespace(**opt)
+
+
+def wavelet_regulariser(encoder, lam):
+    """nerf/utils.py:640-655 (unweighted branch): lam * sum_l mean|yh_l| * numel_l/numel_all / n_levels."""
+    feats = encoder.get_wavelet_features()
+    if lam <= 0 or len(feats) == 0:
+        return None
+    total = sum(v.numel() for v in feats)
+    reg = sum(v.abs().mean() * (v.numel() / total) for v in feats) / len(feats)
+    return lam * reg
+
+
+class TrainStep:
+    def __init__(self, model, opt=None, optimizer=None, world_size=1):
+        self.model = model
+        self.opt = opt or default_opt()
+        self.optimizer = optimizer
+        self.scaler = torch.amp.GradScaler("cuda", enabled=self.opt.fp16)
+        self.global_step = 0
+        self.world_size = world_size
+        self.criterion = torch.nn.MSELoss(reduction='none')
+
+    def forward_backward(self, rays_o, rays_d, images, update_grid=None):
+        """rays_o/rays_d/images: [N,3] device tensors (this rank's shard). Returns the detached loss tensor."""
+        model, opt = self.model, self.opt
+        enc = model.encoder
+        model.train()
+        enc.reset_cahce()
+        enc.get_planes()
+        do_update = (self.global_step % opt.update_extra_interval == 0) if update_grid is None else update_grid
+        if do_update:
+            with torch.autocast("cuda", dtype=torch.float16, enabled=opt.fp16):
+                model.update_extra_state()
+        with torch.autocast("cuda", dtype=torch.float16, enabled=opt.fp16):
+            bg = torch.zeros_like(images) + opt.background_color
+            out = model.render(rays_o.unsqueeze(0), rays_d.unsqueeze(0), staged=False, bg_color=bg, perturb=True,
+                               force_all_rays=False, dt_gamma=opt.dt_gamma, max_steps=opt.max_steps)
+            pred = out['image'].view(-1, 3)
+            loss = self.criterion(pred, images).mean(-1).mean()
+            reg = wavelet_regulariser(enc, opt.wavelet_regularization)
+            if reg is not None:
+                loss = loss + reg
+            enc.reset_cahce()
+            self.scaler.scale(loss).backward()
+        if self.world_size > 1:
+            parallel.allreduce_gradients(model, self.world_size)
+        self.global_step += 1
+        return loss.detach()
+
+    def optimizer_step(self):
+        if self.optimizer is None:
+            return
+        self.scaler.step(self.optimizer)
+        self.scaler.update()
+        self.optimizer.zero_grad(set_to_none=True)
+
+    def step(self, rays_o, rays_d, images, update_grid=None):
+        self.optimizer.zero_grad(set_to_none=True) if self.optimizer is not None else self.model.zero_grad(set_to_none=True)
+        loss = self.forward_backward(rays_o, rays_d, images, update_grid)
+        self.optimizer_step()
+        return loss
+
+
+def make_optimizer(model, lr=1e-2):
+    """main_nerf.py:119: Adam(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15)."""
+    return torch.optim.Adam(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15)

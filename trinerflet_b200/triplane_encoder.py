@@ -1,0 +1,313 @@
+"""TriPlaneVolume -- drop-in for reconstruction/triplaneencoder/triplane_encoder.py:26-530 on the path every
+README command uses (wavelet-parameterised planes, bior6.8, all levels learnable, no rotation / dropout /
+auto-scale / upscale).  Same constructor kwargs, attributes, method names and state-dict keys:
+
+    planes_features                    logical [3, C, n0, n0]
+    planes_features_wavelet_coefs.{l}  logical [3, C, 3, n0*2^l, n0*2^l]
+    plane_axes [3,3,2], plane_normals [3,3,1] (buffers)
+
+B200-first differences (DESIGN.md "data layout"):
+  * parameters, gradients and planes keep the reference's logical shapes but are STORED channels-last
+    (C fastest: strides of a `[3,n,n,C]` / `[3,3,n,n,C]` tensor permuted back), so that one texel's C features are
+    one contiguous run for the sampling gather/scatter and pixel rows are contiguous for the IDWT kernels;
+    `load_state_dict` / `state_dict` / optimizers are stride-agnostic, so reference checkpoints load unchanged;
+  * `build_planes` is one fused CUDA kernel per level (tnl_idwt_level_forward) instead of 2 pads +
+    6 conv_transpose2d + 3 adds per level; its backward is the exact adjoint kernel;
+  * `sample_from_planes` is one gather kernel (tnl_sample_planes_forward); backward one scatter kernel.
+There is no CPU path: tensors must be CUDA tensors.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from ._lib import call, ptr, stream
+
+PAD_DICT = {'bior6.8': 4}  # triplane_encoder.py:174-180; only bior6.8 is used by the reference's configs
+
+
+def get_levels(upscale_factor):
+    """reconstruction/triplaneencoder/utils.py:274-279."""
+    wavelet_levels = math.log2(upscale_factor)
+    if abs(wavelet_levels - round(wavelet_levels)) > 1e-5:
+        raise ValueError('Unsupported res. should be 2^')
+    return round(wavelet_levels)
+
+
+# ----------------------------------------------------------------------------------------------
+# channels-last helpers
+# ----------------------------------------------------------------------------------------------
+def cl_empty_planes(C, n, device=None, dtype=torch.float32, zero=False):
+    """Logical [3, C, n, n] tensor stored as [3][n][n][C]."""
+    f = torch.zeros if zero else torch.empty
+    return f(3, n, n, C, device=device, dtype=dtype).permute(0, 3, 1, 2)
+
+
+def cl_empty_coefs(C, n, device=None, dtype=torch.float32, zero=False):
+    """Logical [3, C, 3, n, n] tensor stored as [3][3][n][n][C]."""
+    f = torch.zeros if zero else torch.empty
+    return f(3, 3, n, n, C, device=device, dtype=dtype).permute(0, 4, 1, 2, 3)
+
+
+def is_cl_planes(t):
+    return t.dim() == 4 and t.permute(0, 2, 3, 1).is_contiguous()
+
+
+def is_cl_coefs(t):
+    return t.dim() == 5 and t.permute(0, 2, 3, 4, 1).is_contiguous()
+
+
+def to_cl_planes(t):
+    if is_cl_planes(t):
+        return t
+    out = cl_empty_planes(t.shape[1], t.shape[2], device=t.device, dtype=t.dtype)
+    out.copy_(t)
+    return out
+
+
+def to_cl_coefs(t):
+    if is_cl_coefs(t):
+        return t
+    out = cl_empty_coefs(t.shape[1], t.shape[3], device=t.device, dtype=t.dtype)
+    out.copy_(t)
+    return out
+
+
+def _require_cuda_f32(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f"trinerflet_b200: {what} must be a CUDA tensor (no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"trinerflet_b200: {what} must be float32")
+
+
+# ----------------------------------------------------------------------------------------------
+# multilevel inverse DWT  (build_planes, triplane_encoder.py:364-405)
+# ----------------------------------------------------------------------------------------------
+class _BuildPlanes(Function):
+    """planes = IDWT_L(...IDWT_1(2*x0, yh_0)..., yh_{L-1}) with zero padding 4 per level.  Linear in all inputs,
+    so backward needs no saved activations: it is the chain of adjoint level kernels."""
+
+    @staticmethod
+    def forward(ctx, planes_features, *coefs):
+        _require_cuda_f32(planes_features, "planes_features")
+        x = to_cl_planes(planes_features.detach())
+        C, n = x.shape[1], x.shape[2]
+        ctx.n0, ctx.C, ctx.levels = n, C, len(coefs)
+        for yh in coefs:
+            _require_cuda_f32(yh, "wavelet coefficients")
+            if yh.shape != (3, C, 3, n, n):
+                raise RuntimeError(f"wavelet level has shape {tuple(yh.shape)}, expected {(3, C, 3, n, n)}")
+            yh = to_cl_coefs(yh.detach())
+            out = cl_empty_planes(C, 2 * n, device=x.device)
+            call("tnl_idwt_level_forward", ptr(x), ptr(yh), ptr(out), n, C, stream())
+            x, n = out, 2 * n
+        return x
+
+    @staticmethod
+    def backward(ctx, g):
+        g = to_cl_planes(g)
+        C = ctx.C
+        n = ctx.n0 * (2 ** ctx.levels)
+        grads = []
+        for _ in range(ctx.levels):
+            n //= 2
+            g_x = cl_empty_planes(C, n, device=g.device)
+            g_yh = cl_empty_coefs(C, n, device=g.device)
+            call("tnl_idwt_level_backward", ptr(g), ptr(g_x), ptr(g_yh), n, C, stream())
+            grads.append(g_yh)
+            g = g_x
+        return (g, *reversed(grads))
+
+
+def build_planes(planes_features, coefs):
+    return _BuildPlanes.apply(planes_features, *coefs)
+
+
+# ----------------------------------------------------------------------------------------------
+# tri-plane bilinear sampling (sample_from_planes_aux, triplane_encoder.py:314-332)
+# ----------------------------------------------------------------------------------------------
+def _inv_bound(bound):
+    # CUDA evaluates `tensor / python_scalar` as tensor * fp32(1/scalar)
+    return float(np.float32(1.0) / np.float32(bound))
+
+
+class _SamplePlanes(Function):
+    @staticmethod
+    def forward(ctx, planes, coords, bound, fp16_coords, n_valid):
+        _require_cuda_f32(planes, "planes")
+        planes_cl = to_cl_planes(planes.detach())
+        coords = coords.detach().contiguous().float()
+        M = coords.shape[0]
+        C, R = planes.shape[1], planes.shape[2]
+        feat = torch.empty(M, 3 * C, device=planes.device, dtype=torch.float32)
+        inv = _inv_bound(bound)
+        call("tnl_sample_planes_forward", ptr(planes_cl), ptr(coords), M, R, C, inv, int(bool(fp16_coords)),
+             ptr(n_valid), ptr(feat), stream())
+        ctx.save_for_backward(coords, n_valid if n_valid is not None else torch.empty(0))
+        ctx.meta = (M, R, C, inv, int(bool(fp16_coords)), n_valid is not None)
+        return feat
+
+    @staticmethod
+    def backward(ctx, g_feat):
+        coords, n_valid = ctx.saved_tensors
+        M, R, C, inv, fp16_coords, has_nv = ctx.meta
+        g_feat = g_feat.contiguous().float()
+        g_planes = cl_empty_planes(C, R, device=g_feat.device, zero=True)
+        call("tnl_sample_planes_backward", ptr(g_feat), ptr(coords), M, R, C, inv, fp16_coords,
+             ptr(n_valid) if has_nv else None, ptr(g_planes), stream())
+        return g_planes, None, None, None, None
+
+
+def sample_planes(planes, coords, bound, fp16_coords=None, n_valid=None):
+    """planes logical [3,C,R,R] -> features [M, 3C] (fp32). fp16_coords=None follows the autocast state, as the
+    reference's projection matmul does."""
+    if fp16_coords is None:
+        fp16_coords = torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.float16
+    return _SamplePlanes.apply(planes, coords, float(bound), bool(fp16_coords), n_valid)
+
+
+# ----------------------------------------------------------------------------------------------
+# module
+# ----------------------------------------------------------------------------------------------
+class TriPlaneVolume(nn.Module):
+    def __init__(self, number_of_features=3, plane_resolution=224, init_sigma=0.1, lbound=1,
+                 viewdir_plane_resolution=32, two_planes_per_axis=False, planes_features=None, viewdir_plane=None,
+                 apply_activation_on_features=False, inner_multi_res_scale=1, inner_multi_res_viewdir_scale=1,
+                 viewdir_mode='plane', inner_multi_res_scale_current=1, learn_rotation_axis=False, dropout=0,
+                 wavelet_type='bior6.8', lbound_auto_scale=False, upscale_ratio_bound=-1, upscale_levels=2,
+                 wavelet_base_resolution=0):
+        super().__init__()
+        unsupported = []
+        if two_planes_per_axis: unsupported.append("two_planes_per_axis")
+        if apply_activation_on_features: unsupported.append("apply_activation_on_features")
+        if learn_rotation_axis: unsupported.append("learn_rotation_axis")
+        if 0 < dropout < 1: unsupported.append("dropout")
+        if lbound_auto_scale: unsupported.append("lbound_auto_scale")
+        if 0 < upscale_ratio_bound < 1: unsupported.append("upscale_ratio_bound")
+        if wavelet_base_resolution not in (0,): unsupported.append("wavelet_base_resolution")
+        if inner_multi_res_scale_current != 1: unsupported.append("inner_multi_res_scale_current != 1")
+        if inner_multi_res_scale > 1 and wavelet_type not in PAD_DICT: unsupported.append(f"wavelet_type={wavelet_type}")
+        if unsupported:
+            raise NotImplementedError("trinerflet_b200.TriPlaneVolume: options outside the hot path (no reference config "
+                                      f"uses them, SURVEY.md 8a-2): {unsupported}")
+        self.number_of_features = number_of_features
+        self.plane_resolution = plane_resolution
+        self.init_sigma = init_sigma
+        self.lbound = lbound
+        self.lbound_viewdir = 1
+        self.output_dim = 3 * number_of_features
+        self.viewdir_plane_resolution = viewdir_plane_resolution
+        self.two_planes_per_axis = False
+        self.apply_activation_on_features = False
+        self.wavelet_type = wavelet_type
+        self.inner_wavelet_scale = inner_multi_res_scale
+        self.inner_wavelet_viewdir_scale = inner_multi_res_viewdir_scale
+        self.inner_multi_res_scale_current = inner_multi_res_scale_current
+        self.wavelet_base_resolution = wavelet_base_resolution
+        self.learn_rotation_axis = False
+        self.rotation_matrix = None
+        self.dropout = None
+        self.lbound_auto_scale = False
+        self.lbound_scale = None
+        self.upscale_ratio_bound = upscale_ratio_bound
+        self.upscale_levels = upscale_levels
+        self.upscale_enabled = False
+        self.plane_direction = ['up', 'front', 'right']
+
+        # plane bases, triplane_encoder.py:250-289 : up=(x,z), front=(x,y), right=(y,z)
+        eye = torch.eye(3)
+        axes = torch.stack([torch.cat([eye[:, 0:1], eye[:, 2:3]], dim=1),
+                            torch.cat([eye[:, 0:1], eye[:, 1:2]], dim=1),
+                            torch.cat([eye[:, 1:2], eye[:, 2:3]], dim=1)], dim=0)
+        normals = torch.stack([eye[:, 1:2], eye[:, 2:3], eye[:, 0:1]], dim=0)
+        self.register_buffer('plane_axes', axes.clone())
+        self.register_buffer('plane_normals', normals.clone())
+
+        self.last_used_planes = None
+        self._init_plane_features(planes_features)
+
+    # -- parameters (triplane_encoder.py:155-231) --------------------------------------------------
+    def _init_plane_features(self, planes_features):
+        C, R = self.number_of_features, self.plane_resolution
+        if self.inner_wavelet_scale <= 1:
+            levels, n0 = 0, R
+        else:
+            levels = get_levels(self.inner_wavelet_scale)
+            if R % (2 ** levels) != 0:
+                raise ValueError("plane_resolution must be divisible by the wavelet upscale factor")
+            n0 = R // (2 ** levels)
+        self.planes_features_wavelet_all_level = levels
+        self.planes_features_wavelet_current_level = 0
+        self.planes_features_wavelet_pad = PAD_DICT.get(self.wavelet_type, 0)
+        self.planes_features_wavelet_yh_shapes = [torch.Size([3, C, 3, n0 * 2 ** l, n0 * 2 ** l]) for l in range(levels)]
+        if planes_features is None:
+            planes_features = self.init_sigma * torch.randn(3, C, n0, n0)  # same RNG call as the reference (:212 / :162)
+        base = cl_empty_planes(C, n0)
+        base.copy_(planes_features.detach())
+        self.planes_features = nn.Parameter(base)
+        coefs = []
+        for l in range(levels):
+            coefs.append(nn.Parameter(cl_empty_coefs(C, n0 * 2 ** l, zero=True)))  # zero-init, :220
+        self.planes_features_wavelet_coefs = nn.ParameterList(coefs)
+
+    def _apply(self, fn, *args, **kwargs):
+        # nn.Module._apply (e.g. .to(device)) preserves strides for dense non-overlapping tensors; nothing to do,
+        # but drop the plane cache because it lives on the old device.
+        self.last_used_planes = None
+        return super()._apply(fn, *args, **kwargs)
+
+    # -- reference API -----------------------------------------------------------------------------
+    def get_wavelet_features(self):
+        return list(self.planes_features_wavelet_coefs) if self.inner_wavelet_scale > 1 else []
+
+    def get_wavelet_features_upscaled(self):
+        return []
+
+    def get_lbound_scale(self):
+        return None
+
+    def get_params(self, opt_cfg):
+        return self.parameters()
+
+    def get_params2(self, lr):
+        return [{'params': [], 'lr': 10 * lr}, {'params': list(self.parameters()), 'lr': lr}]
+
+    def reset_cahce(self):  # (sic) -- reference spelling, nerf/utils.py:1139,1162
+        self.last_used_planes = None
+
+    reset_cache = reset_cahce
+
+    def build_planes(self, planes_features=None, coefs=None):
+        planes_features = self.planes_features if planes_features is None else planes_features
+        coefs = list(self.planes_features_wavelet_coefs) if coefs is None else coefs
+        if self.inner_wavelet_scale <= 1 or len(coefs) == 0:
+            return planes_features
+        return build_planes(planes_features, coefs)
+
+    def get_planes(self, max_res=-1, max_scale=-1, get_all_resolutions=False):
+        if max_res > 0 or max_scale > 0 or get_all_resolutions:
+            raise NotImplementedError("partial-resolution plane queries are not on the training/render hot path")
+        if self.last_used_planes is not None:
+            return self.last_used_planes
+        planes = self.build_planes()
+        self.last_used_planes = planes
+        return planes
+
+    def sample_from_planes(self, coordinates, plane_features=None, lbound=None, n_valid=None):
+        if plane_features is None:
+            plane_features = self.get_planes()
+        if lbound is None:
+            lbound = self.lbound
+        feat = sample_planes(plane_features, coordinates, lbound, n_valid=n_valid)
+        return feat.view(feat.shape[0], 3, self.number_of_features)
+
+    def forward(self, coordinates, bound, n_valid=None):
+        """coordinates [M,3] in [-bound, bound] -> features [M, 3C] (index p*C + c), fp32."""
+        return sample_planes(self.get_planes(), coordinates, bound, n_valid=n_valid)
+
+    # -- checkpoints: accept reference (NCHW-contiguous) tensors, keep channels-last storage -------------
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)  # Tensor.copy_ keeps our strides
+        self.last_used_planes = None
