@@ -34,7 +34,7 @@ def test_render_train_matches_oracle_pipeline():
     with torch.autocast("cuda", dtype=torch.float16):
         out = net.render(ro.cuda().unsqueeze(0), rd.cuda().unsqueeze(0), staged=False, bg_color=0, perturb=True,
                          force_all_rays=True, dt_gamma=0, max_steps=1024)
-    img = out["image"].view(-1, 3).float().cpu()
+    img = out["image"].detach().view(-1, 3).float().cpu()
     # oracle pipeline with the same noises (same torch CUDA RNG stream: one torch.rand(N) call)
     torch.manual_seed(11)
     noises = torch.rand(3000, device="cuda").cpu().numpy()
@@ -51,10 +51,10 @@ def test_render_train_matches_oracle_pipeline():
     planes = ow.build_planes(pf, coefs)
     s_o, rgb_o = of.field_forward(planes, torch.from_numpy(xyzs), torch.from_numpy(dirs), W, 1.5, fp16=True)
     ws_o, dp_o, im_o = orc.composite_rays_train_forward(s_o.numpy(), rgb_o.numpy(), deltas, rays, 1e-4)
-    assert np.abs(out["weights_sum"].float().cpu().numpy() - ws_o).max() <= 5e-3   # fp16 field tolerance (2e-3) x samples
+    assert np.abs(out["weights_sum"].detach().float().cpu().numpy() - ws_o).max() <= 5e-3   # fp16 field tolerance (2e-3) x samples
     assert np.abs(img.numpy() - im_o).max() <= 5e-3
-    m = np.isfinite(dp_o)
-    assert np.abs(out["depth"].view(-1).float().cpu().numpy()[m] - np.clip(dp_o - nears, 0, None)[m] / (fars - nears)[m]).max() <= 5e-3
+    m = fars > nears   # rays that miss the box have near = far = FLT_MAX -> 0/0 = NaN in the reference too (App. A-11)
+    assert np.abs(out["depth"].detach().view(-1).float().cpu().numpy()[m] - np.clip(dp_o - nears, 0, None)[m] / (fars - nears)[m]).max() <= 5e-3
 
 
 def test_train_steps_reduce_loss():

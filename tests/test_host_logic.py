@@ -1,0 +1,105 @@
+"""CPU: host-side logic -- channels-last parameter storage with reference-compatible logical shapes / state-dict keys,
+loading a reference-layout checkpoint, shard arithmetic, synthetic scene determinism, and the ray-sharded gradient
+all-reduce on world_size = 2 (gloo)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from trinerflet_b200 import parallel, scene
+from trinerflet_b200.network import NeRFNetwork
+from trinerflet_b200.triplane_encoder import TriPlaneVolume, is_cl_coefs, is_cl_planes
+
+
+def _net(C=16, R=128, S=4):
+    return NeRFNetwork(bound=1.5, cuda_ray=True, density_thresh=10, triplane_channels=C, triplane_resolution=R,
+                       triplane_wavelet_levels=S)
+
+
+def test_state_dict_contract(golden_dir):
+    net = _net()
+    ref_keys = set(str(k) for k in np.load(os.path.join(golden_dir, "field_fp32.npz"))["state_dict_keys"])
+    keys = set(net.state_dict().keys())
+    assert ref_keys <= keys and keys - ref_keys == {"density_grid", "density_bitfield", "step_counter"}  # cuda_ray buffers
+    enc = net.encoder
+    assert enc.planes_features.shape == (3, 16, 32, 32) and is_cl_planes(enc.planes_features)
+    assert [tuple(p.shape) for p in enc.planes_features_wavelet_coefs] == [(3, 16, 3, 32, 32), (3, 16, 3, 64, 64)]
+    assert all(is_cl_coefs(p) for p in enc.planes_features_wavelet_coefs)
+    assert all(float(p.abs().sum()) == 0 for p in enc.planes_features_wavelet_coefs)   # zero-init (:220)
+    assert net.cascade == 2 and net.density_grid.shape == (2, 128 ** 3) and net.density_bitfield.shape == (2 * 128 ** 3 // 8,)
+    assert enc.output_dim == 48 and net.in_dim == 48 and net.sigma_net[0].weight.shape == (64, 48)
+    assert net.color_net[0].weight.shape == (64, 31) and net.color_net[2].weight.shape == (3, 64)
+    assert torch.equal(enc.plane_axes[0], torch.tensor([[1., 0.], [0., 0.], [0., 1.]]))     # 'up' plane = (x, z)
+
+
+def test_load_reference_layout_checkpoint_keeps_channels_last():
+    net = _net()
+    sd = {k: v.clone().contiguous() for k, v in net.state_dict().items()}      # reference layout: NCHW-contiguous
+    g = torch.Generator().manual_seed(0)
+    sd["encoder.planes_features"] = torch.randn(3, 16, 32, 32, generator=g)
+    sd["encoder.planes_features_wavelet_coefs.1"] = torch.randn(3, 16, 3, 64, 64, generator=g)
+    sd.pop("encoder.planes_features_wavelet_coefs.0")                           # a finer level missing => stays zero (strict=False)
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert missing == ["encoder.planes_features_wavelet_coefs.0"] and not unexpected
+    assert torch.equal(net.encoder.planes_features.detach(), sd["encoder.planes_features"])
+    assert is_cl_planes(net.encoder.planes_features) and is_cl_coefs(net.encoder.planes_features_wavelet_coefs[1])
+    opt = torch.optim.Adam(net.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15)
+    for p in net.parameters():
+        p.grad = torch.ones_like(p)
+    opt.step()
+    assert is_cl_coefs(net.encoder.planes_features_wavelet_coefs[1])            # optimizer keeps the strides
+    assert len(net.get_params(1e-2)) == 4
+
+
+def test_unsupported_options_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        TriPlaneVolume(number_of_features=16, plane_resolution=128, inner_multi_res_scale=4, learn_rotation_axis=True)
+    with pytest.raises(NotImplementedError):
+        NeRFNetwork(bound=1.5, cuda_ray=True, bg_radius=2.0, triplane_channels=16, triplane_resolution=128, triplane_wavelet_levels=4)
+    with pytest.raises(ValueError):
+        TriPlaneVolume(number_of_features=16, plane_resolution=128, inner_multi_res_scale=6)
+
+
+def test_shards_and_scene():
+    for n, w in [(60000, 8), (10, 3), (640000, 7), (5, 8)]:
+        r = [parallel.shard_range(n, i, w) for i in range(w)]
+        assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        assert max(h - l for l, h in r) - min(h - l for l, h in r) <= 1
+    s1, s2 = scene.make_scene(), scene.make_scene()
+    assert torch.equal(s1.poses, s2.poses) and abs(s1.intrinsics[0] - 1111.11) < 0.01
+    assert torch.allclose(s1.poses[:, :3, 3].norm(dim=-1), torch.full((100,), scene.RADIUS), atol=1e-4)
+    ro, rd, tgt = scene.sample_batch(s1, 1000, torch.Generator().manual_seed(0))
+    assert torch.allclose(rd.norm(dim=-1), torch.ones(1000), atol=1e-5)
+    assert float(((ro + 4 * rd).norm(dim=-1) < 1.6).float().mean()) > 0.5     # cameras look at the scene centre
+    grid = scene.ball_density_grid(1.5, 0.75)
+    occ = (grid > 0).float().mean(dim=1)
+    assert abs(occ[0] - 4 / 3 * np.pi * 0.75 ** 3 / 8) < 0.01 and abs(occ[1] - 4 / 3 * np.pi * 0.75 ** 3 / 27) < 0.01
+    assert scene.packbits_cpu(grid, 0.5).shape == (2 * 128 ** 3 // 8,)
+
+
+def _ddp_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = _net(C=16, R=64, S=2)
+    for i, p in enumerate(net.parameters()):
+        p.grad = torch.full_like(p, float(rank + 1)) * (i + 1)
+    parallel.allreduce_gradients(net, world)
+    ok = all(torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1))) for i, p in enumerate(net.parameters()))
+    local = torch.arange(*parallel.shard_range(11, rank, world)).float().unsqueeze(-1)
+    full = parallel.gather_frame(local, 11, rank, world)
+    ok = ok and torch.equal(full.squeeze(-1), torch.arange(11).float())
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_and_gather_world2():
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_ddp_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] and out[1]

@@ -95,5 +95,39 @@ def check(rc, what):
         raise RuntimeError(f"trinerflet_b200.{what} failed (rc={rc}): {msg}")
 
 
+# number of kernels each ABI call launches (for the launch counter the benchmark reports)
+KERNELS_PER_CALL = {"tnl_march_rays_train": 5, "tnl_compact_alive": 3}
+launch_count = 0
+_profile = None  # when enabled: name -> list of (start_event, end_event, scalar_args)
+
+
+def profile_start():
+    """Record a CUDA-event pair around every ABI call on the current stream (bench.py roofline measurement)."""
+    global _profile
+    _profile = {}
+
+
+def profile_stop():
+    """-> {name: [(milliseconds, scalar_args), ...]}; synchronises the device."""
+    global _profile
+    rec, _profile = _profile, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, evs in (rec or {}).items():
+        out[name] = [(e0.elapsed_time(e1), meta) for e0, e1, meta in evs]
+    return out
+
+
 def call(name, *args):
-    check(getattr(load(), name)(*args), name)
+    global launch_count
+    fn = getattr(load(), name)
+    launch_count += KERNELS_PER_CALL.get(name, 1)
+    if _profile is None:
+        check(fn(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = fn(*args)
+    e1.record()
+    _profile.setdefault(name, []).append((e0, e1, tuple(a for a in args if isinstance(a, (int, float)))))
+    check(rc, name)
