@@ -100,12 +100,16 @@ int tnl_sh_encode_forward(const float* inputs, float* outputs, uint32_t B, uint3
  * it (triplane_encoder.py:379-394):  out = IDWT(pad4(2*x), pad4(yh)),  n -> 2n.
  * x [3][n][n][C], yh [3][3][n][n][C] (yh[.,0]=high-pass along H, [.,1]=along W, [.,2]=both),
  * out [3][2n][2n][C].  C % 8 == 0, n % 8 == 0. */
-int tnl_idwt_level_forward(const float* x, const float* yh, float* out, uint32_t n, uint32_t C,
+/* abs_sum (device float*, may be NULL): += sum |yh| over the level -- the forward value of the wavelet L1
+ * regulariser (reconstruction/nerf/utils.py:640-655) as a by-product of the pass that reads yh anyway. */
+int tnl_idwt_level_forward(const float* x, const float* yh, float* out, uint32_t n, uint32_t C, float* abs_sum,
                            tnl_stream_t stream);
 /* Exact adjoint of the above: g_out [3][2n][2n][C] -> g_x [3][n][n][C], g_yh [3][3][n][n][C]
- * (what SFB2D.backward + pad backward + the 2*x factor produce in the reference's autograd graph). */
-int tnl_idwt_level_backward(const float* g_out, float* g_x, float* g_yh, uint32_t n, uint32_t C,
-                            tnl_stream_t stream);
+ * (what SFB2D.backward + pad backward + the 2*x factor produce in the reference's autograd graph).
+ * Optional fused regulariser gradient: if yh and reg_grad (device float*) are non-NULL,
+ * g_yh += reg_coef * (*reg_grad) * sign(yh)   (d/dyh of  sum|yh|, scaled by its upstream gradient). */
+int tnl_idwt_level_backward(const float* g_out, float* g_x, float* g_yh, uint32_t n, uint32_t C, const float* yh,
+                            const float* reg_grad, float reg_coef, tnl_stream_t stream);
 
 /* Bilinear tri-plane sampling: replaces F.grid_sample(bilinear, border, align_corners=True) +
  * permute/concat of TriPlaneVolume.forward (triplane_encoder.py:314-332, 523-530).

@@ -1,0 +1,27 @@
+"""Runs a few base-light training steps (no CPU baseline, no timing) -- the target command for ncu captures:
+   ncu --set full --clock-control none --import-source on -k regex:<kernel> -s <skip> -c 1 -o gpurun_out/<name> python profiles/prof_step.py
+"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from trinerflet_b200 import scene, trainer
+from trinerflet_b200.network import NeRFNetwork
+
+cfg = scene.CONFIGS[os.environ.get("TNL_CONFIG", "base_light")]
+steps = int(os.environ.get("TNL_STEPS", "2"))
+net = NeRFNetwork(bound=1.5, cuda_ray=True, density_thresh=10, min_near=0.2, triplane_channels=cfg["C"],
+                  triplane_resolution=cfg["R"], triplane_wavelet_levels=cfg["S"], hidden_dim=cfg["hidden"],
+                  hidden_dim_color=cfg["hidden"]).cuda()
+scene.init_model_(net, 0)
+scene.install_ball_occupancy(net, 0.75)
+ts = trainer.TrainStep(net, trainer.default_opt(), None)
+sc = scene.make_scene()
+g = torch.Generator().manual_seed(0)
+batches = [tuple(t.cuda() for t in scene.sample_batch(sc, cfg["rays"], g)) for _ in range(steps + 1)]
+ts.forward_backward(*batches[0], update_grid=False)
+net.mean_count = int(net.step_counter[0, 0].item()); net.local_step = 0
+for i in range(steps):
+    net.zero_grad(set_to_none=True)
+    ts.forward_backward(*batches[i + 1], update_grid=False)
+torch.cuda.synchronize()
+print("done", net.mean_count)

@@ -10,7 +10,7 @@
 using namespace tnl;
 
 template <typename Cfg>
-static void emu_fwd(const float* x, const float* yh, float* out, unsigned n, unsigned C) {
+static void emu_fwd(const float* x, const float* yh, float* out, unsigned n, unsigned C, float* abs_sum) {
     unsigned gx, gy, gz, rows;
     idwt_grid<Cfg>(n, C, 148, gx, gy, gz, rows);
     std::vector<float> smem(2 * Cfg::MID_F + 2 * Cfg::STAGE);
@@ -31,18 +31,19 @@ static void emu_fwd(const float* x, const float* yh, float* out, unsigned n, uns
             for (int t = 0; t < Cfg::NT; ++t) {
                 fwd_issue_stage<Cfg>(geo[t], stage0 + ((ss + 1) & 1) * Cfg::STAGE, x, yh, t, ss + 1);
                 switch (ss % 3) {
-                    case 0: fwd_phase_a<Cfg, 0>(st[t], stage, mid, t); break;
-                    case 1: fwd_phase_a<Cfg, 1>(st[t], stage, mid, t); break;
-                    default: fwd_phase_a<Cfg, 2>(st[t], stage, mid, t); break;
+                    case 0: fwd_phase_a<Cfg, 0>(geo[t], st[t], stage, mid, t, ss); break;
+                    case 1: fwd_phase_a<Cfg, 1>(geo[t], st[t], stage, mid, t, ss); break;
+                    default: fwd_phase_a<Cfg, 2>(geo[t], st[t], stage, mid, t, ss); break;
                 }
             }
             for (int t = 0; t < Cfg::NT; ++t) fwd_phase_b<Cfg>(geo[t], mid, out, t, ss);
         }
+        if (abs_sum) for (int t = 0; t < Cfg::NT; ++t) *abs_sum += st[t].abs_acc;
     }
 }
 
 template <typename Cfg>
-static void emu_bwd(const float* g, float* g_x, float* g_yh, unsigned n, unsigned C) {
+static void emu_bwd(const float* g, float* g_x, float* g_yh, unsigned n, unsigned C, const float* yh, float reg) {
     unsigned gx, gy, gz, rows;
     idwt_grid<Cfg>(n, C, 148, gx, gy, gz, rows);
     std::vector<float> smem(2 * Cfg::MID_B + 2 * Cfg::STAGE);
@@ -68,24 +69,24 @@ static void emu_bwd(const float* g, float* g_x, float* g_yh, unsigned n, unsigne
                     default: bwd_phase_a<Cfg, 2>(st[t], stage, mid, t); break;
                 }
             }
-            for (int t = 0; t < Cfg::NT; ++t) bwd_phase_b<Cfg>(geo[t], mid, g_x, g_yh, t, ss);
+            for (int t = 0; t < Cfg::NT; ++t) bwd_phase_b<Cfg>(geo[t], mid, g_x, g_yh, t, ss, yh, reg);
         }
     }
 }
 
 extern "C" {
-int emu_idwt_level_forward(const float* x, const float* yh, float* out, uint32_t n, uint32_t C) {
-    if (C % 32 == 0) emu_fwd<IdwtCfg<32, 32>>(x, yh, out, n, C);
-    else if (C % 24 == 0) emu_fwd<IdwtCfg<24, 32>>(x, yh, out, n, C);
-    else if (C % 16 == 0) emu_fwd<IdwtCfg<16, 32>>(x, yh, out, n, C);
-    else emu_fwd<IdwtCfg<8, 32>>(x, yh, out, n, C);
+int emu_idwt_level_forward(const float* x, const float* yh, float* out, uint32_t n, uint32_t C, float* abs_sum) {
+    if (C % 32 == 0) emu_fwd<IdwtCfg<32, 32>>(x, yh, out, n, C, abs_sum);
+    else if (C % 24 == 0) emu_fwd<IdwtCfg<24, 32>>(x, yh, out, n, C, abs_sum);
+    else if (C % 16 == 0) emu_fwd<IdwtCfg<16, 32>>(x, yh, out, n, C, abs_sum);
+    else emu_fwd<IdwtCfg<8, 32>>(x, yh, out, n, C, abs_sum);
     return 0;
 }
-int emu_idwt_level_backward(const float* g, float* g_x, float* g_yh, uint32_t n, uint32_t C) {
-    if (C % 32 == 0) emu_bwd<IdwtCfg<32, 32>>(g, g_x, g_yh, n, C);
-    else if (C % 24 == 0) emu_bwd<IdwtCfg<24, 32>>(g, g_x, g_yh, n, C);
-    else if (C % 16 == 0) emu_bwd<IdwtCfg<16, 32>>(g, g_x, g_yh, n, C);
-    else emu_bwd<IdwtCfg<8, 32>>(g, g_x, g_yh, n, C);
+int emu_idwt_level_backward(const float* g, float* g_x, float* g_yh, uint32_t n, uint32_t C, const float* yh, float reg) {
+    if (C % 32 == 0) emu_bwd<IdwtCfg<32, 32>>(g, g_x, g_yh, n, C, yh, reg);
+    else if (C % 24 == 0) emu_bwd<IdwtCfg<24, 32>>(g, g_x, g_yh, n, C, yh, reg);
+    else if (C % 16 == 0) emu_bwd<IdwtCfg<16, 32>>(g, g_x, g_yh, n, C, yh, reg);
+    else emu_bwd<IdwtCfg<8, 32>>(g, g_x, g_yh, n, C, yh, reg);
     return 0;
 }
 }

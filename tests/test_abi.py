@@ -34,7 +34,7 @@ def test_version_and_argument_errors_need_no_gpu():
     dims = _lib.MlpDims(96, 64, 64)
     assert lib.tnl_mlp_packed_bytes(ctypes.byref(dims)) == 2 * 2 * (96 * 64 + 64 * 16 + 32 * 64 + 64 * 64) + 2 * (8 + 16) * 64
     assert lib.tnl_march_rays_train_workspace(60000) >= 4 * 59
-    assert lib.tnl_idwt_level_forward(ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), 12, 32, None) == -1
+    assert lib.tnl_idwt_level_forward(ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), 12, 32, None, None) == -1
 
 
 def test_no_cpu_fallback():

@@ -43,6 +43,30 @@ def test_build_planes_matches_oracle(C, n0, levels):
         assert a.grad.shape == b.grad.shape and rel_l2(a.grad, b.grad) <= TOL_GRAD
 
 
+def test_fused_wavelet_regulariser():
+    """encoder.wavelet_l1 (value from the IDWT forward, gradient inside the IDWT backward) vs the reference's literal
+    torch expression (nerf/utils.py:640-655)."""
+    from trinerflet_b200 import trainer
+    from trinerflet_b200.triplane_encoder import TriPlaneVolume
+    enc = TriPlaneVolume(number_of_features=16, plane_resolution=256, inner_multi_res_scale=8).cuda()
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for p in enc.planes_features_wavelet_coefs:
+            p.copy_(0.05 * torch.randn(p.shape, generator=g))
+            p[:, :, :, ::3, ::5] = 0.0     # exact zeros: sign(0) = 0
+    w = torch.randn(3, 16, 256, 256, generator=g).cuda()
+    grads = []
+    for fused in (True, False):
+        enc.zero_grad(set_to_none=True); enc.reset_cahce()
+        planes = enc.get_planes()
+        reg = trainer.wavelet_regulariser(enc, 0.2, fused=fused)
+        ((planes * w).sum() * 1e-3 + 64.0 * reg).backward()
+        grads.append((float(reg), [p.grad.clone() for p in enc.parameters()]))
+    assert abs(grads[0][0] - grads[1][0]) <= 1e-5 * abs(grads[1][0])
+    for a, b in zip(grads[0][1], grads[1][1]):
+        assert rel_l2(a, b) <= 1e-5
+
+
 def test_golden_encoder_fixture(golden_dir):
     """The reference's own TriPlaneVolume (run on CPU by tests/golden/make_golden.py) vs our module on the GPU.
     The fixture uses C = 4 < 8, so channels are zero-padded to 8 (independent channels: exact)."""

@@ -40,13 +40,19 @@ def test_emulated_kernels_match_oracle(emu, C, n):
     xc = np.ascontiguousarray(x.detach().permute(0, 2, 3, 1).numpy())
     yc = np.ascontiguousarray(yh.detach().permute(0, 2, 3, 4, 1).numpy())
     out = np.full((3, 2 * n, 2 * n, C), np.nan, np.float32)
-    emu.emu_idwt_level_forward(_p(xc), _p(yc), _p(out), ctypes.c_uint32(n), ctypes.c_uint32(C))
+    asum = np.zeros(1, np.float32)
+    emu.emu_idwt_level_forward(_p(xc), _p(yc), _p(out), ctypes.c_uint32(n), ctypes.c_uint32(C), _p(asum))
+    assert abs(asum[0] - yh.detach().abs().sum().item()) <= 1e-4 * asum[0]     # every coefficient counted exactly once
     scale = ref.abs().max().item()
     assert np.isfinite(out).all()
     assert (torch.from_numpy(out).permute(0, 3, 1, 2) - ref.detach()).abs().max().item() <= 1e-5 * scale
     gc = np.ascontiguousarray(gout.permute(0, 2, 3, 1).numpy())
     gx = np.full((3, n, n, C), np.nan, np.float32)
     gyh = np.full((3, 3, n, n, C), np.nan, np.float32)
-    emu.emu_idwt_level_backward(_p(gc), _p(gx), _p(gyh), ctypes.c_uint32(n), ctypes.c_uint32(C))
+    emu.emu_idwt_level_backward(_p(gc), _p(gx), _p(gyh), ctypes.c_uint32(n), ctypes.c_uint32(C), None, ctypes.c_float(0))
     assert (torch.from_numpy(gx).permute(0, 3, 1, 2) - x.grad).abs().max().item() <= 1e-5 * x.grad.abs().max().item()
     assert (torch.from_numpy(gyh).permute(0, 4, 1, 2, 3) - yh.grad).abs().max().item() <= 1e-5 * yh.grad.abs().max().item()
+    gyh2 = np.full((3, 3, n, n, C), np.nan, np.float32)      # fused L1-regulariser gradient: + reg * sign(yh)
+    emu.emu_idwt_level_backward(_p(gc), _p(gx), _p(gyh2), ctypes.c_uint32(n), ctypes.c_uint32(C), _p(yc), ctypes.c_float(0.25))
+    want = yh.grad + 0.25 * torch.sign(yh.detach())
+    assert (torch.from_numpy(gyh2).permute(0, 4, 1, 2, 3) - want).abs().max().item() <= 1e-5 * want.abs().max().item()

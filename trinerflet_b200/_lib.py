@@ -41,8 +41,8 @@ SIGNATURES = {
     "tnl_compact_alive_workspace": (_sz, [_u32]),
     "tnl_compact_alive": (_int, [_vp, _u32, _vp, _vp, _vp, _sz, _vp]),
     "tnl_sh_encode_forward": (_int, [_vp, _vp, _u32, _u32, _vp]),
-    "tnl_idwt_level_forward": (_int, [_vp, _vp, _vp, _u32, _u32, _vp]),
-    "tnl_idwt_level_backward": (_int, [_vp, _vp, _vp, _u32, _u32, _vp]),
+    "tnl_idwt_level_forward": (_int, [_vp, _vp, _vp, _u32, _u32, _vp, _vp]),
+    "tnl_idwt_level_backward": (_int, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _f32, _vp]),
     "tnl_sample_planes_forward": (_int, [_vp, _vp, _u32, _u32, _u32, _f32, _int, _vp, _vp, _vp]),
     "tnl_sample_planes_backward": (_int, [_vp, _vp, _u32, _u32, _u32, _f32, _int, _vp, _vp, _vp]),
     "tnl_mlp_packed_bytes": (_sz, [_DP]),

@@ -26,7 +26,7 @@ namespace tnl {
 template <typename Cfg>
 __global__ void __launch_bounds__(Cfg::NT, (768 / Cfg::NT) > 0 ? (768 / Cfg::NT) : 1)
 k_idwt_fwd(const float* __restrict__ x, const float* __restrict__ yh, float* __restrict__ out, int n, int C,
-           int rows_per_cta) {
+           int rows_per_cta, float* __restrict__ abs_sum) {
     extern __shared__ __align__(16) float smem[];
     float* mid0 = smem;
     float* stage0 = smem + 2 * Cfg::MID_F;
@@ -42,7 +42,7 @@ k_idwt_fwd(const float* __restrict__ x, const float* __restrict__ yh, float* __r
         fwd_issue_stage<Cfg>(g, stage0 + ((ss + 1) & 1) * Cfg::STAGE, x, yh, tid, ss + 1);    \
         cp_async_wait<1>();                                                                   \
         float* mid = mid0 + (ss & 1) * Cfg::MID_F;                                            \
-        fwd_phase_a<Cfg, PH>(st, stage0 + (ss & 1) * Cfg::STAGE, mid, tid);                   \
+        fwd_phase_a<Cfg, PH>(g, st, stage0 + (ss & 1) * Cfg::STAGE, mid, tid, ss);            \
         __syncthreads();                                                                      \
         fwd_phase_b<Cfg>(g, mid, out, tid, ss);                                               \
     }
@@ -50,12 +50,26 @@ k_idwt_fwd(const float* __restrict__ x, const float* __restrict__ yh, float* __r
 #undef TNL_STEP
     }
     cp_async_wait<0>();
+    if (abs_sum != nullptr) {  // block-reduce the |yh| partial sums, one atomic per CTA
+        float v = st.abs_acc;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if ((tid & 31) == 0) smem[tid >> 5] = v;
+        __syncthreads();
+        if (tid < 32) {
+            float w = tid < (Cfg::NT + 31) / 32 ? smem[tid] : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+            if (tid == 0) atomicAdd(abs_sum, w);
+        }
+    }
 }
 
 template <typename Cfg>
 __global__ void __launch_bounds__(Cfg::NT, (768 / Cfg::NT) > 0 ? (768 / Cfg::NT) : 1)
 k_idwt_bwd(const float* __restrict__ gout, float* __restrict__ g_x, float* __restrict__ g_yh, int n, int C,
-           int rows_per_cta) {
+           int rows_per_cta, const float* __restrict__ yh, const float* __restrict__ reg_grad, float reg_coef) {
     extern __shared__ __align__(16) float smem[];
     float* mid0 = smem;
     float* stage0 = smem + 2 * Cfg::MID_B;
@@ -63,6 +77,8 @@ k_idwt_bwd(const float* __restrict__ gout, float* __restrict__ g_x, float* __res
     const IdwtGeom g = idwt_geom<Cfg>(tid, IdwtBlock{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z}, n, C, rows_per_cta);
     BwdState st;
     bwd_state_init(st);
+    const float reg = (yh != nullptr && reg_grad != nullptr) ? reg_coef * __ldg(reg_grad) : 0.f;
+    const float* yh_reg = (yh != nullptr && reg_grad != nullptr) ? yh : nullptr;
     bwd_issue_stage<Cfg>(g, stage0, gout, tid, 0);
     for (int s = 0; s < g.nsteps; s += 3) {
 #define TNL_STEP(PH)                                                                          \
@@ -73,7 +89,7 @@ k_idwt_bwd(const float* __restrict__ gout, float* __restrict__ g_x, float* __res
         float* mid = mid0 + (ss & 1) * Cfg::MID_B;                                            \
         bwd_phase_a<Cfg, PH>(st, stage0 + (ss & 1) * Cfg::STAGE, mid, tid);                   \
         __syncthreads();                                                                      \
-        bwd_phase_b<Cfg>(g, mid, g_x, g_yh, tid, ss);                                         \
+        bwd_phase_b<Cfg>(g, mid, g_x, g_yh, tid, ss, yh_reg, reg);                            \
     }
         TNL_STEP(0) TNL_STEP(1) TNL_STEP(2)
 #undef TNL_STEP
@@ -82,7 +98,8 @@ k_idwt_bwd(const float* __restrict__ gout, float* __restrict__ g_x, float* __res
 }
 
 template <typename Cfg>
-static int launch_fwd(const float* x, const float* yh, float* out, uint32_t n, uint32_t C, cudaStream_t stream) {
+static int launch_fwd(const float* x, const float* yh, float* out, uint32_t n, uint32_t C, float* abs_sum,
+                      cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_idwt_fwd<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_F);
@@ -90,12 +107,13 @@ static int launch_fwd(const float* x, const float* yh, float* out, uint32_t n, u
     }
     unsigned gx, gy, gz, rows;
     idwt_grid<Cfg>(n, C, kNumSM, gx, gy, gz, rows);
-    k_idwt_fwd<Cfg><<<dim3(gx, gy, gz), Cfg::NT, Cfg::SMEM_F, stream>>>(x, yh, out, (int)n, (int)C, (int)rows);
+    k_idwt_fwd<Cfg><<<dim3(gx, gy, gz), Cfg::NT, Cfg::SMEM_F, stream>>>(x, yh, out, (int)n, (int)C, (int)rows, abs_sum);
     return finish_launch("idwt_level_forward");
 }
 
 template <typename Cfg>
-static int launch_bwd(const float* g, float* g_x, float* g_yh, uint32_t n, uint32_t C, cudaStream_t stream) {
+static int launch_bwd(const float* g, float* g_x, float* g_yh, uint32_t n, uint32_t C, const float* yh,
+                      const float* reg_grad, float reg_coef, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_idwt_bwd<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_B);
@@ -103,7 +121,8 @@ static int launch_bwd(const float* g, float* g_x, float* g_yh, uint32_t n, uint3
     }
     unsigned gx, gy, gz, rows;
     idwt_grid<Cfg>(n, C, kNumSM, gx, gy, gz, rows);
-    k_idwt_bwd<Cfg><<<dim3(gx, gy, gz), Cfg::NT, Cfg::SMEM_B, stream>>>(g, g_x, g_yh, (int)n, (int)C, (int)rows);
+    k_idwt_bwd<Cfg><<<dim3(gx, gy, gz), Cfg::NT, Cfg::SMEM_B, stream>>>(g, g_x, g_yh, (int)n, (int)C, (int)rows, yh, reg_grad,
+                                                                        reg_coef);
     return finish_launch("idwt_level_backward");
 }
 
@@ -113,26 +132,28 @@ using namespace tnl;
 
 extern "C" {
 
-int tnl_idwt_level_forward(const float* x, const float* yh, float* out, uint32_t n, uint32_t C, tnl_stream_t stream) {
+int tnl_idwt_level_forward(const float* x, const float* yh, float* out, uint32_t n, uint32_t C, float* abs_sum,
+                           tnl_stream_t stream) {
     TNL_ARG_CHECK(x && yh && out, "null pointer");
     TNL_ARG_CHECK(n >= 8 && n % 8 == 0 && n <= 16384, "n must be a multiple of 8 in [8, 16384]");
     TNL_ARG_CHECK(C >= 8 && C % 8 == 0, "C must be a multiple of 8");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (C % 32 == 0) return launch_fwd<IdwtCfg<32, 32>>(x, yh, out, n, C, s);
-    if (C % 24 == 0) return launch_fwd<IdwtCfg<24, 32>>(x, yh, out, n, C, s);
-    if (C % 16 == 0) return launch_fwd<IdwtCfg<16, 32>>(x, yh, out, n, C, s);
-    return launch_fwd<IdwtCfg<8, 32>>(x, yh, out, n, C, s);
+    if (C % 32 == 0) return launch_fwd<IdwtCfg<32, 32>>(x, yh, out, n, C, abs_sum, s);
+    if (C % 24 == 0) return launch_fwd<IdwtCfg<24, 32>>(x, yh, out, n, C, abs_sum, s);
+    if (C % 16 == 0) return launch_fwd<IdwtCfg<16, 32>>(x, yh, out, n, C, abs_sum, s);
+    return launch_fwd<IdwtCfg<8, 32>>(x, yh, out, n, C, abs_sum, s);
 }
 
-int tnl_idwt_level_backward(const float* g_out, float* g_x, float* g_yh, uint32_t n, uint32_t C, tnl_stream_t stream) {
+int tnl_idwt_level_backward(const float* g_out, float* g_x, float* g_yh, uint32_t n, uint32_t C, const float* yh,
+                            const float* reg_grad, float reg_coef, tnl_stream_t stream) {
     TNL_ARG_CHECK(g_out && g_x && g_yh, "null pointer");
     TNL_ARG_CHECK(n >= 8 && n % 8 == 0 && n <= 16384, "n must be a multiple of 8 in [8, 16384]");
     TNL_ARG_CHECK(C >= 8 && C % 8 == 0, "C must be a multiple of 8");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (C % 32 == 0) return launch_bwd<IdwtCfg<32, 32>>(g_out, g_x, g_yh, n, C, s);
-    if (C % 24 == 0) return launch_bwd<IdwtCfg<24, 32>>(g_out, g_x, g_yh, n, C, s);
-    if (C % 16 == 0) return launch_bwd<IdwtCfg<16, 32>>(g_out, g_x, g_yh, n, C, s);
-    return launch_bwd<IdwtCfg<8, 32>>(g_out, g_x, g_yh, n, C, s);
+    if (C % 32 == 0) return launch_bwd<IdwtCfg<32, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, s);
+    if (C % 24 == 0) return launch_bwd<IdwtCfg<24, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, s);
+    if (C % 16 == 0) return launch_bwd<IdwtCfg<16, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, s);
+    return launch_bwd<IdwtCfg<8, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, s);
 }
 
 }  // extern "C"

@@ -133,10 +133,12 @@ TNL_HD IdwtGeom idwt_geom(int tid, IdwtBlock b, int n, int C, int rows_per_cta) 
 // ================================================================================================
 struct FwdState {
     float wLL[9], wLH[9], wHL[9], wHH[9];
+    float abs_acc;  // sum |yh| over the detail coefficients this thread owns (wavelet L1 regulariser by-product)
 };
 
 TNL_HD void fwd_state_init(FwdState& st) {
     for (int i = 0; i < 9; ++i) st.wLL[i] = st.wLH[i] = st.wHL[i] = st.wHH[i] = 0.f;
+    st.abs_acc = 0.f;
 }
 
 // stage the RA coarse rows of step ss (rows begin + ss*RA ..) for this thread's column
@@ -180,11 +182,12 @@ TNL_HD void synth_pair(const float (&lo)[9], const float (&hi)[9], float& even, 
 }
 
 template <int SLOT>
-TNL_HD void fwd_row(FwdState& st, const float* stage, float* mid, int tid, int rr, int NT, int RB, int RS) {
+TNL_HD void fwd_row(FwdState& st, const float* stage, float* mid, int tid, int rr, int NT, int RB, int RS, bool own) {
     st.wLL[SLOT] = stage[(rr * 4 + 0) * NT + tid];
     st.wLH[SLOT] = stage[(rr * 4 + 1) * NT + tid];
     st.wHL[SLOT] = stage[(rr * 4 + 2) * NT + tid];
     st.wHH[SLOT] = stage[(rr * 4 + 3) * NT + tid];
+    if (own) st.abs_acc += fabsf(st.wLH[SLOT]) + fabsf(st.wHL[SLOT]) + fabsf(st.wHH[SLOT]);
     float e0, o0, e1, o1;
     synth_pair<SLOT, true>(st.wLL, st.wLH, e0, o0);
     synth_pair<SLOT, false>(st.wHL, st.wHH, e1, o1);
@@ -196,10 +199,13 @@ TNL_HD void fwd_row(FwdState& st, const float* stage, float* mid, int tid, int r
 
 // phase A of step phase PH (= step index mod 3): RA rows enter the windows at ring slots 3*PH .. 3*PH+2
 template <typename Cfg, int PH>
-TNL_HD void fwd_phase_a(FwdState& st, const float* stage, float* mid, int tid) {
-    fwd_row<(PH * 3 + 0) % 9>(st, stage, mid, tid, 0, Cfg::NT, Cfg::RB, Cfg::RS_F);
-    fwd_row<(PH * 3 + 1) % 9>(st, stage, mid, tid, 1, Cfg::NT, Cfg::RB, Cfg::RS_F);
-    fwd_row<(PH * 3 + 2) % 9>(st, stage, mid, tid, 2, Cfg::NT, Cfg::RB, Cfg::RS_F);
+TNL_HD void fwd_phase_a(const IdwtGeom& g, FwdState& st, const float* stage, float* mid, int tid, int ss) {
+    // a coefficient is "owned" by exactly one CTA: its column lies in the strip proper (not the halo) and its row in the chunk
+    const bool col_own = g.col >= 4 && g.col < 4 + Cfg::TM;
+    const int j0 = g.begin + ss * Cfg::RA;
+    fwd_row<(PH * 3 + 0) % 9>(st, stage, mid, tid, 0, Cfg::NT, Cfg::RB, Cfg::RS_F, col_own && j0 + 0 >= g.row_lo && j0 + 0 < g.row_hi);
+    fwd_row<(PH * 3 + 1) % 9>(st, stage, mid, tid, 1, Cfg::NT, Cfg::RB, Cfg::RS_F, col_own && j0 + 1 >= g.row_lo && j0 + 1 < g.row_hi);
+    fwd_row<(PH * 3 + 2) % 9>(st, stage, mid, tid, 2, Cfg::NT, Cfg::RB, Cfg::RS_F, col_own && j0 + 2 >= g.row_lo && j0 + 2 < g.row_hi);
 }
 
 // phase B: W-axis synthesis. item = (mid row r, strip sb of 8 output columns, channel cb)
@@ -315,8 +321,12 @@ TNL_HD void bwd_phase_a(BwdState& st, const float* stage, float* mid, int tid) {
 }
 
 // phase B: W-axis adjoint. item = (row r, pair of coarse columns sb, channel cb)
+TNL_HD float signf_(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }  // torch.sign
+
+// yh / reg: optional fused gradient of the wavelet L1 regulariser, g_yh += reg * sign(yh)  (nerf/utils.py:640-655)
 template <typename Cfg>
-TNL_HD void bwd_phase_b(const IdwtGeom& g, const float* mid, float* g_x, float* g_yh, int tid, int ss) {
+TNL_HD void bwd_phase_b(const IdwtGeom& g, const float* mid, float* g_x, float* g_yh, int tid, int ss, const float* yh,
+                        float reg) {
     const int cb = tid % Cfg::CG;
     const int rs = tid / Cfg::CG;  // 0 .. 23 = 3 rows x 8 column pairs
     const int r = rs % Cfg::RA;
@@ -351,10 +361,18 @@ TNL_HD void bwd_phase_b(const IdwtGeom& g, const float* mid, float* g_x, float* 
         const int w = g.m0 + 2 * sb + e;
         if (w < g.n) {
             const size_t px = (size_t)m * g.n + w;
+            const size_t i0 = ((size_t)(g.plane * 3 + 0) * plane_px + px) * g.C + g.c0 + cb;
+            const size_t i1 = ((size_t)(g.plane * 3 + 1) * plane_px + px) * g.C + g.c0 + cb;
+            const size_t i2 = ((size_t)(g.plane * 3 + 2) * plane_px + px) * g.C + g.c0 + cb;
+            if (yh != nullptr) {
+                lh = fmaf(reg, signf_(yh[i0]), lh);
+                hl = fmaf(reg, signf_(yh[i1]), hl);
+                hh = fmaf(reg, signf_(yh[i2]), hh);
+            }
             g_x[((size_t)g.plane * plane_px + px) * g.C + g.c0 + cb] = 2.0f * ll;
-            g_yh[((size_t)(g.plane * 3 + 0) * plane_px + px) * g.C + g.c0 + cb] = lh;
-            g_yh[((size_t)(g.plane * 3 + 1) * plane_px + px) * g.C + g.c0 + cb] = hl;
-            g_yh[((size_t)(g.plane * 3 + 2) * plane_px + px) * g.C + g.c0 + cb] = hh;
+            g_yh[i0] = lh;
+            g_yh[i1] = hl;
+            g_yh[i2] = hh;
         }
     }
 }

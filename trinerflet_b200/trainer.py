@@ -19,16 +19,20 @@ from . import parallel
 
 def default_opt(**over):
     opt = dict(fp16=True, max_steps=1024, dt_gamma=0.0, background_color=0.0, wavelet_regularization=0.2,
-               update_extra_interval=16, lr=1e-2)
+               update_extra_interval=16, lr=1e-2, fused_regulariser=True)
     opt.update(over)
     return SimpleNamespace(**opt)
 
 
-def wavelet_regulariser(encoder, lam):
-    """nerf/utils.py:640-655 (unweighted branch): lam * sum_l mean|yh_l| * numel_l/numel_all / n_levels."""
+def wavelet_regulariser(encoder, lam, fused=True):
+    """nerf/utils.py:640-655 (unweighted branch): lam * sum_l mean|yh_l| * numel_l/numel_all / n_levels.
+    fused=True takes the value from the |yh| sums of this step's plane reconstruction and applies the gradient inside
+    the IDWT backward kernels; fused=False is the reference's literal torch expression (three extra passes per level)."""
     feats = encoder.get_wavelet_features()
     if lam <= 0 or len(feats) == 0:
         return None
+    if fused:
+        return encoder.wavelet_l1(lam)
     total = sum(v.numel() for v in feats)
     reg = sum(v.abs().mean() * (v.numel() / total) for v in feats) / len(feats)
     return lam * reg
@@ -61,7 +65,7 @@ class TrainStep:
                                force_all_rays=False, dt_gamma=opt.dt_gamma, max_steps=opt.max_steps)
             pred = out['image'].view(-1, 3)
             loss = self.criterion(pred, images).mean(-1).mean()
-            reg = wavelet_regulariser(enc, opt.wavelet_regularization)
+            reg = wavelet_regulariser(enc, opt.wavelet_regularization, getattr(opt, "fused_regulariser", True))
             if reg is not None:
                 loss = loss + reg
             enc.reset_cahce()

@@ -86,8 +86,10 @@ def _require_cuda_f32(t, what):
 # multilevel inverse DWT  (build_planes, triplane_encoder.py:364-405)
 # ----------------------------------------------------------------------------------------------
 class _BuildPlanes(Function):
-    """planes = IDWT_L(...IDWT_1(2*x0, yh_0)..., yh_{L-1}) with zero padding 4 per level.  Linear in all inputs,
-    so backward needs no saved activations: it is the chain of adjoint level kernels."""
+    """planes = IDWT_L(...IDWT_1(2*x0, yh_0)..., yh_{L-1}) with zero padding 4 per level, plus abs_sums[l] = sum|yh_l|
+    (the forward value of the wavelet L1 regulariser, a free by-product of the pass that reads yh).  Linear in all
+    inputs, so backward needs no saved activations: it is the chain of adjoint level kernels, with the regulariser
+    gradient  g_abs[l] * sign(yh_l)  folded into the coefficient-gradient store."""
 
     @staticmethod
     def forward(ctx, planes_features, *coefs):
@@ -95,34 +97,53 @@ class _BuildPlanes(Function):
         x = to_cl_planes(planes_features.detach())
         C, n = x.shape[1], x.shape[2]
         ctx.n0, ctx.C, ctx.levels = n, C, len(coefs)
-        for yh in coefs:
+        ctx.set_materialize_grads(False)   # an unused abs_sums output must not cost a pass over the coefficients
+        abs_sums = torch.zeros(max(len(coefs), 1), device=x.device, dtype=torch.float32)
+        saved = []
+        for l, yh in enumerate(coefs):
             _require_cuda_f32(yh, "wavelet coefficients")
             if yh.shape != (3, C, 3, n, n):
                 raise RuntimeError(f"wavelet level has shape {tuple(yh.shape)}, expected {(3, C, 3, n, n)}")
             yh = to_cl_coefs(yh.detach())
+            saved.append(yh)
             out = cl_empty_planes(C, 2 * n, device=x.device)
-            call("tnl_idwt_level_forward", ptr(x), ptr(yh), ptr(out), n, C, stream())
+            call("tnl_idwt_level_forward", ptr(x), ptr(yh), ptr(out), n, C, ptr(abs_sums[l:l + 1]), stream())
             x, n = out, 2 * n
-        return x
+        ctx.save_for_backward(*saved)
+        return x, abs_sums
 
     @staticmethod
-    def backward(ctx, g):
-        g = to_cl_planes(g)
+    def backward(ctx, g, g_abs):
         C = ctx.C
         n = ctx.n0 * (2 ** ctx.levels)
+        yhs = ctx.saved_tensors
+        if g is None:
+            g = cl_empty_planes(C, n, device=yhs[0].device, zero=True)
+        g = to_cl_planes(g)
+        if g_abs is not None:
+            g_abs = g_abs.contiguous().float()
         grads = []
-        for _ in range(ctx.levels):
+        for l in reversed(range(ctx.levels)):
             n //= 2
             g_x = cl_empty_planes(C, n, device=g.device)
             g_yh = cl_empty_coefs(C, n, device=g.device)
-            call("tnl_idwt_level_backward", ptr(g), ptr(g_x), ptr(g_yh), n, C, stream())
+            if g_abs is not None:
+                call("tnl_idwt_level_backward", ptr(g), ptr(g_x), ptr(g_yh), n, C, ptr(yhs[l]), ptr(g_abs[l:l + 1]), 1.0,
+                     stream())
+            else:
+                call("tnl_idwt_level_backward", ptr(g), ptr(g_x), ptr(g_yh), n, C, None, None, 0.0, stream())
             grads.append(g_yh)
             g = g_x
         return (g, *reversed(grads))
 
 
-def build_planes(planes_features, coefs):
+def build_planes_with_abs(planes_features, coefs):
+    """-> (planes [3,C,R,R], abs_sums [L] with abs_sums[l] = sum |coefs[l]|), both differentiable."""
     return _BuildPlanes.apply(planes_features, *coefs)
+
+
+def build_planes(planes_features, coefs):
+    return _BuildPlanes.apply(planes_features, *coefs)[0]
 
 
 # ----------------------------------------------------------------------------------------------
@@ -226,6 +247,7 @@ class TriPlaneVolume(nn.Module):
         self.register_buffer('plane_normals', normals.clone())
 
         self.last_used_planes = None
+        self._last_abs_sums = None
         self._init_plane_features(planes_features)
 
     # -- parameters (triplane_encoder.py:155-231) --------------------------------------------------
@@ -276,6 +298,7 @@ class TriPlaneVolume(nn.Module):
 
     def reset_cahce(self):  # (sic) -- reference spelling, nerf/utils.py:1139,1162
         self.last_used_planes = None
+        self._last_abs_sums = None
 
     reset_cache = reset_cahce
 
@@ -284,7 +307,9 @@ class TriPlaneVolume(nn.Module):
         coefs = list(self.planes_features_wavelet_coefs) if coefs is None else coefs
         if self.inner_wavelet_scale <= 1 or len(coefs) == 0:
             return planes_features
-        return build_planes(planes_features, coefs)
+        planes, abs_sums = build_planes_with_abs(planes_features, coefs)
+        self._last_abs_sums = abs_sums
+        return planes
 
     def get_planes(self, max_res=-1, max_scale=-1, get_all_resolutions=False):
         if max_res > 0 or max_scale > 0 or get_all_resolutions:
@@ -294,6 +319,18 @@ class TriPlaneVolume(nn.Module):
         planes = self.build_planes()
         self.last_used_planes = planes
         return planes
+
+    def wavelet_l1(self, lam):
+        """lam * (sum_l mean|yh_l| * numel_l / numel_all) / L -- the regulariser of nerf/utils.py:640-655 (unweighted
+        branch), taken from the |yh| sums the plane reconstruction produced; its gradient is applied inside the IDWT
+        backward kernels (no extra pass over the coefficients).  Call after get_planes() of the same step."""
+        feats = self.get_wavelet_features()
+        if len(feats) == 0:
+            return None
+        if self.last_used_planes is None or getattr(self, "_last_abs_sums", None) is None:
+            self.get_planes()
+        total = sum(v.numel() for v in feats)
+        return lam * self._last_abs_sums.sum() / (total * len(feats))
 
     def sample_from_planes(self, coordinates, plane_features=None, lbound=None, n_valid=None):
         if plane_features is None:
