@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=0, help="rays per GPU per step (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU work for the cpu_baseline leg")
     return ap.parse_args()
 
@@ -225,9 +226,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step(b):
+    def eager_step(b):
         net.zero_grad(set_to_none=True)
         return ts.forward_backward(*b, update_grid=False)
+
+    use_graph = not args.no_graph
+    if use_graph:
+        c0 = _lib.launch_count
+        ts.capture(*devb[-2], warmup=0)
+        ts._graph_kernel_count = _lib.launch_count - c0
+
+    def one_step(b):
+        return ts.replay(*b) if use_graph else eager_step(b)
 
     for i in range(args.warmup):
         one_step(devb[i])
@@ -244,6 +254,8 @@ def main():
     e1.record()
     barrier()
     launches = _lib.launch_count - launches0
+    if use_graph:   # replays do not pass through the Python launch counter: kernels per captured step x steps
+        launches = ts._graph_kernel_count * args.steps
     clk = clocks.stop() if rank == 0 else None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     counts = net.step_counter[:min(16, args.steps), 0].float().mean().reshape(1)
@@ -262,7 +274,7 @@ def main():
     h2d = d2h = 0
     for i in range(args.steps):
         hb = host[args.warmup + i]
-        b = tuple(t.to(dev, non_blocking=True) for t in hb)
+        b = hb if use_graph else tuple(t.to(dev, non_blocking=True) for t in hb)   # graph mode: H2D into the static buffers
         h2d = sum(t.numel() * t.element_size() for t in hb)
         loss = one_step(b)
         _ = loss.item()
@@ -280,7 +292,7 @@ def main():
         _lib.profile_start()
         nprof = min(args.steps, 5)
         for i in range(nprof):
-            one_step(devb[args.warmup + i])
+            eager_step(devb[args.warmup + i])
         prof = _lib.profile_stop()
         kernels = {}
         for name, recs in prof.items():
@@ -332,6 +344,7 @@ def main():
                                    f"{n_rays} rays/GPU/step, synthetic 800x800 Blender-shaped scene, ball occupancy r=0.75, random-init",
                        "rays_per_gpu": n_rays, "global_rays": n_rays * world, "parallelism": f"ray-sharded dp{world}, replicated coefficients, NCCL grad all-reduce",
                        "timed_region": "get_planes (IDWT) + render + loss + backward (+ grad all-reduce); optimizer and density-grid refresh excluded (metric definition), see extras",
+                       "launch": "one CUDA-graph replay per step" if use_graph else "eager Python launches",
                        "l2": "inputs (1.6 GB of coefficients/planes per pass) exceed the 126 MB L2; a different ray batch every step"},
             "clocks": clk, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "extras": extras,

@@ -70,10 +70,43 @@ class TrainStep:
                 loss = loss + reg
             enc.reset_cahce()
             self.scaler.scale(loss).backward()
-        if self.world_size > 1:
+        if self.world_size > 1 and not torch.cuda.is_current_stream_capturing():
             parallel.allreduce_gradients(model, self.world_size)
         self.global_step += 1
         return loss.detach()
+
+    # ---- CUDA-graph mode: the whole fwd+bwd of a steady-state step is one graph launch ------------------------------
+    def capture(self, rays_o, rays_d, images, warmup=3):
+        """Capture forward_backward (steady state: mean_count > 0, no density-grid refresh) into a CUDA graph.
+        Inputs are copied into static buffers before each replay; parameter gradients live in the graph's memory pool
+        and are overwritten by every replay (equivalent to zero_grad(set_to_none=True) + backward).  The step counter
+        ring slot is the one current at capture time."""
+        assert self.model.mean_count > 0, "capture needs the steady state (mean_count > 0): run a few eager steps first"
+        self._static = tuple(t.clone() for t in (rays_o, rays_d, images))
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.model.zero_grad(set_to_none=True)
+                self.forward_backward(*self._static, update_grid=False)
+        torch.cuda.current_stream().wait_stream(side)
+        self.model.zero_grad(set_to_none=True)
+        slot = self.model.local_step
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_loss = self.forward_backward(*self._static, update_grid=False)
+        self._graph_slot = slot
+        return self
+
+    def replay(self, rays_o, rays_d, images):
+        """One captured fwd+bwd on new inputs (device or pinned-host tensors); returns the (static) loss tensor."""
+        for dst, src in zip(self._static, (rays_o, rays_d, images)):
+            dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        if self.world_size > 1:
+            parallel.allreduce_gradients(self.model, self.world_size)
+        self.global_step += 1
+        return self._static_loss
 
     def optimizer_step(self):
         if self.optimizer is None:
