@@ -13,7 +13,7 @@ template <typename Cfg>
 static void emu_fwd(const float* x, const float* yh, float* out, unsigned n, unsigned C, float* abs_sum) {
     unsigned gx, gy, gz, rows;
     idwt_grid<Cfg>(n, C, 148, gx, gy, gz, rows);
-    std::vector<float> smem(2 * Cfg::MID_F + 2 * Cfg::STAGE);
+    std::vector<float> smem(2 * Cfg::MID_F + 3 * Cfg::STAGE);
     std::vector<FwdState> st(Cfg::NT);
     std::vector<IdwtGeom> geo(Cfg::NT);
     for (unsigned bz = 0; bz < gz; ++bz) for (unsigned by = 0; by < gy; ++by) for (unsigned bx = 0; bx < gx; ++bx) {
@@ -21,22 +21,23 @@ static void emu_fwd(const float* x, const float* yh, float* out, unsigned n, uns
         float* stage0 = smem.data() + 2 * Cfg::MID_F;
         for (int t = 0; t < Cfg::NT; ++t) {
             geo[t] = idwt_geom<Cfg>(t, IdwtBlock{(int)bx, (int)by, (int)bz}, (int)n, (int)C, (int)rows);
-            fwd_state_init(st[t]);
-            fwd_issue_stage<Cfg>(geo[t], stage0, x, yh, t, 0);
+            fwd_state_init<Cfg>(st[t], geo[t], x, yh, t);
+            fwd_issue_stage<Cfg>(geo[t], st[t], stage0, t);
+            fwd_issue_stage<Cfg>(geo[t], st[t], stage0 + Cfg::STAGE, t);
         }
         const int nsteps = geo[0].nsteps;
         for (int ss = 0; ss < nsteps; ++ss) {
             float* mid = mid0 + (ss & 1) * Cfg::MID_F;
-            const float* stage = stage0 + (ss & 1) * Cfg::STAGE;
+            const float* stage = stage0 + (ss % 3) * Cfg::STAGE;
             for (int t = 0; t < Cfg::NT; ++t) {
-                fwd_issue_stage<Cfg>(geo[t], stage0 + ((ss + 1) & 1) * Cfg::STAGE, x, yh, t, ss + 1);
+                fwd_issue_stage<Cfg>(geo[t], st[t], stage0 + ((ss + 2) % 3) * Cfg::STAGE, t);
                 switch (ss % 3) {
                     case 0: fwd_phase_a<Cfg, 0>(geo[t], st[t], stage, mid, t, ss); break;
                     case 1: fwd_phase_a<Cfg, 1>(geo[t], st[t], stage, mid, t, ss); break;
                     default: fwd_phase_a<Cfg, 2>(geo[t], st[t], stage, mid, t, ss); break;
                 }
             }
-            for (int t = 0; t < Cfg::NT; ++t) fwd_phase_b<Cfg>(geo[t], mid, out, t, ss);
+            for (int t = 0; t < Cfg::NT; ++t) fwd_phase_b<Cfg>(geo[t], st[t], mid, out, ss);
         }
         if (abs_sum) for (int t = 0; t < Cfg::NT; ++t) *abs_sum += st[t].abs_acc;
     }
@@ -46,7 +47,7 @@ template <typename Cfg>
 static void emu_bwd(const float* g, float* g_x, float* g_yh, unsigned n, unsigned C, const float* yh, float reg) {
     unsigned gx, gy, gz, rows;
     idwt_grid<Cfg>(n, C, 148, gx, gy, gz, rows);
-    std::vector<float> smem(2 * Cfg::MID_B + 2 * Cfg::STAGE);
+    std::vector<float> smem(2 * Cfg::MID_B + 3 * Cfg::STAGE);
     std::vector<BwdState> st(Cfg::NT);
     std::vector<IdwtGeom> geo(Cfg::NT);
     for (unsigned bz = 0; bz < gz; ++bz) for (unsigned by = 0; by < gy; ++by) for (unsigned bx = 0; bx < gx; ++bx) {
@@ -54,15 +55,16 @@ static void emu_bwd(const float* g, float* g_x, float* g_yh, unsigned n, unsigne
         float* stage0 = smem.data() + 2 * Cfg::MID_B;
         for (int t = 0; t < Cfg::NT; ++t) {
             geo[t] = idwt_geom<Cfg>(t, IdwtBlock{(int)bx, (int)by, (int)bz}, (int)n, (int)C, (int)rows);
-            bwd_state_init(st[t]);
-            bwd_issue_stage<Cfg>(geo[t], stage0, g, t, 0);
+            bwd_state_init<Cfg>(st[t], geo[t], g);
+            bwd_issue_stage<Cfg>(geo[t], st[t], stage0, t);
+            bwd_issue_stage<Cfg>(geo[t], st[t], stage0 + Cfg::STAGE, t);
         }
         const int nsteps = geo[0].nsteps;
         for (int ss = 0; ss < nsteps; ++ss) {
             float* mid = mid0 + (ss & 1) * Cfg::MID_B;
-            const float* stage = stage0 + (ss & 1) * Cfg::STAGE;
+            const float* stage = stage0 + (ss % 3) * Cfg::STAGE;
             for (int t = 0; t < Cfg::NT; ++t) {
-                bwd_issue_stage<Cfg>(geo[t], stage0 + ((ss + 1) & 1) * Cfg::STAGE, g, t, ss + 1);
+                bwd_issue_stage<Cfg>(geo[t], st[t], stage0 + ((ss + 2) % 3) * Cfg::STAGE, t);
                 switch (ss % 3) {
                     case 0: bwd_phase_a<Cfg, 0>(st[t], stage, mid, t); break;
                     case 1: bwd_phase_a<Cfg, 1>(st[t], stage, mid, t); break;

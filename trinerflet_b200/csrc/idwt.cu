@@ -20,6 +20,7 @@
 //   co-limited ("IDWT roofline").
 #include "common.cuh"
 #include "idwt_core.cuh"
+#include <stdlib.h>
 
 namespace tnl {
 
@@ -33,18 +34,19 @@ k_idwt_fwd(const float* __restrict__ x, const float* __restrict__ yh, float* __r
     const int tid = threadIdx.x;
     const IdwtGeom g = idwt_geom<Cfg>(tid, IdwtBlock{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z}, n, C, rows_per_cta);
     FwdState st;
-    fwd_state_init(st);
-    fwd_issue_stage<Cfg>(g, stage0, x, yh, tid, 0);
+    fwd_state_init<Cfg>(st, g, x, yh, tid);
+    fwd_issue_stage<Cfg>(g, st, stage0, tid);
+    fwd_issue_stage<Cfg>(g, st, stage0 + Cfg::STAGE, tid);
     for (int s = 0; s < g.nsteps; s += 3) {
 #define TNL_STEP(PH)                                                                          \
     if (s + PH < g.nsteps) {                                                                  \
         const int ss = s + PH;                                                                \
-        fwd_issue_stage<Cfg>(g, stage0 + ((ss + 1) & 1) * Cfg::STAGE, x, yh, tid, ss + 1);    \
-        cp_async_wait<1>();                                                                   \
+        fwd_issue_stage<Cfg>(g, st, stage0 + ((PH + 2) % 3) * Cfg::STAGE, tid);               \
+        cp_async_wait<2>();                                                                   \
         float* mid = mid0 + (ss & 1) * Cfg::MID_F;                                            \
-        fwd_phase_a<Cfg, PH>(g, st, stage0 + (ss & 1) * Cfg::STAGE, mid, tid, ss);            \
+        fwd_phase_a<Cfg, PH>(g, st, stage0 + PH * Cfg::STAGE, mid, tid, ss);                  \
         __syncthreads();                                                                      \
-        fwd_phase_b<Cfg>(g, mid, out, tid, ss);                                               \
+        fwd_phase_b<Cfg>(g, st, mid, out, ss);                                                \
     }
         TNL_STEP(0) TNL_STEP(1) TNL_STEP(2)
 #undef TNL_STEP
@@ -76,18 +78,19 @@ k_idwt_bwd(const float* __restrict__ gout, float* __restrict__ g_x, float* __res
     const int tid = threadIdx.x;
     const IdwtGeom g = idwt_geom<Cfg>(tid, IdwtBlock{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z}, n, C, rows_per_cta);
     BwdState st;
-    bwd_state_init(st);
+    bwd_state_init<Cfg>(st, g, gout);
     const float reg = (yh != nullptr && reg_grad != nullptr) ? reg_coef * __ldg(reg_grad) : 0.f;
     const float* yh_reg = (yh != nullptr && reg_grad != nullptr) ? yh : nullptr;
-    bwd_issue_stage<Cfg>(g, stage0, gout, tid, 0);
+    bwd_issue_stage<Cfg>(g, st, stage0, tid);
+    bwd_issue_stage<Cfg>(g, st, stage0 + Cfg::STAGE, tid);
     for (int s = 0; s < g.nsteps; s += 3) {
 #define TNL_STEP(PH)                                                                          \
     if (s + PH < g.nsteps) {                                                                  \
         const int ss = s + PH;                                                                \
-        bwd_issue_stage<Cfg>(g, stage0 + ((ss + 1) & 1) * Cfg::STAGE, gout, tid, ss + 1);     \
-        cp_async_wait<1>();                                                                   \
+        bwd_issue_stage<Cfg>(g, st, stage0 + ((PH + 2) % 3) * Cfg::STAGE, tid);               \
+        cp_async_wait<2>();                                                                   \
         float* mid = mid0 + (ss & 1) * Cfg::MID_B;                                            \
-        bwd_phase_a<Cfg, PH>(st, stage0 + (ss & 1) * Cfg::STAGE, mid, tid);                   \
+        bwd_phase_a<Cfg, PH>(st, stage0 + PH * Cfg::STAGE, mid, tid);                         \
         __syncthreads();                                                                      \
         bwd_phase_b<Cfg>(g, mid, g_x, g_yh, tid, ss, yh_reg, reg);                            \
     }
@@ -138,7 +141,7 @@ int tnl_idwt_level_forward(const float* x, const float* yh, float* out, uint32_t
     TNL_ARG_CHECK(n >= 8 && n % 8 == 0 && n <= 16384, "n must be a multiple of 8 in [8, 16384]");
     TNL_ARG_CHECK(C >= 8 && C % 8 == 0, "C must be a multiple of 8");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (C % 32 == 0) return launch_fwd<IdwtCfg<32, 32>>(x, yh, out, n, C, abs_sum, s);
+    if (C % 32 == 0 && getenv("TNL_IDWT_CG32")) return launch_fwd<IdwtCfg<32, 32>>(x, yh, out, n, C, abs_sum, s);
     if (C % 24 == 0) return launch_fwd<IdwtCfg<24, 32>>(x, yh, out, n, C, abs_sum, s);
     if (C % 16 == 0) return launch_fwd<IdwtCfg<16, 32>>(x, yh, out, n, C, abs_sum, s);
     return launch_fwd<IdwtCfg<8, 32>>(x, yh, out, n, C, abs_sum, s);
@@ -150,7 +153,7 @@ int tnl_idwt_level_backward(const float* g_out, float* g_x, float* g_yh, uint32_
     TNL_ARG_CHECK(n >= 8 && n % 8 == 0 && n <= 16384, "n must be a multiple of 8 in [8, 16384]");
     TNL_ARG_CHECK(C >= 8 && C % 8 == 0, "C must be a multiple of 8");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (C % 32 == 0) return launch_bwd<IdwtCfg<32, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, s);
+    if (C % 32 == 0 && getenv("TNL_IDWT_CG32")) return launch_bwd<IdwtCfg<32, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, s);
     if (C % 24 == 0) return launch_bwd<IdwtCfg<24, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, s);
     if (C % 16 == 0) return launch_bwd<IdwtCfg<16, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, s);
     return launch_bwd<IdwtCfg<8, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, s);
