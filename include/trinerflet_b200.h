@@ -116,14 +116,23 @@ int tnl_idwt_level_backward(const float* g_out, float* g_x, float* g_yh, uint32_
  * planes [3][R][R][C]; xyz [M][3]; feat [M][3C] with feature index p*C + c.
  * u = xyz * inv_bound (inv_bound = 1/bound in fp32, CUDA's tensor/scalar rule); if fp16_coords != 0,
  * u is rounded to fp16 first (the autocast quirk of triplane_encoder.py:299).
- * n_valid (device int32*, may be NULL): rows >= *n_valid are skipped (feat rows written as zeros). */
+ * n_valid (device int32*, may be NULL): rows >= *n_valid are skipped (feat rows written as zeros).
+ * perm (device int32 [M], may be NULL): visit order (tnl_cell_sort); row m of feat always belongs to point m. */
 int tnl_sample_planes_forward(const float* planes, const float* xyz, uint32_t M, uint32_t R, uint32_t C,
-                              float inv_bound, int fp16_coords, const int32_t* n_valid, float* feat,
-                              tnl_stream_t stream);
+                              float inv_bound, int fp16_coords, const int32_t* n_valid, const int32_t* perm,
+                              float* feat, tnl_stream_t stream);
 /* Adjoint scatter (grid_sampler_2d_backward w.r.t. input): g_planes += ...; caller zero-fills g_planes. */
 int tnl_sample_planes_backward(const float* g_feat, const float* xyz, uint32_t M, uint32_t R, uint32_t C,
-                               float inv_bound, int fp16_coords, const int32_t* n_valid, float* g_planes,
-                               tnl_stream_t stream);
+                               float inv_bound, int fp16_coords, const int32_t* n_valid, const int32_t* perm,
+                               float* g_planes, tnl_stream_t stream);
+
+/* Spatial binning of sample points: perm[i] = row of the i-th point in the order of a G^3 Morton grid over
+ * [-bound, bound]^3 (rows >= *n_valid last).  Kernels taking `perm` visit points in that order, which makes the
+ * plane gathers / gradient scatters of neighbouring threads hit the same texels (L2 locality); per-point results
+ * are unchanged.  No reference counterpart (the reference evaluates samples in marching order). */
+size_t tnl_cell_sort_workspace(uint32_t M, uint32_t G);
+int tnl_cell_sort(const float* xyz, uint32_t M, const int32_t* n_valid, float inv_bound, uint32_t G, int32_t* perm,
+                  void* workspace, size_t workspace_bytes, tnl_stream_t stream);
 
 /* ------------------------------------------------------------------ sigma / color MLP heads -- */
 /* NeRFNetwork.forward / .density (network.py:118-166) with the fp16-autocast arithmetic the reference

@@ -111,6 +111,15 @@ def test_sampling_matches_oracle(C, R, fp16):
     assert rel_linf(f_g, f_o) <= TOL_FWD
     (f_g * w.cuda()).sum().backward()
     assert rel_l2(p_g.grad, p_o.grad) <= TOL_GRAD
+    # spatially sorted visiting order: identical features, gradients equal up to atomic summation order
+    from trinerflet_b200.triplane_encoder import cell_sort
+    perm = cell_sort(xyz.cuda(), bound, None, 16)
+    assert torch.equal(torch.sort(perm.long())[0], torch.arange(M, device="cuda"))
+    p_s = cl_planes(planes.cuda()).requires_grad_(True)
+    f_s = sample_planes(p_s, xyz.cuda(), bound, fp16_coords=fp16, perm=perm)
+    assert torch.equal(f_s, f_g)
+    (f_s * w.cuda()).sum().backward()
+    assert rel_l2(p_s.grad, p_o.grad) <= TOL_GRAD
     # n_valid: rows past the counter are skipped (zeros out, no gradient)
     nv = torch.tensor([M // 2], dtype=torch.int32, device="cuda")
     p_g2 = cl_planes(planes.cuda()).requires_grad_(True)

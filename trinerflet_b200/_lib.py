@@ -43,8 +43,10 @@ SIGNATURES = {
     "tnl_sh_encode_forward": (_int, [_vp, _vp, _u32, _u32, _vp]),
     "tnl_idwt_level_forward": (_int, [_vp, _vp, _vp, _u32, _u32, _vp, _vp]),
     "tnl_idwt_level_backward": (_int, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _f32, _vp]),
-    "tnl_sample_planes_forward": (_int, [_vp, _vp, _u32, _u32, _u32, _f32, _int, _vp, _vp, _vp]),
-    "tnl_sample_planes_backward": (_int, [_vp, _vp, _u32, _u32, _u32, _f32, _int, _vp, _vp, _vp]),
+    "tnl_sample_planes_forward": (_int, [_vp, _vp, _u32, _u32, _u32, _f32, _int, _vp, _vp, _vp, _vp]),
+    "tnl_sample_planes_backward": (_int, [_vp, _vp, _u32, _u32, _u32, _f32, _int, _vp, _vp, _vp, _vp]),
+    "tnl_cell_sort_workspace": (_sz, [_u32, _u32]),
+    "tnl_cell_sort": (_int, [_vp, _u32, _vp, _f32, _u32, _vp, _vp, _sz, _vp]),
     "tnl_mlp_packed_bytes": (_sz, [_DP]),
     "tnl_mlp_pack_weights": (_int, [_DP, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tnl_mlp_forward": (_int, [_DP, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
@@ -96,7 +98,7 @@ def check(rc, what):
 
 
 # number of kernels each ABI call launches (for the launch counter the benchmark reports)
-KERNELS_PER_CALL = {"tnl_march_rays_train": 5, "tnl_compact_alive": 3}
+KERNELS_PER_CALL = {"tnl_march_rays_train": 5, "tnl_compact_alive": 3, "tnl_cell_sort": 3}
 launch_count = 0
 _profile = None  # when enabled: name -> list of (start_event, end_event, scalar_args)
 

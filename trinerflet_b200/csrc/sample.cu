@@ -60,14 +60,16 @@ __device__ __forceinline__ void plane_coords(const float* __restrict__ xyz, uint
 
 __global__ void __launch_bounds__(256)
 k_sample_fwd(const float* __restrict__ planes, const float* __restrict__ xyz, uint32_t M, int R, int C, float inv_bound,
-             int fp16_coords, const int32_t* __restrict__ n_valid, float* __restrict__ feat) {
+             int fp16_coords, const int32_t* __restrict__ n_valid, const int32_t* __restrict__ perm,
+             float* __restrict__ feat) {
     const int cq_per = C >> 2;
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t total = (uint64_t)M * 3 * cq_per;
     if (idx >= total) return;
     const int cq = (int)(idx % cq_per);
     const int p = (int)((idx / cq_per) % 3);
-    const uint32_t m = (uint32_t)(idx / ((uint64_t)3 * cq_per));
+    uint32_t m = (uint32_t)(idx / ((uint64_t)3 * cq_per));
+    if (perm) m = (uint32_t)__ldg(perm + m);
     float4* dst = reinterpret_cast<float4*>(feat + (size_t)m * 3 * C + (size_t)p * C) + cq;
     if (n_valid && (int32_t)m >= *n_valid) {
         *dst = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -106,14 +108,16 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v, float w) {
 
 __global__ void __launch_bounds__(256)
 k_sample_bwd(const float* __restrict__ g_feat, const float* __restrict__ xyz, uint32_t M, int R, int C, float inv_bound,
-             int fp16_coords, const int32_t* __restrict__ n_valid, float* __restrict__ g_planes) {
+             int fp16_coords, const int32_t* __restrict__ n_valid, const int32_t* __restrict__ perm,
+             float* __restrict__ g_planes) {
     const int cq_per = C >> 2;
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t total = (uint64_t)M * 3 * cq_per;
     if (idx >= total) return;
     const int cq = (int)(idx % cq_per);
     const int p = (int)((idx / cq_per) % 3);
-    const uint32_t m = (uint32_t)(idx / ((uint64_t)3 * cq_per));
+    uint32_t m = (uint32_t)(idx / ((uint64_t)3 * cq_per));
+    if (perm) m = (uint32_t)__ldg(perm + m);
     if (n_valid && (int32_t)m >= *n_valid) return;
     const float4 g = __ldg(reinterpret_cast<const float4*>(g_feat + (size_t)m * 3 * C + (size_t)p * C) + cq);
     if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) return;  // adding zeros is a no-op
@@ -135,26 +139,28 @@ using namespace tnl;
 extern "C" {
 
 int tnl_sample_planes_forward(const float* planes, const float* xyz, uint32_t M, uint32_t R, uint32_t C, float inv_bound,
-                              int fp16_coords, const int32_t* n_valid, float* feat, tnl_stream_t stream) {
+                              int fp16_coords, const int32_t* n_valid, const int32_t* perm, float* feat,
+                              tnl_stream_t stream) {
     if (M == 0) return 0;
     TNL_ARG_CHECK(planes && xyz && feat, "null pointer");
     TNL_ARG_CHECK(C >= 4 && C % 4 == 0 && R >= 2, "C must be a multiple of 4, R >= 2");
     TNL_ARG_CHECK(((uintptr_t)planes & 15) == 0 && ((uintptr_t)feat & 15) == 0, "planes/feat must be 16-byte aligned");
     const uint64_t total = (uint64_t)M * 3 * (C / 4);
     k_sample_fwd<<<(unsigned)ceil_div(total, (uint64_t)256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        planes, xyz, M, (int)R, (int)C, inv_bound, fp16_coords, n_valid, feat);
+        planes, xyz, M, (int)R, (int)C, inv_bound, fp16_coords, n_valid, perm, feat);
     return finish_launch("sample_planes_forward");
 }
 
 int tnl_sample_planes_backward(const float* g_feat, const float* xyz, uint32_t M, uint32_t R, uint32_t C, float inv_bound,
-                               int fp16_coords, const int32_t* n_valid, float* g_planes, tnl_stream_t stream) {
+                               int fp16_coords, const int32_t* n_valid, const int32_t* perm, float* g_planes,
+                               tnl_stream_t stream) {
     if (M == 0) return 0;
     TNL_ARG_CHECK(g_feat && xyz && g_planes, "null pointer");
     TNL_ARG_CHECK(C >= 4 && C % 4 == 0 && R >= 2, "C must be a multiple of 4, R >= 2");
     TNL_ARG_CHECK(((uintptr_t)g_planes & 15) == 0 && ((uintptr_t)g_feat & 15) == 0, "g_planes/g_feat must be 16-byte aligned");
     const uint64_t total = (uint64_t)M * 3 * (C / 4);
     k_sample_bwd<<<(unsigned)ceil_div(total, (uint64_t)256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        g_feat, xyz, M, (int)R, (int)C, inv_bound, fp16_coords, n_valid, g_planes);
+        g_feat, xyz, M, (int)R, (int)C, inv_bound, fp16_coords, n_valid, perm, g_planes);
     return finish_launch("sample_planes_backward");
 }
 

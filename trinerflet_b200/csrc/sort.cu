@@ -1,0 +1,128 @@
+// Spatial binning of the step's sample points (counting sort by 3-D cell) -- sm_100a.
+//
+// Why: the reference evaluates samples in marching order, i.e. ray by ray for randomly drawn pixels, so
+// consecutive warps touch unrelated plane texels: almost every 128-byte texel fetched by the gather and every
+// read-modify-write of the gradient scatter misses the 126 MB L2 (ncu: k_sample_bwd moves 9 GB through DRAM for
+// 0.3 GB of distinct gradient texels).  Visiting the same points in the order of a coarse 3-D grid makes the
+// projections on all three planes coherent at once, so texels are fetched from DRAM about once per step.
+// Per-point results are unchanged (every point is still evaluated exactly once; outputs are written back to the
+// point's original row), only the order of floating-point accumulation into gradients differs.
+//
+// perm[i] = original row of the i-th point in cell order; cells = G^3 grid over [-bound, bound]^3 in Morton order,
+// rows >= *n_valid (padding) are placed last in their original order.
+#include "common.cuh"
+
+namespace tnl {
+
+__device__ __forceinline__ uint32_t spread3s(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+__device__ __forceinline__ uint32_t cell_key(const float* __restrict__ xyz, uint32_t m, float inv_bound, int G) {
+    uint32_t c[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float u = fminf(fmaxf((__ldg(xyz + 3 * (size_t)m + a) * inv_bound + 1.0f) * 0.5f, 0.0f), 1.0f);
+        c[a] = min((uint32_t)(u * (float)G), (uint32_t)(G - 1));
+    }
+    return spread3s(c[0]) | (spread3s(c[1]) << 1) | (spread3s(c[2]) << 2);
+}
+
+// pass 1: histogram (bins = G^3 + 1; the last bin collects padding rows)
+__global__ void k_cell_hist(const float* __restrict__ xyz, uint32_t M, const int32_t* __restrict__ n_valid, float inv_bound,
+                            int G, uint32_t* __restrict__ hist, uint32_t* __restrict__ keys) {
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const uint32_t nv = n_valid ? (uint32_t)max(*n_valid, 0) : M;
+    const uint32_t key = m < nv ? cell_key(xyz, m, inv_bound, G) : (uint32_t)(G * G * G);
+    keys[m] = key;
+    atomicAdd(hist + key, 1u);
+}
+
+// pass 2 (single block): exclusive scan of the histogram in place
+__global__ void k_cell_scan(uint32_t* __restrict__ hist, uint32_t nbins) {
+    __shared__ uint32_t sm[33];
+    __shared__ uint32_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < nbins; base += blockDim.x * 4) {
+        // each thread scans 4 consecutive bins
+        const uint32_t i0 = base + threadIdx.x * 4;
+        uint32_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (i0 + j < nbins) ? hist[i0 + j] : 0u;
+        const uint32_t tsum = v[0] + v[1] + v[2] + v[3];
+        uint32_t incl = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) sm[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = (lane < (int)(blockDim.x >> 5)) ? sm[lane] : 0u, wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += u;
+            }
+            sm[lane] = wi - w;
+            if (lane == 31) sm[32] = wi;
+        }
+        __syncthreads();
+        uint32_t ex = carry_s + sm[warp] + incl - tsum;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (i0 + j < nbins) hist[i0 + j] = ex;
+            ex += v[j];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s += sm[32];
+        __syncthreads();
+    }
+}
+
+// pass 3: scatter row ids into their bins
+__global__ void k_cell_scatter(const uint32_t* __restrict__ keys, uint32_t M, uint32_t* __restrict__ cursor,
+                               int32_t* __restrict__ perm) {
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const uint32_t slot = atomicAdd(cursor + keys[m], 1u);
+    perm[slot] = (int32_t)m;
+}
+
+}  // namespace tnl
+
+using namespace tnl;
+
+extern "C" {
+
+size_t tnl_cell_sort_workspace(uint32_t M, uint32_t G) { return sizeof(uint32_t) * ((size_t)G * G * G + 1 + M); }
+
+int tnl_cell_sort(const float* xyz, uint32_t M, const int32_t* n_valid, float inv_bound, uint32_t G, int32_t* perm,
+                  void* workspace, size_t workspace_bytes, tnl_stream_t stream) {
+    if (M == 0) return 0;
+    TNL_ARG_CHECK(xyz && perm, "null pointer");
+    TNL_ARG_CHECK(G >= 2 && G <= 256, "G must be in [2, 256]");
+    if (workspace == nullptr || workspace_bytes < tnl_cell_sort_workspace(M, G)) {
+        set_error("cell_sort: workspace too small");
+        return TNL_ERR_WORKSPACE;
+    }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const uint32_t nbins = G * G * G + 1;
+    uint32_t* hist = static_cast<uint32_t*>(workspace);
+    uint32_t* keys = hist + nbins;
+    cudaMemsetAsync(hist, 0, sizeof(uint32_t) * nbins, s);
+    k_cell_hist<<<ceil_div(M, 256u), 256, 0, s>>>(xyz, M, n_valid, inv_bound, (int)G, hist, keys);
+    k_cell_scan<<<1, 1024, 0, s>>>(hist, nbins);
+    k_cell_scatter<<<ceil_div(M, 256u), 256, 0, s>>>(keys, M, hist, perm);
+    return finish_launch("cell_sort");
+}
+
+}  // extern "C"

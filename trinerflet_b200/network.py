@@ -132,9 +132,17 @@ class NeRFNetwork(NeRFRenderer):
         return (torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.float16
                 and fused_dims_supported(self.in_dim, self.hidden_dim, self.hidden_dim_color, need_grad))
 
+    # visit the samples of a training step in the order of a coarse 3-D grid (L2 locality of the plane gather /
+    # gradient scatter, see csrc/sort.cu); per-point results do not depend on it
+    spatial_sort_min_points = 1 << 18
+
     def forward(self, x, d, n_valid=None):
         """x [M,3] in [-bound, bound], d [M,3] unit dirs -> sigma [M] fp32, color [M,3]."""
-        feat = self.encoder(x, bound=self.bound, n_valid=n_valid)
+        perm = None
+        if x.is_cuda and x.shape[0] >= self.spatial_sort_min_points and torch.is_grad_enabled():
+            from .triplane_encoder import cell_sort
+            perm = cell_sort(x, self.bound, n_valid, 64)
+        feat = self.encoder(x, bound=self.bound, n_valid=n_valid, perm=perm)
         need_grad = torch.is_grad_enabled() and any(w.requires_grad for w in self._weights())
         if self._fused(need_grad):
             return _FieldMLP.apply(feat, d, n_valid, *self._weights())

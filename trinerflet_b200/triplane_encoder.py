@@ -156,7 +156,7 @@ def _inv_bound(bound):
 
 class _SamplePlanes(Function):
     @staticmethod
-    def forward(ctx, planes, coords, bound, fp16_coords, n_valid):
+    def forward(ctx, planes, coords, bound, fp16_coords, n_valid, perm=None):
         _require_cuda_f32(planes, "planes")
         planes_cl = to_cl_planes(planes.detach())
         coords = coords.detach().contiguous().float()
@@ -165,28 +165,40 @@ class _SamplePlanes(Function):
         feat = torch.empty(M, 3 * C, device=planes.device, dtype=torch.float32)
         inv = _inv_bound(bound)
         call("tnl_sample_planes_forward", ptr(planes_cl), ptr(coords), M, R, C, inv, int(bool(fp16_coords)),
-             ptr(n_valid), ptr(feat), stream())
-        ctx.save_for_backward(coords, n_valid if n_valid is not None else torch.empty(0))
-        ctx.meta = (M, R, C, inv, int(bool(fp16_coords)), n_valid is not None)
+             ptr(n_valid), ptr(perm), ptr(feat), stream())
+        ctx.save_for_backward(coords, n_valid if n_valid is not None else torch.empty(0),
+                              perm if perm is not None else torch.empty(0))
+        ctx.meta = (M, R, C, inv, int(bool(fp16_coords)), n_valid is not None, perm is not None)
         return feat
 
     @staticmethod
     def backward(ctx, g_feat):
-        coords, n_valid = ctx.saved_tensors
-        M, R, C, inv, fp16_coords, has_nv = ctx.meta
+        coords, n_valid, perm = ctx.saved_tensors
+        M, R, C, inv, fp16_coords, has_nv, has_perm = ctx.meta
         g_feat = g_feat.contiguous().float()
         g_planes = cl_empty_planes(C, R, device=g_feat.device, zero=True)
         call("tnl_sample_planes_backward", ptr(g_feat), ptr(coords), M, R, C, inv, fp16_coords,
-             ptr(n_valid) if has_nv else None, ptr(g_planes), stream())
-        return g_planes, None, None, None, None
+             ptr(n_valid) if has_nv else None, ptr(perm) if has_perm else None, ptr(g_planes), stream())
+        return g_planes, None, None, None, None, None
 
 
-def sample_planes(planes, coords, bound, fp16_coords=None, n_valid=None):
+def cell_sort(coords, bound, n_valid=None, G=64):
+    """perm [M] int32: visit order of the points by a G^3 Morton grid (tnl_cell_sort)."""
+    from . import _lib
+    coords = coords.detach().contiguous().float()
+    M = coords.shape[0]
+    perm = torch.empty(M, dtype=torch.int32, device=coords.device)
+    ws = torch.empty(max(int(_lib.load().tnl_cell_sort_workspace(M, G)), 16), dtype=torch.uint8, device=coords.device)
+    call("tnl_cell_sort", ptr(coords), M, ptr(n_valid), _inv_bound(bound), G, ptr(perm), ptr(ws), ws.numel(), stream())
+    return perm
+
+
+def sample_planes(planes, coords, bound, fp16_coords=None, n_valid=None, perm=None):
     """planes logical [3,C,R,R] -> features [M, 3C] (fp32). fp16_coords=None follows the autocast state, as the
     reference's projection matmul does."""
     if fp16_coords is None:
         fp16_coords = torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.float16
-    return _SamplePlanes.apply(planes, coords, float(bound), bool(fp16_coords), n_valid)
+    return _SamplePlanes.apply(planes, coords, float(bound), bool(fp16_coords), n_valid, perm)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -340,9 +352,9 @@ class TriPlaneVolume(nn.Module):
         feat = sample_planes(plane_features, coordinates, lbound, n_valid=n_valid)
         return feat.view(feat.shape[0], 3, self.number_of_features)
 
-    def forward(self, coordinates, bound, n_valid=None):
+    def forward(self, coordinates, bound, n_valid=None, perm=None):
         """coordinates [M,3] in [-bound, bound] -> features [M, 3C] (index p*C + c), fp32."""
-        return sample_planes(self.get_planes(), coordinates, bound, n_valid=n_valid)
+        return sample_planes(self.get_planes(), coordinates, bound, n_valid=n_valid, perm=perm)
 
     # -- checkpoints: accept reference (NCHW-contiguous) tensors, keep channels-last storage -------------
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
