@@ -196,7 +196,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     _lib.load()
 
     C, R, S = cfg["C"], cfg["R"], cfg["S"]
@@ -289,6 +290,9 @@ def main():
     line = None
     if rank == 0:
         # ---- per-kernel times (CUDA events around every ABI call on the launching stream) ----
+        ts.world_size = 1          # rank-0-only section: no collectives from here on
+        if ts.reducer is not None:
+            ts.reducer.world_size = 1
         _lib.profile_start()
         nprof = min(args.steps, 5)
         for i in range(nprof):
@@ -313,7 +317,8 @@ def main():
                     "frac": round(kernels[dom]["achieved_GBps"] / peak, 4), "traffic": None, "peak_source": peak_src,
                     "launch_ms": round(kernels[dom]["ms_per_step"] / kernels[dom]["calls_per_step"], 4)}
         Bstep = step_bytes(P, C, m_valid, n_rays)
-        extras = {"M_samples_per_step": m_valid, "B_step_GB": round(Bstep / 1e9, 3),
+        extras = {"sparse_allreduce_tile_fraction": (round(ts.reducer.fraction, 4) if ts.reducer is not None else None),
+                  "M_samples_per_step": m_valid, "B_step_GB": round(Bstep / 1e9, 3),
                   "step_achieved_GBps": round(Bstep / 1e9 / (ms_per_step * 1e-3), 1),
                   "step_frac_of_hbm_roofline": round(Bstep / 1e9 / (ms_per_step * 1e-3) / peak, 4), "kernels": kernels}
         # optimizer + density-grid refresh, outside the metric

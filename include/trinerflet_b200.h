@@ -172,6 +172,18 @@ int tnl_grid_cell_positions(const int32_t* indices, uint32_t n, uint32_t H, floa
  * full sweep (indices == NULL => idx = i) or scattered cells; see DESIGN.md for the tmp_grid semantics. */
 int tnl_grid_ema_update(float* grid, const float* tmp_grid, uint32_t n, float decay, tnl_stream_t stream);
 
+/* ------------------------------------------------------------------ multi-GPU gradient exchange ---- */
+/* flags [3][R/T][R/T] (uint8): 1 where a tile of T x T texels can receive plane gradient, i.e. lies under the projection
+ * of an occupied density-grid cell (+ margin texels).  Deterministic function of the bitfield: identical on all ranks. */
+int tnl_mark_dirty_tiles(const uint8_t* bitfield, uint32_t cascade, uint32_t H, float bound, uint32_t R, uint32_t T,
+                         uint32_t margin, uint8_t* flags, tnl_stream_t stream);
+/* gather / scatter the listed tiles between planes [3][R][R][C] and a compact buffer [n_tiles][T][T][C]
+ * (tile id = (p * R/T + ty) * R/T + tx); unpack multiplies by `scale` (1/world_size for an average). */
+int tnl_tiles_pack(const float* planes, const int32_t* tile_ids, uint32_t n_tiles, uint32_t R, uint32_t C, uint32_t T,
+                   float* compact, tnl_stream_t stream);
+int tnl_tiles_unpack(const float* compact, const int32_t* tile_ids, uint32_t n_tiles, uint32_t R, uint32_t C, uint32_t T,
+                     float scale, float* planes, tnl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

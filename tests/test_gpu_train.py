@@ -109,3 +109,24 @@ def test_inference_render_and_sharding_helpers():
     # ray tiles are independent: rendering shards separately reproduces the full frame (chunk schedules differ,
     # so sample positions may move by float noise of the accumulated t; fp16 field tolerance applies)
     assert (torch.cat(parts) - img).abs().max().item() <= 5e-3
+
+
+def test_sparse_plane_gradient_exchange_single_rank():
+    """The ray-sharded code path (graph cut at the planes + dirty-tile pack / all-reduce / unpack) run with one rank must
+    reproduce the plain single-backward gradients; check=True asserts that no gradient lies outside the dirty tiles."""
+    from trinerflet_b200 import parallel, scene, trainer
+    sc = scene.make_scene()
+    ro, rd, tgt = (t.cuda() for t in scene.sample_batch(sc, 4096, torch.Generator().manual_seed(3)))
+    grads = []
+    for sparse in (False, True):
+        net = _model("tiny")
+        ts = trainer.TrainStep(net, trainer.default_opt(), None, world_size=1)
+        if sparse:
+            ts.reducer = parallel.PlaneGradReducer(net, 1, tile=32, check=True).refresh()
+            assert 0.02 < ts.reducer.fraction < 0.9
+        torch.manual_seed(0)
+        loss = ts.forward_backward(ro, rd, tgt, update_grid=False)
+        grads.append((float(loss), [p.grad.clone() for p in net.parameters()]))
+    assert abs(grads[0][0] - grads[1][0]) <= 1e-6 * abs(grads[0][0])
+    for a, b in zip(grads[0][1], grads[1][1]):
+        assert rel_l2(a, b) <= 1e-5

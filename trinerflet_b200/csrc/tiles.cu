@@ -1,0 +1,112 @@
+// Dirty-tile bookkeeping for the multi-GPU gradient exchange -- sm_100a.
+//
+// In ray-sharded data parallelism every rank must sum the gradient of the three feature planes (P bytes, 1.6 GB for
+// base-light).  A sample only touches texels under the projection of an occupied density-grid cell, so the plane
+// gradient is exactly zero outside those projections (about 20-25 % of the plane area for a centred object).  All ranks
+// hold the same density bitfield, so they derive the same "dirty" tile set without communicating; the exchange then
+// packs those tiles into a compact buffer, all-reduces it with NCCL and scatters it back.  No reference counterpart
+// (the reference is single-GPU).
+#include "common.cuh"
+
+namespace tnl {
+
+__device__ __forceinline__ uint32_t compact3t(uint32_t x) {
+    x &= 0x49249249u;
+    x = (x | (x >> 2)) & 0xc30c30c3u;
+    x = (x | (x >> 4)) & 0x0f00f00fu;
+    x = (x | (x >> 8)) & 0xff0000ffu;
+    x = (x | (x >> 16)) & 0x0000ffffu;
+    return x;
+}
+
+// one thread per density-grid cell: an occupied cell of cascade `level` covers, per axis,
+//   p in [(2n/H - 1) * mb, (2(n+1)/H - 1) * mb],  mb = min(2^level, bound)       (raymarching.cu:370-376 inverted)
+// a sample at p reads/writes texels floor(ix), floor(ix)+1 with ix = (p/bound + 1)/2 * (R-1) (+- fp16 rounding of p/bound);
+// `margin` texels of slack cover the rounding and the bilinear footprint.
+__global__ void k_mark_dirty_tiles(const uint8_t* __restrict__ bitfield, uint32_t cascade, uint32_t H, float bound, int R, int T,
+                                   int margin, uint8_t* __restrict__ flags) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t H3 = H * H * H;
+    if (i >= cascade * H3) return;
+    if (!((bitfield[i >> 3] >> (i & 7)) & 1)) return;
+    const uint32_t level = i / H3, mort = i % H3;
+    const float mb = fminf(scalbnf(1.0f, (int)level), bound);
+    const uint32_t c[3] = {compact3t(mort), compact3t(mort >> 1), compact3t(mort >> 2)};
+    int lo[3], hi[3];
+    const int nt = R / T;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float p0 = (2.0f * (float)c[a] / (float)H - 1.0f) * mb, p1 = (2.0f * (float)(c[a] + 1) / (float)H - 1.0f) * mb;
+        const float x0 = (p0 / bound + 1.0f) * 0.5f * (float)(R - 1), x1 = (p1 / bound + 1.0f) * 0.5f * (float)(R - 1);
+        lo[a] = max(0, (int)floorf(x0) - margin) / T;
+        hi[a] = min(R - 1, (int)floorf(x1) + 1 + margin) / T;
+    }
+    // plane 0: (gx, gy) = (x, z); plane 1: (x, y); plane 2: (y, z); gx indexes W (columns), gy indexes H (rows)
+    const int ax[3][2] = {{0, 2}, {0, 1}, {1, 2}};
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+        for (int ty = lo[ax[p][1]]; ty <= hi[ax[p][1]]; ++ty)
+            for (int tx = lo[ax[p][0]]; tx <= hi[ax[p][0]]; ++tx) flags[(p * nt + ty) * nt + tx] = 1;
+}
+
+// tile id = (p * nt + ty) * nt + tx ; compact layout [n][T][T][C]; one CTA per (tile, row)
+template <bool PACK>
+__global__ void __launch_bounds__(256)
+k_tiles_copy(float* __restrict__ planes, float* __restrict__ compact, const int32_t* __restrict__ tile_ids, int R, int C, int T,
+             float scale) {
+    const int tile = blockIdx.x, row = blockIdx.y;
+    const int id = tile_ids[tile];
+    const int nt = R / T;
+    const int p = id / (nt * nt), ty = (id / nt) % nt, tx = id % nt;
+    float4* src = reinterpret_cast<float4*>(planes + (((size_t)p * R + (size_t)ty * T + row) * R + (size_t)tx * T) * C);
+    float4* dst = reinterpret_cast<float4*>(compact + (((size_t)tile * T + row) * T) * C);
+    const int n4 = T * C / 4;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+        if (PACK) dst[i] = src[i];
+        else {
+            float4 v = dst[i];
+            v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+            src[i] = v;
+        }
+    }
+}
+
+}  // namespace tnl
+
+using namespace tnl;
+
+extern "C" {
+
+int tnl_mark_dirty_tiles(const uint8_t* bitfield, uint32_t cascade, uint32_t H, float bound, uint32_t R, uint32_t T,
+                         uint32_t margin, uint8_t* flags, tnl_stream_t stream) {
+    TNL_ARG_CHECK(bitfield && flags, "null pointer");
+    TNL_ARG_CHECK(T >= 4 && R % T == 0, "tile size must divide R");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const uint32_t nt = R / T;
+    cudaMemsetAsync(flags, 0, 3 * nt * nt, s);
+    const uint32_t n = cascade * H * H * H;
+    k_mark_dirty_tiles<<<ceil_div(n, 256u), 256, 0, s>>>(bitfield, cascade, H, bound, (int)R, (int)T, (int)margin, flags);
+    return finish_launch("mark_dirty_tiles");
+}
+
+int tnl_tiles_pack(const float* planes, const int32_t* tile_ids, uint32_t n_tiles, uint32_t R, uint32_t C, uint32_t T,
+                   float* compact, tnl_stream_t stream) {
+    if (n_tiles == 0) return 0;
+    TNL_ARG_CHECK(planes && tile_ids && compact, "null pointer");
+    TNL_ARG_CHECK(R % T == 0 && (T * C) % 4 == 0, "bad tile geometry");
+    k_tiles_copy<true><<<dim3(n_tiles, T), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        const_cast<float*>(planes), compact, tile_ids, (int)R, (int)C, (int)T, 1.0f);
+    return finish_launch("tiles_pack");
+}
+
+int tnl_tiles_unpack(const float* compact, const int32_t* tile_ids, uint32_t n_tiles, uint32_t R, uint32_t C, uint32_t T,
+                     float scale, float* planes, tnl_stream_t stream) {
+    if (n_tiles == 0) return 0;
+    TNL_ARG_CHECK(planes && tile_ids && compact, "null pointer");
+    TNL_ARG_CHECK(R % T == 0 && (T * C) % 4 == 0, "bad tile geometry");
+    k_tiles_copy<false><<<dim3(n_tiles, T), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        planes, const_cast<float*>(compact), tile_ids, (int)R, (int)C, (int)T, scale);
+    return finish_launch("tiles_unpack");
+}
+
+}  // extern "C"

@@ -54,6 +54,70 @@ def allreduce_gradients(model, world_size, average=True):
             off += n
 
 
+class PlaneGradReducer:
+    """All-reduce of the feature-plane gradient restricted to the tiles that can be non-zero (csrc/tiles.cu).
+
+    Every rank derives the same dirty-tile list from its (identical) density bitfield, packs those tiles of its local
+    plane gradient into a compact [n_tiles, T, T, C] buffer, all-reduces that buffer (NCCL over NVLink) and scatters the
+    average back.  For a centred object this moves ~20-25 % of the P bytes a dense all-reduce would.  `refresh()` must be
+    called whenever the bitfield changes (after update_extra_state); it costs one small D2H copy of the tile flags."""
+
+    def __init__(self, model, world_size, tile=32, margin=2, check=False):
+        self.model, self.world_size, self.tile, self.margin, self.check = model, world_size, tile, margin, check
+        self.tile_ids = None
+        self.compact = None
+
+    def refresh(self):
+        from ._lib import call, ptr, stream
+        m = self.model
+        R, C = m.encoder.plane_resolution, m.encoder.number_of_features
+        T = self.tile
+        nt = R // T
+        flags = torch.empty(3 * nt * nt, dtype=torch.uint8, device=m.density_bitfield.device)
+        call("tnl_mark_dirty_tiles", ptr(m.density_bitfield), m.cascade, m.grid_size, float(m.bound), R, T, self.margin,
+             ptr(flags), stream())
+        self.tile_ids = torch.nonzero(flags).squeeze(-1).int().contiguous()          # one sync, once per grid refresh
+        self.n_tiles = int(self.tile_ids.shape[0])
+        self.compact = torch.empty(max(self.n_tiles, 1) * T * T * C, dtype=torch.float32, device=flags.device)
+        self.fraction = self.n_tiles / float(3 * nt * nt)
+        return self
+
+    def reduce_(self, g_planes):
+        """In place: g_planes (logical [3,C,R,R], channels-last storage) <- average over ranks."""
+        from ._lib import call, ptr, stream
+        if self.tile_ids is None:
+            self.refresh()
+        R, C, T = g_planes.shape[2], g_planes.shape[1], self.tile
+        dense = _dense_view(g_planes)
+        if self.check:   # debug: nothing outside the dirty tiles may be non-zero
+            total = dense.abs().sum()
+        call("tnl_tiles_pack", ptr(dense), ptr(self.tile_ids), self.n_tiles, R, C, T, ptr(self.compact), stream())
+        if self.check:
+            inside = self.compact[: self.n_tiles * T * T * C].abs().sum()
+            if not torch.allclose(total, inside, rtol=1e-4):
+                raise RuntimeError("PlaneGradReducer: plane gradient found outside the dirty tiles")
+        if self.world_size > 1 and dist.is_initialized():
+            dist.all_reduce(self.compact, op=dist.ReduceOp.SUM)
+        call("tnl_tiles_unpack", ptr(self.compact), ptr(self.tile_ids), self.n_tiles, R, C, T, 1.0 / self.world_size,
+             ptr(dense), stream())
+        return g_planes
+
+
+def allreduce_small(params, world_size):
+    """One bucketed all-reduce (average) for a list of small parameter gradients (the MLP heads)."""
+    grads = [_dense_view(p.grad) for p in params if p.grad is not None]
+    if world_size <= 1 or not dist.is_initialized() or not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.div_(world_size)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+
+
 def gather_frame(local, n_total, rank, world_size):
     """Final gather of a ray-tile-sharded render: `local` [n_local, ...] -> [n_total, ...] on every rank."""
     if world_size <= 1 or not dist.is_initialized():

@@ -39,7 +39,7 @@ def wavelet_regulariser(encoder, lam, fused=True):
 
 
 class TrainStep:
-    def __init__(self, model, opt=None, optimizer=None, world_size=1):
+    def __init__(self, model, opt=None, optimizer=None, world_size=1, sparse_allreduce=True, check_sparse=False):
         self.model = model
         self.opt = opt or default_opt()
         self.optimizer = optimizer
@@ -47,6 +47,19 @@ class TrainStep:
         self.global_step = 0
         self.world_size = world_size
         self.criterion = torch.nn.MSELoss(reduction='none')
+        # N > 1: the plane gradient is exchanged between the render backward and the IDWT backward, dirty tiles only
+        self.reducer = parallel.PlaneGradReducer(model, world_size, check=check_sparse) if (world_size > 1 and sparse_allreduce) else None
+        self._graphs = None
+
+    # ---- the three segments of a step ---------------------------------------------------------------------------------
+    def _render_loss(self, rays_o, rays_d, images):
+        model, opt = self.model, self.opt
+        with torch.autocast("cuda", dtype=torch.float16, enabled=opt.fp16):
+            bg = torch.zeros_like(images) + opt.background_color
+            out = model.render(rays_o.unsqueeze(0), rays_d.unsqueeze(0), staged=False, bg_color=bg, perturb=True,
+                               force_all_rays=False, dt_gamma=opt.dt_gamma, max_steps=opt.max_steps)
+            pred = out['image'].view(-1, 3)
+            return self.criterion(pred, images).mean(-1).mean()
 
     def forward_backward(self, rays_o, rays_d, images, update_grid=None):
         """rays_o/rays_d/images: [N,3] device tensors (this rank's shard). Returns the detached loss tensor."""
@@ -54,35 +67,69 @@ class TrainStep:
         enc = model.encoder
         model.train()
         enc.reset_cahce()
-        enc.get_planes()
+        planes = enc.get_planes()
         do_update = (self.global_step % opt.update_extra_interval == 0) if update_grid is None else update_grid
         if do_update:
             with torch.autocast("cuda", dtype=torch.float16, enabled=opt.fp16):
                 model.update_extra_state()
-        with torch.autocast("cuda", dtype=torch.float16, enabled=opt.fp16):
-            bg = torch.zeros_like(images) + opt.background_color
-            out = model.render(rays_o.unsqueeze(0), rays_d.unsqueeze(0), staged=False, bg_color=bg, perturb=True,
-                               force_all_rays=False, dt_gamma=opt.dt_gamma, max_steps=opt.max_steps)
-            pred = out['image'].view(-1, 3)
-            loss = self.criterion(pred, images).mean(-1).mean()
-            reg = wavelet_regulariser(enc, opt.wavelet_regularization, getattr(opt, "fused_regulariser", True))
-            if reg is not None:
-                loss = loss + reg
-            enc.reset_cahce()
-            self.scaler.scale(loss).backward()
-        if self.world_size > 1 and not torch.cuda.is_current_stream_capturing():
-            parallel.allreduce_gradients(model, self.world_size)
+            if self.reducer is not None:
+                self.reducer.refresh()
+        capturing = torch.cuda.is_current_stream_capturing()
+        if self.reducer is None:
+            # single GPU (or dense exchange): one backward through render + IDWT
+            with torch.autocast("cuda", dtype=torch.float16, enabled=opt.fp16):
+                loss = self._render_loss(rays_o, rays_d, images)
+                reg = wavelet_regulariser(enc, opt.wavelet_regularization, getattr(opt, "fused_regulariser", True))
+                if reg is not None:
+                    loss = loss + reg
+                enc.reset_cahce()
+                self.scaler.scale(loss).backward()
+            if self.world_size > 1 and not capturing:
+                parallel.allreduce_gradients(model, self.world_size)
+        else:
+            # ray-sharded DP: cut the graph at the planes, exchange the (sparse) plane gradient, then run the IDWT backward
+            leaf = planes.detach().requires_grad_(True)
+            enc.last_used_planes = leaf
+            with torch.autocast("cuda", dtype=torch.float16, enabled=opt.fp16):
+                loss = self._render_loss(rays_o, rays_d, images)
+                reg = wavelet_regulariser(enc, opt.wavelet_regularization, True)
+                enc.reset_cahce()
+                self.scaler.scale(loss).backward()                    # -> leaf.grad and the MLP gradients of this shard
+            self._cut = (planes, leaf, reg)
+            if not capturing:
+                self._exchange_and_finish()
+            loss = loss.detach() + (reg.detach() if reg is not None else 0.0)
         self.global_step += 1
         return loss.detach()
 
-    # ---- CUDA-graph mode: the whole fwd+bwd of a steady-state step is one graph launch ------------------------------
+    def _exchange(self):
+        planes, leaf, reg = self._cut
+        self.reducer.reduce_(leaf.grad)
+        mlp = [p for n, p in self.model.named_parameters() if not n.startswith("encoder.")]
+        parallel.allreduce_small(mlp, self.world_size)
+
+    def _idwt_backward(self):
+        planes, leaf, reg = self._cut
+        if reg is not None:   # identical on every rank: added once, after the exchange
+            torch.autograd.backward([planes, self.scaler.scale(reg)], [leaf.grad, None])
+        else:
+            torch.autograd.backward([planes], [leaf.grad])
+
+    def _exchange_and_finish(self):
+        self._exchange()
+        self._idwt_backward()
+        self._cut = None   # drop the autograd graph (and the AccumulateGrad nodes it keeps alive) of this step
+
+    # ---- CUDA-graph mode: a steady-state step is one (N = 1) or two (N > 1, NCCL in between) graph launches ----------
     def capture(self, rays_o, rays_d, images, warmup=3):
-        """Capture forward_backward (steady state: mean_count > 0, no density-grid refresh) into a CUDA graph.
+        """Capture forward_backward (steady state: mean_count > 0, no density-grid refresh) into CUDA graphs.
         Inputs are copied into static buffers before each replay; parameter gradients live in the graph's memory pool
         and are overwritten by every replay (equivalent to zero_grad(set_to_none=True) + backward).  The step counter
         ring slot is the one current at capture time."""
         assert self.model.mean_count > 0, "capture needs the steady state (mean_count > 0): run a few eager steps first"
         self._static = tuple(t.clone() for t in (rays_o, rays_d, images))
+        if self.reducer is not None:
+            self.reducer.refresh()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -91,19 +138,30 @@ class TrainStep:
                 self.forward_backward(*self._static, update_grid=False)
         torch.cuda.current_stream().wait_stream(side)
         self.model.zero_grad(set_to_none=True)
-        slot = self.model.local_step
-        self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
+        self._cut = None
+        # both captures run on the same side stream: the autograd nodes of the IDWT (created while capturing A) execute
+        # on the stream they were recorded on, which must be the stream that is capturing B
+        gA = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gA, stream=side):
             self._static_loss = self.forward_backward(*self._static, update_grid=False)
-        self._graph_slot = slot
+        gB = None
+        if self.reducer is not None:
+            gB = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gB, pool=gA.pool(), stream=side):
+                self._idwt_backward()
+        self._graphs = (gA, gB)
         return self
 
     def replay(self, rays_o, rays_d, images):
         """One captured fwd+bwd on new inputs (device or pinned-host tensors); returns the (static) loss tensor."""
         for dst, src in zip(self._static, (rays_o, rays_d, images)):
             dst.copy_(src, non_blocking=True)
-        self._graph.replay()
-        if self.world_size > 1:
+        gA, gB = self._graphs
+        gA.replay()
+        if gB is not None:
+            self._exchange()
+            gB.replay()
+        elif self.world_size > 1:
             parallel.allreduce_gradients(self.model, self.world_size)
         self.global_step += 1
         return self._static_loss
