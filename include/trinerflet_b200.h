@@ -107,9 +107,11 @@ int tnl_idwt_level_forward(const float* x, const float* yh, float* out, uint32_t
 /* Exact adjoint of the above: g_out [3][2n][2n][C] -> g_x [3][n][n][C], g_yh [3][3][n][n][C]
  * (what SFB2D.backward + pad backward + the 2*x factor produce in the reference's autograd graph).
  * Optional fused regulariser gradient: if yh and reg_grad (device float*) are non-NULL,
- * g_yh += reg_coef * (*reg_grad) * sign(yh)   (d/dyh of  sum|yh|, scaled by its upstream gradient). */
+ * g_yh += reg_coef * (*reg_grad) * sign(yh)   (d/dyh of  sum|yh|, scaled by its upstream gradient).
+ * plane0 / nplanes: process only planes [plane0, plane0 + nplanes) (the multi-GPU path pipelines the per-plane gradient
+ * exchange against the backward of the previous plane); (0, 3) = all. */
 int tnl_idwt_level_backward(const float* g_out, float* g_x, float* g_yh, uint32_t n, uint32_t C, const float* yh,
-                            const float* reg_grad, float reg_coef, tnl_stream_t stream);
+                            const float* reg_grad, float reg_coef, uint32_t plane0, uint32_t nplanes, tnl_stream_t stream);
 
 /* Bilinear tri-plane sampling: replaces F.grid_sample(bilinear, border, align_corners=True) +
  * permute/concat of TriPlaneVolume.forward (triplane_encoder.py:314-332, 523-530).
@@ -178,11 +180,12 @@ int tnl_grid_ema_update(float* grid, const float* tmp_grid, uint32_t n, float de
 int tnl_mark_dirty_tiles(const uint8_t* bitfield, uint32_t cascade, uint32_t H, float bound, uint32_t R, uint32_t T,
                          uint32_t margin, uint8_t* flags, tnl_stream_t stream);
 /* gather / scatter the listed tiles between planes [3][R][R][C] and a compact buffer [n_tiles][T][T][C]
- * (tile id = (p * R/T + ty) * R/T + tx); unpack multiplies by `scale` (1/world_size for an average). */
+ * (tile id = (p * R/T + ty) * R/T + tx); unpack multiplies by `scale` (1/world_size for an average).
+ * bf16 != 0: the compact (transport) buffer is bfloat16 -- half the NVLink bytes; planes stay fp32. */
 int tnl_tiles_pack(const float* planes, const int32_t* tile_ids, uint32_t n_tiles, uint32_t R, uint32_t C, uint32_t T,
-                   float* compact, tnl_stream_t stream);
-int tnl_tiles_unpack(const float* compact, const int32_t* tile_ids, uint32_t n_tiles, uint32_t R, uint32_t C, uint32_t T,
-                     float scale, float* planes, tnl_stream_t stream);
+                   void* compact, int bf16, tnl_stream_t stream);
+int tnl_tiles_unpack(const void* compact, const int32_t* tile_ids, uint32_t n_tiles, uint32_t R, uint32_t C, uint32_t T,
+                     float scale, int bf16, float* planes, tnl_stream_t stream);
 
 #ifdef __cplusplus
 }

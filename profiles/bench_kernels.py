@@ -23,9 +23,9 @@ def bench_idwt(C=32, n=1024):
     by = 2 * 3 * C * (2 * n) ** 2 * 4
     t = timeit(lambda: call("tnl_idwt_level_forward", ptr(x), ptr(yh), ptr(out), n, C, ptr(asum), stream()))
     print(f"idwt_fwd  n={n} C={C}: {t:.3f} ms  {by / t / 1e6:.0f} GB/s algorithmic")
-    t = timeit(lambda: call("tnl_idwt_level_backward", ptr(out), ptr(gx), ptr(gyh), n, C, None, None, 0.0, stream()))
+    t = timeit(lambda: call("tnl_idwt_level_backward", ptr(out), ptr(gx), ptr(gyh), n, C, None, None, 0.0, 0, 3, stream()))
     print(f"idwt_bwd  n={n} C={C}: {t:.3f} ms  {by / t / 1e6:.0f} GB/s algorithmic")
-    t = timeit(lambda: call("tnl_idwt_level_backward", ptr(out), ptr(gx), ptr(gyh), n, C, ptr(yh), ptr(g1), 1.0, stream()))
+    t = timeit(lambda: call("tnl_idwt_level_backward", ptr(out), ptr(gx), ptr(gyh), n, C, ptr(yh), ptr(g1), 1.0, 0, 3, stream()))
     print(f"idwt_bwd+reg n={n} C={C}: {t:.3f} ms  {by / t / 1e6:.0f} GB/s algorithmic")
 
 if __name__ == "__main__":

@@ -9,5 +9,5 @@ out = cl_empty_planes(C, 2 * n, device="cuda"); asum = torch.zeros(1, device="cu
 gx = cl_empty_planes(C, n, device="cuda"); gyh = cl_empty_coefs(C, n, device="cuda"); g1 = torch.ones(1, device="cuda")
 for _ in range(2):
     call("tnl_idwt_level_forward", ptr(x), ptr(yh), ptr(out), n, C, ptr(asum), stream())
-    call("tnl_idwt_level_backward", ptr(out), ptr(gx), ptr(gyh), n, C, ptr(yh), ptr(g1), 1.0, stream())
+    call("tnl_idwt_level_backward", ptr(out), ptr(gx), ptr(gyh), n, C, ptr(yh), ptr(g1), 1.0, 0, 3, stream())
 torch.cuda.synchronize()

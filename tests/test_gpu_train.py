@@ -118,15 +118,19 @@ def test_sparse_plane_gradient_exchange_single_rank():
     sc = scene.make_scene()
     ro, rd, tgt = (t.cuda() for t in scene.sample_batch(sc, 4096, torch.Generator().manual_seed(3)))
     grads = []
-    for sparse in (False, True):
+    for mode in ("plain", "sparse_fp32", "sparse_fp32_pipelined", "sparse_bf16"):
         net = _model("tiny")
         ts = trainer.TrainStep(net, trainer.default_opt(), None, world_size=1)
-        if sparse:
-            ts.reducer = parallel.PlaneGradReducer(net, 1, tile=32, check=True).refresh()
+        if mode != "plain":
+            tr = torch.bfloat16 if mode == "sparse_bf16" else torch.float32
+            ts.reducer = parallel.PlaneGradReducer(net, 1, tile=32, check=True, transport=tr).refresh()
+            ts.pipelined_tail = mode.endswith("pipelined")
             assert 0.02 < ts.reducer.fraction < 0.9
         torch.manual_seed(0)
         loss = ts.forward_backward(ro, rd, tgt, update_grid=False)
         grads.append((float(loss), [p.grad.clone() for p in net.parameters()]))
-    assert abs(grads[0][0] - grads[1][0]) <= 1e-6 * abs(grads[0][0])
-    for a, b in zip(grads[0][1], grads[1][1]):
-        assert rel_l2(a, b) <= 1e-5
+    for k in (1, 2, 3):
+        assert abs(grads[0][0] - grads[k][0]) <= 1e-6 * abs(grads[0][0])
+        for a, b in zip(grads[0][1], grads[k][1]):
+            # fp32 transport is exact; bf16 transport rounds the plane gradient to 8 mantissa bits (stated bound 1e-2)
+            assert rel_l2(a, b) <= (1e-5 if k < 3 else 1e-2)

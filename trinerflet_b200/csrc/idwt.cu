@@ -71,12 +71,13 @@ k_idwt_fwd(const float* __restrict__ x, const float* __restrict__ yh, float* __r
 template <typename Cfg>
 __global__ void __launch_bounds__(Cfg::NT, (768 / Cfg::NT) > 0 ? (768 / Cfg::NT) : 1)
 k_idwt_bwd(const float* __restrict__ gout, float* __restrict__ g_x, float* __restrict__ g_yh, int n, int C,
-           int rows_per_cta, const float* __restrict__ yh, const float* __restrict__ reg_grad, float reg_coef) {
+           int rows_per_cta, const float* __restrict__ yh, const float* __restrict__ reg_grad, float reg_coef, int plane0) {
     extern __shared__ __align__(16) float smem[];
     float* mid0 = smem;
     float* stage0 = smem + 2 * Cfg::MID_B;
     const int tid = threadIdx.x;
-    const IdwtGeom g = idwt_geom<Cfg>(tid, IdwtBlock{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z}, n, C, rows_per_cta);
+    const IdwtGeom g = idwt_geom<Cfg>(tid, IdwtBlock{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z + plane0 * (C / Cfg::CG)}, n, C,
+                                     rows_per_cta);
     BwdState st;
     bwd_state_init<Cfg>(st, g, gout);
     const float reg = (yh != nullptr && reg_grad != nullptr) ? reg_coef * __ldg(reg_grad) : 0.f;
@@ -116,7 +117,7 @@ static int launch_fwd(const float* x, const float* yh, float* out, uint32_t n, u
 
 template <typename Cfg>
 static int launch_bwd(const float* g, float* g_x, float* g_yh, uint32_t n, uint32_t C, const float* yh,
-                      const float* reg_grad, float reg_coef, cudaStream_t stream) {
+                      const float* reg_grad, float reg_coef, uint32_t plane0, uint32_t nplanes, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_idwt_bwd<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_B);
@@ -124,8 +125,9 @@ static int launch_bwd(const float* g, float* g_x, float* g_yh, uint32_t n, uint3
     }
     unsigned gx, gy, gz, rows;
     idwt_grid<Cfg>(n, C, kNumSM, gx, gy, gz, rows);
+    gz = nplanes * (C / Cfg::CG);
     k_idwt_bwd<Cfg><<<dim3(gx, gy, gz), Cfg::NT, Cfg::SMEM_B, stream>>>(g, g_x, g_yh, (int)n, (int)C, (int)rows, yh, reg_grad,
-                                                                        reg_coef);
+                                                                        reg_coef, (int)plane0);
     return finish_launch("idwt_level_backward");
 }
 
@@ -148,15 +150,16 @@ int tnl_idwt_level_forward(const float* x, const float* yh, float* out, uint32_t
 }
 
 int tnl_idwt_level_backward(const float* g_out, float* g_x, float* g_yh, uint32_t n, uint32_t C, const float* yh,
-                            const float* reg_grad, float reg_coef, tnl_stream_t stream) {
+                            const float* reg_grad, float reg_coef, uint32_t plane0, uint32_t nplanes, tnl_stream_t stream) {
+    TNL_ARG_CHECK(nplanes >= 1 && plane0 + nplanes <= 3, "plane range must lie in [0, 3)");
     TNL_ARG_CHECK(g_out && g_x && g_yh, "null pointer");
     TNL_ARG_CHECK(n >= 8 && n % 8 == 0 && n <= 16384, "n must be a multiple of 8 in [8, 16384]");
     TNL_ARG_CHECK(C >= 8 && C % 8 == 0, "C must be a multiple of 8");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (C % 32 == 0 && getenv("TNL_IDWT_CG32")) return launch_bwd<IdwtCfg<32, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, s);
-    if (C % 24 == 0) return launch_bwd<IdwtCfg<24, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, s);
-    if (C % 16 == 0) return launch_bwd<IdwtCfg<16, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, s);
-    return launch_bwd<IdwtCfg<8, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, s);
+    if (C % 32 == 0 && getenv("TNL_IDWT_CG32")) return launch_bwd<IdwtCfg<32, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, plane0, nplanes, s);
+    if (C % 24 == 0) return launch_bwd<IdwtCfg<24, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, plane0, nplanes, s);
+    if (C % 16 == 0) return launch_bwd<IdwtCfg<16, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, plane0, nplanes, s);
+    return launch_bwd<IdwtCfg<8, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, plane0, nplanes, s);
 }
 
 }  // extern "C"

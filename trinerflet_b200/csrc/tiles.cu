@@ -7,6 +7,7 @@
 // packs those tiles into a compact buffer, all-reduces it with NCCL and scatters it back.  No reference counterpart
 // (the reference is single-GPU).
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace tnl {
 
@@ -49,24 +50,40 @@ __global__ void k_mark_dirty_tiles(const uint8_t* __restrict__ bitfield, uint32_
             for (int tx = lo[ax[p][0]]; tx <= hi[ax[p][0]]; ++tx) flags[(p * nt + ty) * nt + tx] = 1;
 }
 
-// tile id = (p * nt + ty) * nt + tx ; compact layout [n][T][T][C]; one CTA per (tile, row)
-template <bool PACK>
+// tile id = (p * nt + ty) * nt + tx ; compact layout [n][T][T][C]; one CTA per (tile, row).
+// BF16: the compact buffer holds bfloat16 (halves the bytes on NVLink; the plane gradient itself stays fp32).
+template <bool PACK, bool BF16>
 __global__ void __launch_bounds__(256)
-k_tiles_copy(float* __restrict__ planes, float* __restrict__ compact, const int32_t* __restrict__ tile_ids, int R, int C, int T,
+k_tiles_copy(float* __restrict__ planes, void* __restrict__ compact, const int32_t* __restrict__ tile_ids, int R, int C, int T,
              float scale) {
     const int tile = blockIdx.x, row = blockIdx.y;
     const int id = tile_ids[tile];
     const int nt = R / T;
     const int p = id / (nt * nt), ty = (id / nt) % nt, tx = id % nt;
     float4* src = reinterpret_cast<float4*>(planes + (((size_t)p * R + (size_t)ty * T + row) * R + (size_t)tx * T) * C);
-    float4* dst = reinterpret_cast<float4*>(compact + (((size_t)tile * T + row) * T) * C);
+    const size_t off4 = (((size_t)tile * T + row) * T) * C / 4;
     const int n4 = T * C / 4;
     for (int i = threadIdx.x; i < n4; i += blockDim.x) {
-        if (PACK) dst[i] = src[i];
-        else {
-            float4 v = dst[i];
-            v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
-            src[i] = v;
+        if (BF16) {
+            uint2* dst = reinterpret_cast<uint2*>(compact) + off4;
+            if (PACK) {
+                const float4 v = src[i];
+                const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+                dst[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+            } else {
+                const uint2 u = dst[i];
+                const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+                const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+                src[i] = make_float4(a.x * scale, a.y * scale, b.x * scale, b.y * scale);
+            }
+        } else {
+            float4* dst = reinterpret_cast<float4*>(compact) + off4;
+            if (PACK) dst[i] = src[i];
+            else {
+                float4 v = dst[i];
+                v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+                src[i] = v;
+            }
         }
     }
 }
@@ -90,22 +107,24 @@ int tnl_mark_dirty_tiles(const uint8_t* bitfield, uint32_t cascade, uint32_t H, 
 }
 
 int tnl_tiles_pack(const float* planes, const int32_t* tile_ids, uint32_t n_tiles, uint32_t R, uint32_t C, uint32_t T,
-                   float* compact, tnl_stream_t stream) {
+                   void* compact, int bf16, tnl_stream_t stream) {
     if (n_tiles == 0) return 0;
     TNL_ARG_CHECK(planes && tile_ids && compact, "null pointer");
     TNL_ARG_CHECK(R % T == 0 && (T * C) % 4 == 0, "bad tile geometry");
-    k_tiles_copy<true><<<dim3(n_tiles, T), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        const_cast<float*>(planes), compact, tile_ids, (int)R, (int)C, (int)T, 1.0f);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (bf16) k_tiles_copy<true, true><<<dim3(n_tiles, T), 256, 0, s>>>(const_cast<float*>(planes), compact, tile_ids, (int)R, (int)C, (int)T, 1.0f);
+    else k_tiles_copy<true, false><<<dim3(n_tiles, T), 256, 0, s>>>(const_cast<float*>(planes), compact, tile_ids, (int)R, (int)C, (int)T, 1.0f);
     return finish_launch("tiles_pack");
 }
 
-int tnl_tiles_unpack(const float* compact, const int32_t* tile_ids, uint32_t n_tiles, uint32_t R, uint32_t C, uint32_t T,
-                     float scale, float* planes, tnl_stream_t stream) {
+int tnl_tiles_unpack(const void* compact, const int32_t* tile_ids, uint32_t n_tiles, uint32_t R, uint32_t C, uint32_t T,
+                     float scale, int bf16, float* planes, tnl_stream_t stream) {
     if (n_tiles == 0) return 0;
     TNL_ARG_CHECK(planes && tile_ids && compact, "null pointer");
     TNL_ARG_CHECK(R % T == 0 && (T * C) % 4 == 0, "bad tile geometry");
-    k_tiles_copy<false><<<dim3(n_tiles, T), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        planes, const_cast<float*>(compact), tile_ids, (int)R, (int)C, (int)T, scale);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (bf16) k_tiles_copy<false, true><<<dim3(n_tiles, T), 256, 0, s>>>(planes, const_cast<void*>(compact), tile_ids, (int)R, (int)C, (int)T, scale);
+    else k_tiles_copy<false, false><<<dim3(n_tiles, T), 256, 0, s>>>(planes, const_cast<void*>(compact), tile_ids, (int)R, (int)C, (int)T, scale);
     return finish_launch("tiles_unpack");
 }
 

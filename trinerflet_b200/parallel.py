@@ -62,8 +62,14 @@ class PlaneGradReducer:
     average back.  For a centred object this moves ~20-25 % of the P bytes a dense all-reduce would.  `refresh()` must be
     called whenever the bitfield changes (after update_extra_state); it costs one small D2H copy of the tile flags."""
 
-    def __init__(self, model, world_size, tile=32, margin=2, check=False):
+    def __init__(self, model, world_size, tile=32, margin=2, check=False, transport=torch.bfloat16):
+        """transport: dtype of the compact buffer on the wire. bfloat16 (default) halves the NVLink bytes; every rank's
+        partial plane gradient is rounded to 8 mantissa bits before the sum (relative error <= 2^-9 per element, rel-L2 of
+        the summed gradient ~3e-3 -- inside the 1e-2 gradient tolerance of the fp16-autocast path).
+        torch.float32 gives the exact sum."""
         self.model, self.world_size, self.tile, self.margin, self.check = model, world_size, tile, margin, check
+        self.transport = transport
+        self.bf16 = int(transport == torch.bfloat16)
         self.tile_ids = None
         self.compact = None
 
@@ -78,7 +84,13 @@ class PlaneGradReducer:
              ptr(flags), stream())
         self.tile_ids = torch.nonzero(flags).squeeze(-1).int().contiguous()          # one sync, once per grid refresh
         self.n_tiles = int(self.tile_ids.shape[0])
-        self.compact = torch.empty(max(self.n_tiles, 1) * T * T * C, dtype=torch.float32, device=flags.device)
+        per_plane = torch.bincount(self.tile_ids.long() // (nt * nt), minlength=3).tolist()   # ids ascend: plane-major
+        self.plane_ranges = []
+        start = 0
+        for cnt in per_plane:
+            self.plane_ranges.append((start, int(cnt)))
+            start += int(cnt)
+        self.compact = torch.empty(max(self.n_tiles, 1) * T * T * C, dtype=self.transport, device=flags.device)
         self.fraction = self.n_tiles / float(3 * nt * nt)
         return self
 
@@ -91,16 +103,37 @@ class PlaneGradReducer:
         dense = _dense_view(g_planes)
         if self.check:   # debug: nothing outside the dirty tiles may be non-zero
             total = dense.abs().sum()
-        call("tnl_tiles_pack", ptr(dense), ptr(self.tile_ids), self.n_tiles, R, C, T, ptr(self.compact), stream())
+        call("tnl_tiles_pack", ptr(dense), ptr(self.tile_ids), self.n_tiles, R, C, T, ptr(self.compact), self.bf16, stream())
         if self.check:
-            inside = self.compact[: self.n_tiles * T * T * C].abs().sum()
-            if not torch.allclose(total, inside, rtol=1e-4):
+            inside = self.compact[: self.n_tiles * T * T * C].float().abs().sum()
+            if not torch.allclose(total, inside, rtol=1e-4 if not self.bf16 else 1e-2):
                 raise RuntimeError("PlaneGradReducer: plane gradient found outside the dirty tiles")
         if self.world_size > 1 and dist.is_initialized():
             dist.all_reduce(self.compact, op=dist.ReduceOp.SUM)
         call("tnl_tiles_unpack", ptr(self.compact), ptr(self.tile_ids), self.n_tiles, R, C, T, 1.0 / self.world_size,
-             ptr(dense), stream())
+             self.bf16, ptr(dense), stream())
         return g_planes
+
+
+def _reduce_plane(self, g_planes, plane):
+    """Average the dirty tiles of one plane across ranks, in place (pack -> NCCL all-reduce -> unpack) on the current stream."""
+    from ._lib import call, ptr, stream
+    if self.tile_ids is None:
+        self.refresh()
+    R, C, T = g_planes.shape[2], g_planes.shape[1], self.tile
+    start, cnt = self.plane_ranges[plane]
+    if cnt == 0:
+        return
+    dense = _dense_view(g_planes)
+    ids = self.tile_ids[start:start + cnt]
+    buf = self.compact[start * T * T * C:(start + cnt) * T * T * C]
+    call("tnl_tiles_pack", ptr(dense), ptr(ids), cnt, R, C, T, ptr(buf), self.bf16, stream())
+    if self.world_size > 1 and dist.is_initialized():
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    call("tnl_tiles_unpack", ptr(buf), ptr(ids), cnt, R, C, T, 1.0 / self.world_size, self.bf16, ptr(dense), stream())
+
+
+PlaneGradReducer.reduce_plane_ = _reduce_plane
 
 
 def allreduce_small(params, world_size):

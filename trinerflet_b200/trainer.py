@@ -39,7 +39,8 @@ def wavelet_regulariser(encoder, lam, fused=True):
 
 
 class TrainStep:
-    def __init__(self, model, opt=None, optimizer=None, world_size=1, sparse_allreduce=True, check_sparse=False):
+    def __init__(self, model, opt=None, optimizer=None, world_size=1, sparse_allreduce=True, check_sparse=False,
+                 transport=torch.bfloat16):
         self.model = model
         self.opt = opt or default_opt()
         self.optimizer = optimizer
@@ -48,7 +49,10 @@ class TrainStep:
         self.world_size = world_size
         self.criterion = torch.nn.MSELoss(reduction='none')
         # N > 1: the plane gradient is exchanged between the render backward and the IDWT backward, dirty tiles only
-        self.reducer = parallel.PlaneGradReducer(model, world_size, check=check_sparse) if (world_size > 1 and sparse_allreduce) else None
+        self.reducer = parallel.PlaneGradReducer(model, world_size, check=check_sparse, transport=transport) if (world_size > 1 and sparse_allreduce) else None
+        # eager-mode option: per-plane exchange on a side stream overlapped with the per-plane IDWT backward.  Measured on
+        # 8 x B200 it does not beat the sequential exchange (NCCL and the IDWT kernels contend for SMs / HBM), so it is off.
+        self.pipelined_tail = False
         self._graphs = None
 
     # ---- the three segments of a step ---------------------------------------------------------------------------------
@@ -115,9 +119,51 @@ class TrainStep:
         else:
             torch.autograd.backward([planes], [leaf.grad])
 
+    def _tail_pipelined(self):
+        """N > 1: per-plane gradient exchange on a communication stream, overlapped with the IDWT backward of the previous
+        plane on the compute stream:   exch(0) | exch(1) || idwt(0) | exch(2) || idwt(1) | idwt(2).
+        The regulariser gradient (identical on every rank) is added inside the IDWT backward kernels, after the exchange."""
+        from .triplane_encoder import PlanewiseIdwtBackward
+        planes, leaf, reg = self._cut
+        enc, opt = self.model.encoder, self.opt
+        feats = enc.get_wavelet_features()
+        lam = opt.wavelet_regularization
+        reg_coef = lam / (sum(v.numel() for v in feats) * len(feats)) if (lam > 0 and len(feats) > 0) else 0.0
+        scale_t = getattr(self.scaler, "_scale", None) if self.scaler.is_enabled() else None
+        if scale_t is None:
+            scale_t = torch.ones(1, device=leaf.device)
+        bw = PlanewiseIdwtBackward(enc, leaf.grad, scale_t, reg_coef)
+        main = torch.cuda.current_stream()
+        if getattr(self, "_comm", None) is None:
+            self._comm = torch.cuda.Stream()
+        comm = self._comm
+        comm.wait_stream(main)
+        done = []
+        mlp = [p for n, p in self.model.named_parameters() if not n.startswith("encoder.")]
+        with torch.cuda.stream(comm):
+            for p in range(3):
+                self.reducer.reduce_plane_(leaf.grad, p)
+                ev = torch.cuda.Event()
+                ev.record(comm)
+                done.append(ev)
+            parallel.allreduce_small(mlp, self.world_size)
+            ev_small = torch.cuda.Event()
+            ev_small.record(comm)
+        import os
+        if os.environ.get("TNL_TAIL_SEQ"):      # diagnostic: no overlap (exchange everything, then the IDWT backward)
+            main.wait_event(done[2])
+        for p in range(3):
+            main.wait_event(done[p])
+            bw.run(p)
+        main.wait_event(ev_small)
+        bw.assign()
+
     def _exchange_and_finish(self):
-        self._exchange()
-        self._idwt_backward()
+        if self.pipelined_tail:
+            self._tail_pipelined()
+        else:
+            self._exchange()
+            self._idwt_backward()
         self._cut = None   # drop the autograd graph (and the AccumulateGrad nodes it keeps alive) of this step
 
     # ---- CUDA-graph mode: a steady-state step is one (N = 1) or two (N > 1, NCCL in between) graph launches ----------

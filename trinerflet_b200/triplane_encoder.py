@@ -129,12 +129,44 @@ class _BuildPlanes(Function):
             g_yh = cl_empty_coefs(C, n, device=g.device)
             if g_abs is not None:
                 call("tnl_idwt_level_backward", ptr(g), ptr(g_x), ptr(g_yh), n, C, ptr(yhs[l]), ptr(g_abs[l:l + 1]), 1.0,
-                     stream())
+                     0, 3, stream())
             else:
-                call("tnl_idwt_level_backward", ptr(g), ptr(g_x), ptr(g_yh), n, C, None, None, 0.0, stream())
+                call("tnl_idwt_level_backward", ptr(g), ptr(g_x), ptr(g_yh), n, C, None, None, 0.0, 0, 3, stream())
             grads.append(g_yh)
             g = g_x
         return (g, *reversed(grads))
+
+
+class PlanewiseIdwtBackward:
+    """The adjoint of build_planes driven plane by plane (multi-GPU path): `run(plane)` pushes the gradient of one of the
+    three planes through all levels, so plane p can be processed while the gradient of plane p+1 is still being
+    exchanged.  Writes straight into freshly allocated .grad tensors of the encoder parameters."""
+
+    def __init__(self, encoder, g_planes, reg_scale=None, reg_coef=0.0):
+        self.enc = encoder
+        self.C, self.levels = encoder.number_of_features, len(encoder.planes_features_wavelet_coefs)
+        self.n0 = encoder.planes_features.shape[2]
+        self.g = to_cl_planes(g_planes)
+        self.reg_scale, self.reg_coef = reg_scale, float(reg_coef)
+        dev = self.g.device
+        self.g_x = [cl_empty_planes(self.C, self.n0 * 2 ** l, device=dev) for l in range(self.levels)]
+        self.g_yh = [cl_empty_coefs(self.C, self.n0 * 2 ** l, device=dev) for l in range(self.levels)]
+
+    def run(self, plane):
+        g = self.g
+        for l in reversed(range(self.levels)):
+            n = self.n0 * 2 ** l
+            yh = self.enc.planes_features_wavelet_coefs[l]
+            use_reg = self.reg_scale is not None and self.reg_coef != 0.0
+            call("tnl_idwt_level_backward", ptr(g), ptr(self.g_x[l]), ptr(self.g_yh[l]), n, self.C,
+                 ptr(yh.detach()) if use_reg else None, ptr(self.reg_scale) if use_reg else None, self.reg_coef, plane, 1, stream())
+            g = self.g_x[l]
+
+    def assign(self):
+        """Install the results as parameter gradients (zero_grad(set_to_none=True) semantics)."""
+        self.enc.planes_features.grad = self.g_x[0]
+        for p, g in zip(self.enc.planes_features_wavelet_coefs, self.g_yh):
+            p.grad = g
 
 
 def build_planes_with_abs(planes_features, coefs):
