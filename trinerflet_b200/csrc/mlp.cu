@@ -21,6 +21,7 @@
 //   color_net[0] cols: internal k < 16 = SH k, 16..30 = geo_feat 0..14, 31 = zero padding
 //   color_net[2] rows: 3 real rows padded with zero rows to 8 (forward) / 16 (backward)
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace tnl {
 
@@ -345,9 +346,9 @@ k_mlp_fwd(const uint32_t* __restrict__ wp, const float* __restrict__ feat, const
 //            dW and keeps it in fp32 accumulator registers for the whole kernel; one atomicAdd per
 //            element per CTA at the end.
 // ------------------------------------------------------------------------------------------------
-template <int K1, int H, int HC>
+template <int K1, int H, int HC, int NW>
 struct BwdSmem {
-    static constexpr int PTS = 128;
+    static constexpr int PTS = 16 * NW;
     static constexpr int P_F = K1 + 8, P_H = H + 8, P_I = 32 + 8, P_C = HC + 8, P_S = 16 + 8;  // pitches (halves)
     static constexpr int O_F = 0;                      // feat
     static constexpr int O_H1 = O_F + PTS * P_F;       // relu(h1)
@@ -412,15 +413,46 @@ __device__ __forceinline__ void dw_kstep(float (&acc)[NTILES][4], const __half* 
     }
 }
 
-template <int K1, int H, int HC>
-__global__ void __launch_bounds__(256, 1)
+// reload an operand-fragment set written by store_frags (same warp; used for the ReLU masks so that the forward
+// activations need not stay in registers across the backward chain)
+template <int KS>
+__device__ __forceinline__ void load_frags(const __half* tile, int pitch, int row0, uint32_t (&a)[KS][4], int t) {
+    const uint32_t* p0 = reinterpret_cast<const uint32_t*>(tile + (size_t)row0 * pitch) + t;
+    const uint32_t* p1 = reinterpret_cast<const uint32_t*>(tile + (size_t)(row0 + 8) * pitch) + t;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        a[ks][0] = p0[8 * ks];
+        a[ks][1] = p1[8 * ks];
+        a[ks][2] = p0[8 * ks + 4];
+        a[ks][3] = p1[8 * ks + 4];
+    }
+}
+
+template <int KS>
+__device__ __forceinline__ void relu_mask(uint32_t (&d)[KS][4], const uint32_t (&h)[KS][4]) {
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {  // h > 0  <=>  fp16 magnitude bits non-zero (ReLU output is never negative)
+            const uint32_t v = h[ks][i];
+            const uint32_t m = (((v & 0x7fffu) != 0u) ? 0x0000ffffu : 0u) | (((v & 0x7fff0000u) != 0u) ? 0xffff0000u : 0u);
+            d[ks][i] &= m;
+        }
+}
+
+template <int K1, int H, int HC, int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1)
 k_mlp_bwd(const uint32_t* __restrict__ wp, const float* __restrict__ feat, const float* __restrict__ dirs, uint32_t M,
           const int32_t* __restrict__ n_valid_ptr, const float* __restrict__ g_sigma, const float* __restrict__ g_rgb,
           float* __restrict__ g_feat, float* __restrict__ gW1, float* __restrict__ gW2, float* __restrict__ gW3,
           float* __restrict__ gW4, float* __restrict__ gW5) {
     static_assert(H == 64 && HC == 64, "backward kernel: weight-gradient register tiling is laid out for 64-wide heads");
+    static_assert(NW == 4 || NW == 8, "4 or 8 warps");
     constexpr MlpLayout L = make_layout(K1, H, HC);
-    using SM = BwdSmem<K1, H, HC>;
+    using SM = BwdSmem<K1, H, HC, NW>;
+    constexpr int SPLIT = NW / 4;            // warps sharing one 16-row block of a weight gradient
+    constexpr int T1 = (K1 / 8) / SPLIT;     // k-in tiles of dW1 per warp
+    constexpr int T4 = 8 / SPLIT, T3 = 4 / SPLIT, T25 = 8 / NW;
     extern __shared__ __align__(16) __half sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     uint32_t nvalid = M;
@@ -431,16 +463,18 @@ k_mlp_bwd(const uint32_t* __restrict__ wp, const float* __restrict__ feat, const
     // persistent weight-gradient accumulators: warp w owns
     //   dW1: rows [16*(w/2), +16), k-in tiles [(w%2)*K1/16, +K1/16)      dW4: rows [16*(w/2), +16), tiles [(w%2)*4, +4)
     //   dW3: rows [16*(w/2), +16), tiles [(w%2)*2, +2)                   dW2, dW5: the single 16-row block, tile w
-    constexpr int T1 = K1 / 16;
-    float acc1[T1][4], acc4[4][4], acc3[2][4], acc2[1][4], acc5[1][4];
+    float acc1[T1][4], acc4[T4][4], acc3[T3][4], acc2[T25][4], acc5[T25][4];
 #pragma unroll
     for (int i = 0; i < T1; ++i) acc1[i][0] = acc1[i][1] = acc1[i][2] = acc1[i][3] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc4[i][0] = acc4[i][1] = acc4[i][2] = acc4[i][3] = 0.f;
+    for (int i = 0; i < T4; ++i) acc4[i][0] = acc4[i][1] = acc4[i][2] = acc4[i][3] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) acc3[i][0] = acc3[i][1] = acc3[i][2] = acc3[i][3] = 0.f;
-    acc2[0][0] = acc2[0][1] = acc2[0][2] = acc2[0][3] = 0.f;
-    acc5[0][0] = acc5[0][1] = acc5[0][2] = acc5[0][3] = 0.f;
+    for (int i = 0; i < T3; ++i) acc3[i][0] = acc3[i][1] = acc3[i][2] = acc3[i][3] = 0.f;
+#pragma unroll
+    for (int i = 0; i < T25; ++i) {
+        acc2[i][0] = acc2[i][1] = acc2[i][2] = acc2[i][3] = 0.f;
+        acc5[i][0] = acc5[i][1] = acc5[i][2] = acc5[i][3] = 0.f;
+    }
 
     const uint32_t ntiles = ceil_div(nvalid, (uint32_t)SM::PTS);
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -456,6 +490,7 @@ k_mlp_bwd(const uint32_t* __restrict__ wp, const float* __restrict__ feat, const
         store_frags<2>(sm + SM::O_I2, SM::P_I, row0, s.a3, t);
         store_frags<HC / 16>(sm + SM::O_H3, SM::P_C, row0, s.a4, t);
         store_frags<HC / 16>(sm + SM::O_H4, SM::P_C, row0, s.a5, t);
+        __syncwarp();
 
         // d5 = half(g_rgb) * s * (1 - s), fp16 (sigmoid backward under autocast); columns 3..15 are zero
         uint32_t d5[1][4];
@@ -483,14 +518,11 @@ k_mlp_bwd(const uint32_t* __restrict__ wp, const float* __restrict__ feat, const
             float acc[HC / 8][4];
             layer_mma<1, HC / 8>(acc, d5, wp, L.B5, lane);
             acc_to_frag<HC / 8, false>(acc, d4);
-#pragma unroll
-            for (int ks = 0; ks < HC / 16; ++ks)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {  // ReLU mask from the stored activation (h > 0 <=> fp16 bits != 0 and sign clear)
-                    const uint32_t h = s.a5[ks][i];
-                    const uint32_t m = (((h & 0x7fffu) != 0u) ? 0x0000ffffu : 0u) | (((h & 0x7fff0000u) != 0u) ? 0xffff0000u : 0u);
-                    d4[ks][i] &= m;
-                }
+            {
+                uint32_t hm[HC / 16][4];
+                load_frags<HC / 16>(sm + SM::O_H4, SM::P_C, row0, hm, t);
+                relu_mask<HC / 16>(d4, hm);
+            }
         }
         store_frags<HC / 16>(sm + SM::O_D4, SM::P_C, row0, d4, t);
         // dh3 = (dh4 W4) * [h3 > 0]
@@ -499,14 +531,11 @@ k_mlp_bwd(const uint32_t* __restrict__ wp, const float* __restrict__ feat, const
             float acc[HC / 8][4];
             layer_mma<HC / 16, HC / 8>(acc, d4, wp, L.B4, lane);
             acc_to_frag<HC / 8, false>(acc, d3);
-#pragma unroll
-            for (int ks = 0; ks < HC / 16; ++ks)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t h = s.a4[ks][i];
-                    const uint32_t m = (((h & 0x7fffu) != 0u) ? 0x0000ffffu : 0u) | (((h & 0x7fff0000u) != 0u) ? 0xffff0000u : 0u);
-                    d3[ks][i] &= m;
-                }
+            {
+                uint32_t hm[HC / 16][4];
+                load_frags<HC / 16>(sm + SM::O_H3, SM::P_C, row0, hm, t);
+                relu_mask<HC / 16>(d3, hm);
+            }
         }
         store_frags<HC / 16>(sm + SM::O_D3, SM::P_C, row0, d3, t);
         // d(in2) = dh3 W3 ; only the geo half (internal columns 16..31) is needed
@@ -533,14 +562,11 @@ k_mlp_bwd(const uint32_t* __restrict__ wp, const float* __restrict__ feat, const
             float acc[H / 8][4];
             layer_mma<1, H / 8>(acc, d2, wp, L.B2, lane);
             acc_to_frag<H / 8, false>(acc, d1);
-#pragma unroll
-            for (int ks = 0; ks < H / 16; ++ks)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t h = s.a2[ks][i];
-                    const uint32_t m = (((h & 0x7fffu) != 0u) ? 0x0000ffffu : 0u) | (((h & 0x7fff0000u) != 0u) ? 0xffff0000u : 0u);
-                    d1[ks][i] &= m;
-                }
+            {
+                uint32_t hm[H / 16][4];
+                load_frags<H / 16>(sm + SM::O_H1, SM::P_H, row0, hm, t);
+                relu_mask<H / 16>(d1, hm);
+            }
         }
         store_frags<H / 16>(sm + SM::O_D1, SM::P_H, row0, d1, t);
         // g_feat = dh1 W1 (fp16-rounded, as the autocast linear backward returns it)
@@ -558,21 +584,21 @@ k_mlp_bwd(const uint32_t* __restrict__ wp, const float* __restrict__ feat, const
         __syncthreads();
         // ------------------------------ phase 2 ------------------------------
         {
-            const int nb = warp >> 1, hf = warp & 1;
+            const int nb = warp / SPLIT, hf = warp % SPLIT;
 #pragma unroll 1
             for (int pt0 = 0; pt0 < SM::PTS; pt0 += 16) {
                 dw_kstep<T1>(acc1, sm + SM::O_D1, SM::P_H, nb, sm + SM::O_F, SM::P_F, hf * T1, pt0, lane);
-                dw_kstep<4>(acc4, sm + SM::O_D4, SM::P_C, nb, sm + SM::O_H3, SM::P_C, hf * 4, pt0, lane);
-                dw_kstep<2>(acc3, sm + SM::O_D3, SM::P_C, nb, sm + SM::O_I2, SM::P_I, hf * 2, pt0, lane);
-                dw_kstep<1>(acc2, sm + SM::O_D2, SM::P_S, 0, sm + SM::O_H1, SM::P_H, warp, pt0, lane);
-                dw_kstep<1>(acc5, sm + SM::O_D5, SM::P_S, 0, sm + SM::O_H4, SM::P_C, warp, pt0, lane);
+                dw_kstep<T4>(acc4, sm + SM::O_D4, SM::P_C, nb, sm + SM::O_H3, SM::P_C, hf * T4, pt0, lane);
+                dw_kstep<T3>(acc3, sm + SM::O_D3, SM::P_C, nb, sm + SM::O_I2, SM::P_I, hf * T3, pt0, lane);
+                dw_kstep<T25>(acc2, sm + SM::O_D2, SM::P_S, 0, sm + SM::O_H1, SM::P_H, warp * T25, pt0, lane);
+                dw_kstep<T25>(acc5, sm + SM::O_D5, SM::P_S, 0, sm + SM::O_H4, SM::P_C, warp * T25, pt0, lane);
             }
         }
         __syncthreads();
     }
     // ------------------------------ flush weight gradients ------------------------------
     {
-        const int nb = warp >> 1, hf = warp & 1;
+        const int nb = warp / SPLIT, hf = warp % SPLIT;
         const int n0 = nb * 16 + g, n1 = n0 + 8;
 #pragma unroll
         for (int q = 0; q < T1; ++q) {
@@ -583,32 +609,34 @@ k_mlp_bwd(const uint32_t* __restrict__ wp, const float* __restrict__ feat, const
             atomicAdd(gW1 + (size_t)n1 * K1 + k + 1, acc1[q][3]);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int k = (hf * 4 + q) * 8 + 2 * t;
+        for (int q = 0; q < T4; ++q) {
+            const int k = (hf * T4 + q) * 8 + 2 * t;
             atomicAdd(gW4 + (size_t)n0 * HC + k, acc4[q][0]);
             atomicAdd(gW4 + (size_t)n0 * HC + k + 1, acc4[q][1]);
             atomicAdd(gW4 + (size_t)n1 * HC + k, acc4[q][2]);
             atomicAdd(gW4 + (size_t)n1 * HC + k + 1, acc4[q][3]);
         }
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int k = (hf * 2 + q) * 8 + 2 * t;  // internal color_net[0] column: 0..15 SH, 16..30 geo, 31 padding
+        for (int q = 0; q < T3; ++q) {
+            const int k = (hf * T3 + q) * 8 + 2 * t;  // internal color_net[0] column: 0..15 SH, 16..30 geo, 31 padding
             if (k < 31) { atomicAdd(gW3 + (size_t)n0 * 31 + k, acc3[q][0]); atomicAdd(gW3 + (size_t)n1 * 31 + k, acc3[q][2]); }
             if (k + 1 < 31) { atomicAdd(gW3 + (size_t)n0 * 31 + k + 1, acc3[q][1]); atomicAdd(gW3 + (size_t)n1 * 31 + k + 1, acc3[q][3]); }
         }
-        {   // sigma_net[1]: internal row j < 15 -> reference row j+1, internal 15 -> row 0
-            const int k = warp * 8 + 2 * t;
-            const int ra = g + 1;                    // internal row g  (< 8)
-            const int rb = (g + 8 < 15) ? g + 9 : 0; // internal row g+8
-            atomicAdd(gW2 + (size_t)ra * H + k, acc2[0][0]);
-            atomicAdd(gW2 + (size_t)ra * H + k + 1, acc2[0][1]);
-            atomicAdd(gW2 + (size_t)rb * H + k, acc2[0][2]);
-            atomicAdd(gW2 + (size_t)rb * H + k + 1, acc2[0][3]);
-        }
-        if (g < 3) {  // color_net[2]: rows 0..2 real
-            const int k = warp * 8 + 2 * t;
-            atomicAdd(gW5 + (size_t)g * HC + k, acc5[0][0]);
-            atomicAdd(gW5 + (size_t)g * HC + k + 1, acc5[0][1]);
+#pragma unroll
+        for (int q = 0; q < T25; ++q) {
+            const int k = (warp * T25 + q) * 8 + 2 * t;
+            {   // sigma_net[1]: internal row j < 15 -> reference row j+1, internal 15 -> row 0
+                const int ra = g + 1;                    // internal row g  (< 8)
+                const int rb = (g + 8 < 15) ? g + 9 : 0; // internal row g+8
+                atomicAdd(gW2 + (size_t)ra * H + k, acc2[q][0]);
+                atomicAdd(gW2 + (size_t)ra * H + k + 1, acc2[q][1]);
+                atomicAdd(gW2 + (size_t)rb * H + k, acc2[q][2]);
+                atomicAdd(gW2 + (size_t)rb * H + k + 1, acc2[q][3]);
+            }
+            if (g < 3) {  // color_net[2]: rows 0..2 real
+                atomicAdd(gW5 + (size_t)g * HC + k, acc5[q][0]);
+                atomicAdd(gW5 + (size_t)g * HC + k + 1, acc5[q][1]);
+            }
         }
     }
 }
@@ -686,23 +714,33 @@ int tnl_mlp_backward(const tnl_mlp_dims* dims, const void* packed, const float* 
     TNL_ARG_CHECK(packed && feat && dirs && g_sigma && g_rgb && g_W1 && g_W2 && g_W3 && g_W4 && g_W5, "null pointer");
     TNL_ARG_CHECK(((uintptr_t)feat & 7) == 0 && ((uintptr_t)g_feat & 7) == 0, "feat/g_feat must be 8-byte aligned");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    const uint32_t ntiles = ceil_div(M, 128u);
-    const uint32_t blocks = min(ntiles, (uint32_t)kNumSM);
-#define CALLB(K)                                                                                                        \
+    // two independent 4-warp CTAs per SM: while one is in its latency-bound recompute / dX phase the other runs the
+    // shared-memory-bound weight-gradient phase (TNL_MLP_BWD_NW=8 selects the single 8-warp CTA variant)
+    static const int nw = getenv("TNL_MLP_BWD_NW") ? atoi(getenv("TNL_MLP_BWD_NW")) : 4;
+#define CALLB_NW(K, NW)                                                                                                  \
     do {                                                                                                                \
-        using SMB = BwdSmem<K, 64, 64>;                                                                                 \
+        using SMB = BwdSmem<K, 64, 64, NW>;                                                                             \
         static bool attr = false;                                                                                       \
         if (!attr) {                                                                                                    \
-            cudaFuncSetAttribute(k_mlp_bwd<K, 64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMB::BYTES);   \
+            cudaFuncSetAttribute(k_mlp_bwd<K, 64, 64, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMB::BYTES); \
             attr = true;                                                                                                \
         }                                                                                                               \
-        k_mlp_bwd<K, 64, 64><<<blocks, 256, SMB::BYTES, s>>>(static_cast<const uint32_t*>(packed), feat, dirs, M, n_valid, \
-                                                             g_sigma, g_rgb, g_feat, g_W1, g_W2, g_W3, g_W4, g_W5);      \
+        const uint32_t ntiles = ceil_div(M, (uint32_t)(16 * NW));                                                        \
+        const uint32_t blocks = min(ntiles, (uint32_t)(kNumSM * (NW == 4 ? 2 : 1)));                                     \
+        k_mlp_bwd<K, 64, 64, NW><<<blocks, NW * 32, SMB::BYTES, s>>>(static_cast<const uint32_t*>(packed), feat, dirs, M, \
+                                                                     n_valid, g_sigma, g_rgb, g_feat, g_W1, g_W2, g_W3,  \
+                                                                     g_W4, g_W5);                                        \
+    } while (0)
+#define CALLB(K)                  \
+    do {                          \
+        if (nw == 8) CALLB_NW(K, 8); \
+        else CALLB_NW(K, 4);      \
     } while (0)
     if (dims->in_dim == 48) CALLB(48);
     else if (dims->in_dim == 96) CALLB(96);
     else CALLB(144);
 #undef CALLB
+#undef CALLB_NW
     return finish_launch("mlp_backward");
 }
 
