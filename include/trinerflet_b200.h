@@ -119,12 +119,14 @@ int tnl_idwt_level_backward(const float* g_out, float* g_x, float* g_yh, uint32_
  * u = xyz * inv_bound (inv_bound = 1/bound in fp32, CUDA's tensor/scalar rule); if fp16_coords != 0,
  * u is rounded to fp16 first (the autocast quirk of triplane_encoder.py:299).
  * n_valid (device int32*, may be NULL): rows >= *n_valid are skipped (feat rows written as zeros).
- * perm (device int32 [M], may be NULL): visit order (tnl_cell_sort); row m of feat always belongs to point m. */
+ * perm (device int32 [M], may be NULL): visit order (tnl_cell_sort); row m of feat always belongs to point m.
+ * feat_fp16 != 0: feat / g_feat are __half [M][3C] -- the rounding the first nn.Linear applies under autocast
+ * (network.py:127) done by the producer, halving the bytes of the feature stream. */
 int tnl_sample_planes_forward(const float* planes, const float* xyz, uint32_t M, uint32_t R, uint32_t C,
                               float inv_bound, int fp16_coords, const int32_t* n_valid, const int32_t* perm,
-                              float* feat, tnl_stream_t stream);
+                              void* feat, int feat_fp16, tnl_stream_t stream);
 /* Adjoint scatter (grid_sampler_2d_backward w.r.t. input): g_planes += ...; caller zero-fills g_planes. */
-int tnl_sample_planes_backward(const float* g_feat, const float* xyz, uint32_t M, uint32_t R, uint32_t C,
+int tnl_sample_planes_backward(const void* g_feat, int feat_fp16, const float* xyz, uint32_t M, uint32_t R, uint32_t C,
                                float inv_bound, int fp16_coords, const int32_t* n_valid, const int32_t* perm,
                                float* g_planes, tnl_stream_t stream);
 
@@ -151,16 +153,16 @@ typedef struct tnl_mlp_dims {
 size_t tnl_mlp_packed_bytes(const tnl_mlp_dims* dims);
 int tnl_mlp_pack_weights(const tnl_mlp_dims* dims, const float* W1, const float* W2, const float* W3,
                          const float* W4, const float* W5, void* packed, tnl_stream_t stream);
-/* feat [M][3C] fp32, dirs [M][3] fp32 (NULL => density only) -> sigma [M] fp32, rgb [M][3] fp32
+/* feat [M][3C] fp32 (or __half if feat_fp16), dirs [M][3] fp32 (NULL => density only) -> sigma [M] fp32, rgb [M][3] fp32
  * (fp16-representable), geo [M][15] fp32 (may be NULL).  n_valid as above (skipped rows -> zeros). */
-int tnl_mlp_forward(const tnl_mlp_dims* dims, const void* packed, const float* feat, const float* dirs,
+int tnl_mlp_forward(const tnl_mlp_dims* dims, const void* packed, const void* feat, int feat_fp16, const float* dirs,
                     uint32_t M, const int32_t* n_valid, float* sigma, float* rgb, float* geo,
                     tnl_stream_t stream);
 /* Backward of tnl_mlp_forward: recomputes activations from feat; g_sigma [M], g_rgb [M][3] in;
- * g_feat [M][3C] out (may be NULL); g_W1..g_W5 fp32 accumulated with atomics (caller zero-fills). */
-int tnl_mlp_backward(const tnl_mlp_dims* dims, const void* packed, const float* feat, const float* dirs,
+ * g_feat [M][3C] out, same dtype as feat (may be NULL); g_W1..g_W5 fp32 accumulated with atomics (caller zero-fills). */
+int tnl_mlp_backward(const tnl_mlp_dims* dims, const void* packed, const void* feat, int feat_fp16, const float* dirs,
                      uint32_t M, const int32_t* n_valid, const float* g_sigma, const float* g_rgb,
-                     float* g_feat, float* g_W1, float* g_W2, float* g_W3, float* g_W4, float* g_W5,
+                     void* g_feat, float* g_W1, float* g_W2, float* g_W3, float* g_W4, float* g_W5,
                      tnl_stream_t stream);
 
 /* ------------------------------------------------------------------ density grid ------------- */

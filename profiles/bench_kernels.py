@@ -56,8 +56,8 @@ def bench_sample(C=32, R=2048, n_rays=60000):
             t = timeit(lambda: cell_sort(xyzs, 1.5, None, G), iters=5)
             perm = cell_sort(xyzs, 1.5, None, G)
             print(f"cell_sort G={G}: {t:.3f} ms")
-        tf = timeit(lambda: call("tnl_sample_planes_forward", ptr(planes), ptr(xyzs), M, R, C, inv, 1, None, ptr(perm), ptr(feat), stream()))
-        tb = timeit(lambda: call("tnl_sample_planes_backward", ptr(gfeat), ptr(xyzs), M, R, C, inv, 1, None, ptr(perm), ptr(gpl), stream()))
+        tf = timeit(lambda: call("tnl_sample_planes_forward", ptr(planes), ptr(xyzs), M, R, C, inv, 1, None, ptr(perm), ptr(feat), 0, stream()))
+        tb = timeit(lambda: call("tnl_sample_planes_backward", ptr(gfeat), 0, ptr(xyzs), M, R, C, inv, 1, None, ptr(perm), ptr(gpl), stream()))
         print(f"G={G}: sample_fwd {tf:.3f} ms  sample_bwd {tb:.3f} ms")
 
 if __name__ == "__main__" and "sample" in sys.argv[1:]:

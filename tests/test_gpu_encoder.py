@@ -120,6 +120,14 @@ def test_sampling_matches_oracle(C, R, fp16):
     assert torch.equal(f_s, f_g)
     (f_s * w.cuda()).sum().backward()
     assert rel_l2(p_s.grad, p_o.grad) <= TOL_GRAD
+    # fp16 feature stream: the fp32 features rounded to nearest fp16, and the matching scatter of an fp16 gradient
+    p_h = cl_planes(planes.cuda()).requires_grad_(True)
+    f_h = sample_planes(p_h, xyz.cuda(), bound, fp16_coords=fp16, half_out=True)
+    assert f_h.dtype == torch.float16 and torch.equal(f_h, f_g.half())
+    (f_h.float() * w.cuda().half().float()).sum().backward()
+    p_r = cl_planes(planes.cuda()).requires_grad_(True)
+    (sample_planes(p_r, xyz.cuda(), bound, fp16_coords=fp16) * w.cuda().half().float()).sum().backward()
+    assert rel_l2(p_h.grad, p_r.grad) <= TOL_GRAD
     # n_valid: rows past the counter are skipped (zeros out, no gradient)
     nv = torch.tensor([M // 2], dtype=torch.int32, device="cuda")
     p_g2 = cl_planes(planes.cuda()).requires_grad_(True)

@@ -38,6 +38,8 @@ def test_mlp_forward_fp16(C, hidden, M):
     assert rel_l2(s_g, s_o) <= TOL_SIGMA_REL
     s_d, geo_d = _DensityMLP.apply(feat.cuda(), *Wg)
     assert torch.equal(s_d, s_g)
+    s_h, rgb_h = _FieldMLP.apply(feat.cuda().half(), d.cuda(), None, *Wg)     # fp16 feature stream: same rounding point
+    assert torch.equal(s_h, s_g) and torch.equal(rgb_h, rgb_g)
     assert (geo_d.cpu() - geo_o).abs().max().item() <= TOL_RGB * max(1.0, geo_o.abs().max().item())
 
 
@@ -60,6 +62,14 @@ def test_mlp_backward_fp16(C, M):
     assert rel_l2(f_g.grad, f_o.grad) <= TOL_GRAD
     for a, b in zip(W_g, W_o):
         assert rel_l2(a.grad, b.grad) <= TOL_GRAD, (a.shape, rel_l2(a.grad, b.grad))
+    # fp16 feature stream in, fp16 feature gradient out: identical rounding points, identical results
+    W_f = [w.cuda().requires_grad_(True) for w in W]
+    f_f = feat.cuda().half().requires_grad_(True)
+    s_f, rgb_f = _FieldMLP.apply(f_f, d.cuda(), None, *W_f)
+    ((s_f * gs.cuda()).sum() + (rgb_f * grgb.cuda()).sum()).backward()
+    assert f_f.grad.dtype == torch.float16 and torch.equal(f_f.grad.float(), f_g.grad)
+    for a, b in zip(W_f, W_g):
+        assert rel_l2(a.grad, b.grad) <= 1e-5
     # n_valid: only the first rows contribute
     nv = torch.tensor([M // 3], dtype=torch.int32, device="cuda")
     W_h = [w.cuda().requires_grad_(True) for w in W]

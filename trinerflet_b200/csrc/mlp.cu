@@ -202,6 +202,21 @@ struct TileFwd {
     float rgb[4];             // sigmoid outputs of the 8-wide tile: c0,c1 (row g), c2,c3 (row g+8)
 };
 
+// fp16 feature rows (produced by k_sample_fwd<true>): the operand fragments are plain 32-bit loads
+template <int K1>
+__device__ __forceinline__ void load_feat_frags_h(uint32_t (&a1)[K1 / 16][4], const __half* __restrict__ feat, uint32_t r0,
+                                                  uint32_t r1, bool v0, bool v1, int t) {
+    const uint32_t* p0 = reinterpret_cast<const uint32_t*>(feat + (size_t)r0 * K1) + t;
+    const uint32_t* p1 = reinterpret_cast<const uint32_t*>(feat + (size_t)r1 * K1) + t;
+#pragma unroll
+    for (int ks = 0; ks < K1 / 16; ++ks) {
+        a1[ks][0] = v0 ? __ldg(p0 + 8 * ks) : 0u;
+        a1[ks][1] = v1 ? __ldg(p1 + 8 * ks) : 0u;
+        a1[ks][2] = v0 ? __ldg(p0 + 8 * ks + 4) : 0u;
+        a1[ks][3] = v1 ? __ldg(p1 + 8 * ks + 4) : 0u;
+    }
+}
+
 template <int K1>
 __device__ __forceinline__ void load_feat_frags(uint32_t (&a1)[K1 / 16][4], const float* __restrict__ feat, uint32_t r0,
                                                 uint32_t r1, bool v0, bool v1, int t) {
@@ -279,9 +294,9 @@ __device__ __forceinline__ void tile_forward(TileFwd<K1, H, HC>& s, const MlpLay
 // ------------------------------------------------------------------------------------------------
 // forward kernel: one warp per 16-point tile, grid-stride over tiles
 // ------------------------------------------------------------------------------------------------
-template <int K1, int H, int HC>
+template <int K1, int H, int HC, bool FH>
 __global__ void __launch_bounds__(128)
-k_mlp_fwd(const uint32_t* __restrict__ wp, const float* __restrict__ feat, const float* __restrict__ dirs, uint32_t M,
+k_mlp_fwd(const uint32_t* __restrict__ wp, const void* __restrict__ feat, const float* __restrict__ dirs, uint32_t M,
           const int32_t* __restrict__ n_valid_ptr, float* __restrict__ sigma, float* __restrict__ rgb,
           float* __restrict__ geo) {
     constexpr MlpLayout L = make_layout(K1, H, HC);
@@ -306,7 +321,8 @@ k_mlp_fwd(const uint32_t* __restrict__ wp, const float* __restrict__ feat, const
             continue;
         }
         TileFwd<K1, H, HC> s;
-        load_feat_frags<K1>(s.a1, feat, r0, r1, v0, v1, t);
+        if (FH) load_feat_frags_h<K1>(s.a1, static_cast<const __half*>(feat), r0, r1, v0, v1, t);
+        else load_feat_frags<K1>(s.a1, static_cast<const float*>(feat), r0, r1, v0, v1, t);
         if (dirs) tile_forward<K1, H, HC, true>(s, L, wp, dirs, r0, r1, v0, v1, lane);
         else tile_forward<K1, H, HC, false>(s, L, wp, dirs, r0, r1, v0, v1, lane);
         if (t == 3) {
@@ -440,11 +456,11 @@ __device__ __forceinline__ void relu_mask(uint32_t (&d)[KS][4], const uint32_t (
         }
 }
 
-template <int K1, int H, int HC, int NW>
+template <int K1, int H, int HC, int NW, bool FH>
 __global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1)
-k_mlp_bwd(const uint32_t* __restrict__ wp, const float* __restrict__ feat, const float* __restrict__ dirs, uint32_t M,
+k_mlp_bwd(const uint32_t* __restrict__ wp, const void* __restrict__ feat, const float* __restrict__ dirs, uint32_t M,
           const int32_t* __restrict__ n_valid_ptr, const float* __restrict__ g_sigma, const float* __restrict__ g_rgb,
-          float* __restrict__ g_feat, float* __restrict__ gW1, float* __restrict__ gW2, float* __restrict__ gW3,
+          void* __restrict__ g_feat, float* __restrict__ gW1, float* __restrict__ gW2, float* __restrict__ gW3,
           float* __restrict__ gW4, float* __restrict__ gW5) {
     static_assert(H == 64 && HC == 64, "backward kernel: weight-gradient register tiling is laid out for 64-wide heads");
     static_assert(NW == 4 || NW == 8, "4 or 8 warps");
@@ -483,7 +499,8 @@ k_mlp_bwd(const uint32_t* __restrict__ wp, const float* __restrict__ feat, const
         const uint32_t r0 = tile * SM::PTS + row0, r1 = r0 + 8;
         const bool v0 = r0 < nvalid, v1 = r1 < nvalid;
         TileFwd<K1, H, HC> s;
-        load_feat_frags<K1>(s.a1, feat, r0, r1, v0, v1, t);
+        if (FH) load_feat_frags_h<K1>(s.a1, static_cast<const __half*>(feat), r0, r1, v0, v1, t);
+        else load_feat_frags<K1>(s.a1, static_cast<const float*>(feat), r0, r1, v0, v1, t);
         store_frags<K1 / 16>(sm + SM::O_F, SM::P_F, row0, s.a1, t);
         tile_forward<K1, H, HC, true>(s, L, wp, dirs, r0, r1, v0, v1, lane);
         store_frags<H / 16>(sm + SM::O_H1, SM::P_H, row0, s.a2, t);
@@ -573,12 +590,22 @@ k_mlp_bwd(const uint32_t* __restrict__ wp, const float* __restrict__ feat, const
         if (g_feat) {
             float acc[K1 / 8][4];
             layer_mma<H / 16, K1 / 8>(acc, d1, wp, L.B1, lane);
-            float2* q0 = reinterpret_cast<float2*>(g_feat + (size_t)r0 * K1) + t;
-            float2* q1 = reinterpret_cast<float2*>(g_feat + (size_t)r1 * K1) + t;
+            if (FH) {
+                uint32_t* q0 = reinterpret_cast<uint32_t*>(static_cast<__half*>(g_feat) + (size_t)r0 * K1) + t;
+                uint32_t* q1 = reinterpret_cast<uint32_t*>(static_cast<__half*>(g_feat) + (size_t)r1 * K1) + t;
 #pragma unroll
-            for (int nt = 0; nt < K1 / 8; ++nt) {
-                if (r0 < M) q0[4 * nt] = v0 ? make_float2(r16(acc[nt][0]), r16(acc[nt][1])) : make_float2(0.f, 0.f);
-                if (r1 < M) q1[4 * nt] = v1 ? make_float2(r16(acc[nt][2]), r16(acc[nt][3])) : make_float2(0.f, 0.f);
+                for (int nt = 0; nt < K1 / 8; ++nt) {
+                    if (r0 < M) q0[4 * nt] = v0 ? pack_h2(acc[nt][0], acc[nt][1]) : 0u;
+                    if (r1 < M) q1[4 * nt] = v1 ? pack_h2(acc[nt][2], acc[nt][3]) : 0u;
+                }
+            } else {
+                float2* q0 = reinterpret_cast<float2*>(static_cast<float*>(g_feat) + (size_t)r0 * K1) + t;
+                float2* q1 = reinterpret_cast<float2*>(static_cast<float*>(g_feat) + (size_t)r1 * K1) + t;
+#pragma unroll
+                for (int nt = 0; nt < K1 / 8; ++nt) {
+                    if (r0 < M) q0[4 * nt] = v0 ? make_float2(r16(acc[nt][0]), r16(acc[nt][1])) : make_float2(0.f, 0.f);
+                    if (r1 < M) q1[4 * nt] = v1 ? make_float2(r16(acc[nt][2]), r16(acc[nt][3])) : make_float2(0.f, 0.f);
+                }
             }
         }
         __syncthreads();
@@ -683,8 +710,8 @@ int tnl_mlp_pack_weights(const tnl_mlp_dims* dims, const float* W1, const float*
     return finish_launch("mlp_pack_weights");
 }
 
-int tnl_mlp_forward(const tnl_mlp_dims* dims, const void* packed, const float* feat, const float* dirs, uint32_t M,
-                    const int32_t* n_valid, float* sigma, float* rgb, float* geo, tnl_stream_t stream) {
+int tnl_mlp_forward(const tnl_mlp_dims* dims, const void* packed, const void* feat, int feat_fp16, const float* dirs,
+                    uint32_t M, const int32_t* n_valid, float* sigma, float* rgb, float* geo, tnl_stream_t stream) {
     if (M == 0) return 0;
     if (!dims_supported(dims)) {
         set_error("mlp: unsupported dims");
@@ -696,15 +723,18 @@ int tnl_mlp_forward(const tnl_mlp_dims* dims, const void* packed, const float* f
     const uint32_t ntiles = ceil_div(M, 16u);
     const uint32_t blocks = min(ceil_div(ntiles, 4u), (uint32_t)(kNumSM * 16));
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-#define CALL(K, HH, HCC) \
-    k_mlp_fwd<K, HH, HCC><<<blocks, 128, 0, s>>>(static_cast<const uint32_t*>(packed), feat, dirs, M, n_valid, sigma, rgb, geo)
+#define CALL(K, HH, HCC)                                                                                                  \
+    do {                                                                                                                 \
+        if (feat_fp16) k_mlp_fwd<K, HH, HCC, true><<<blocks, 128, 0, s>>>(static_cast<const uint32_t*>(packed), feat, dirs, M, n_valid, sigma, rgb, geo); \
+        else k_mlp_fwd<K, HH, HCC, false><<<blocks, 128, 0, s>>>(static_cast<const uint32_t*>(packed), feat, dirs, M, n_valid, sigma, rgb, geo); \
+    } while (0)
     TNL_MLP_DISPATCH(dims, CALL);
 #undef CALL
     return finish_launch("mlp_forward");
 }
 
-int tnl_mlp_backward(const tnl_mlp_dims* dims, const void* packed, const float* feat, const float* dirs, uint32_t M,
-                     const int32_t* n_valid, const float* g_sigma, const float* g_rgb, float* g_feat, float* g_W1,
+int tnl_mlp_backward(const tnl_mlp_dims* dims, const void* packed, const void* feat, int feat_fp16, const float* dirs,
+                     uint32_t M, const int32_t* n_valid, const float* g_sigma, const float* g_rgb, void* g_feat, float* g_W1,
                      float* g_W2, float* g_W3, float* g_W4, float* g_W5, tnl_stream_t stream) {
     if (M == 0) return 0;
     if (!dims_supported(dims) || dims->hidden != 64) {
@@ -713,23 +743,29 @@ int tnl_mlp_backward(const tnl_mlp_dims* dims, const void* packed, const float* 
     }
     TNL_ARG_CHECK(packed && feat && dirs && g_sigma && g_rgb && g_W1 && g_W2 && g_W3 && g_W4 && g_W5, "null pointer");
     TNL_ARG_CHECK(((uintptr_t)feat & 7) == 0 && ((uintptr_t)g_feat & 7) == 0, "feat/g_feat must be 8-byte aligned");
+    const bool fh = feat_fp16 != 0;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     // two independent 4-warp CTAs per SM: while one is in its latency-bound recompute / dX phase the other runs the
     // shared-memory-bound weight-gradient phase (TNL_MLP_BWD_NW=8 selects the single 8-warp CTA variant)
     static const int nw = getenv("TNL_MLP_BWD_NW") ? atoi(getenv("TNL_MLP_BWD_NW")) : 4;
-#define CALLB_NW(K, NW)                                                                                                  \
+#define CALLB_FH(K, NW, FHV)                                                                                             \
     do {                                                                                                                \
         using SMB = BwdSmem<K, 64, 64, NW>;                                                                             \
         static bool attr = false;                                                                                       \
         if (!attr) {                                                                                                    \
-            cudaFuncSetAttribute(k_mlp_bwd<K, 64, 64, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMB::BYTES); \
+            cudaFuncSetAttribute(k_mlp_bwd<K, 64, 64, NW, FHV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMB::BYTES); \
             attr = true;                                                                                                \
         }                                                                                                               \
         const uint32_t ntiles = ceil_div(M, (uint32_t)(16 * NW));                                                        \
         const uint32_t blocks = min(ntiles, (uint32_t)(kNumSM * (NW == 4 ? 2 : 1)));                                     \
-        k_mlp_bwd<K, 64, 64, NW><<<blocks, NW * 32, SMB::BYTES, s>>>(static_cast<const uint32_t*>(packed), feat, dirs, M, \
-                                                                     n_valid, g_sigma, g_rgb, g_feat, g_W1, g_W2, g_W3,  \
-                                                                     g_W4, g_W5);                                        \
+        k_mlp_bwd<K, 64, 64, NW, FHV><<<blocks, NW * 32, SMB::BYTES, s>>>(static_cast<const uint32_t*>(packed), feat, dirs, \
+                                                                          M, n_valid, g_sigma, g_rgb, g_feat, g_W1, g_W2, \
+                                                                          g_W3, g_W4, g_W5);                             \
+    } while (0)
+#define CALLB_NW(K, NW)                  \
+    do {                                 \
+        if (fh) CALLB_FH(K, NW, true);   \
+        else CALLB_FH(K, NW, false);     \
     } while (0)
 #define CALLB(K)                  \
     do {                          \
@@ -741,6 +777,7 @@ int tnl_mlp_backward(const tnl_mlp_dims* dims, const void* packed, const float* 
     else CALLB(144);
 #undef CALLB
 #undef CALLB_NW
+#undef CALLB_FH
     return finish_launch("mlp_backward");
 }
 

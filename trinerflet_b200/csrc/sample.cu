@@ -58,10 +58,22 @@ __device__ __forceinline__ void plane_coords(const float* __restrict__ xyz, uint
     }
 }
 
+__device__ __forceinline__ uint2 pack4h(float4 v) {
+    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+__device__ __forceinline__ float4 unpack4h(uint2 u) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// HALF: features are written as fp16 -- the rounding the first nn.Linear applies under autocast anyway (network.py:127),
+// moved into the producer so that the feature stream costs half the bytes.
+template <bool HALF>
 __global__ void __launch_bounds__(256)
 k_sample_fwd(const float* __restrict__ planes, const float* __restrict__ xyz, uint32_t M, int R, int C, float inv_bound,
              int fp16_coords, const int32_t* __restrict__ n_valid, const int32_t* __restrict__ perm,
-             float* __restrict__ feat) {
+             void* __restrict__ feat_) {
     const int cq_per = C >> 2;
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t total = (uint64_t)M * 3 * cq_per;
@@ -70,9 +82,10 @@ k_sample_fwd(const float* __restrict__ planes, const float* __restrict__ xyz, ui
     const int p = (int)((idx / cq_per) % 3);
     uint32_t m = (uint32_t)(idx / ((uint64_t)3 * cq_per));
     if (perm) m = (uint32_t)__ldg(perm + m);
-    float4* dst = reinterpret_cast<float4*>(feat + (size_t)m * 3 * C + (size_t)p * C) + cq;
+    const size_t q4 = ((size_t)m * 3 * C + (size_t)p * C) / 4 + cq;   // index of this thread's 4-channel group
     if (n_valid && (int32_t)m >= *n_valid) {
-        *dst = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (HALF) reinterpret_cast<uint2*>(feat_)[q4] = make_uint2(0u, 0u);
+        else reinterpret_cast<float4*>(feat_)[q4] = make_float4(0.f, 0.f, 0.f, 0.f);
         return;
     }
     float gx, gy;
@@ -97,7 +110,8 @@ k_sample_fwd(const float* __restrict__ planes, const float* __restrict__ xyz, ui
         const float4 v = __ldg(base + dy + dx);
         acc.x = fmaf(v.x, t.se, acc.x); acc.y = fmaf(v.y, t.se, acc.y); acc.z = fmaf(v.z, t.se, acc.z); acc.w = fmaf(v.w, t.se, acc.w);
     }
-    *dst = acc;
+    if (HALF) reinterpret_cast<uint2*>(feat_)[q4] = pack4h(acc);
+    else reinterpret_cast<float4*>(feat_)[q4] = acc;
 }
 
 __device__ __forceinline__ void red_add_v4(float* addr, float4 v, float w) {
@@ -106,8 +120,9 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v, float w) {
                  : "memory");
 }
 
+template <bool HALF>
 __global__ void __launch_bounds__(256)
-k_sample_bwd(const float* __restrict__ g_feat, const float* __restrict__ xyz, uint32_t M, int R, int C, float inv_bound,
+k_sample_bwd(const void* __restrict__ g_feat_, const float* __restrict__ xyz, uint32_t M, int R, int C, float inv_bound,
              int fp16_coords, const int32_t* __restrict__ n_valid, const int32_t* __restrict__ perm,
              float* __restrict__ g_planes) {
     const int cq_per = C >> 2;
@@ -119,7 +134,9 @@ k_sample_bwd(const float* __restrict__ g_feat, const float* __restrict__ xyz, ui
     uint32_t m = (uint32_t)(idx / ((uint64_t)3 * cq_per));
     if (perm) m = (uint32_t)__ldg(perm + m);
     if (n_valid && (int32_t)m >= *n_valid) return;
-    const float4 g = __ldg(reinterpret_cast<const float4*>(g_feat + (size_t)m * 3 * C + (size_t)p * C) + cq);
+    const size_t q4 = ((size_t)m * 3 * C + (size_t)p * C) / 4 + cq;
+    const float4 g = HALF ? unpack4h(__ldg(reinterpret_cast<const uint2*>(g_feat_) + q4))
+                          : __ldg(reinterpret_cast<const float4*>(g_feat_) + q4);
     if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) return;  // adding zeros is a no-op
     float gx, gy;
     plane_coords(xyz, m, p, inv_bound, fp16_coords, gx, gy);
@@ -139,28 +156,36 @@ using namespace tnl;
 extern "C" {
 
 int tnl_sample_planes_forward(const float* planes, const float* xyz, uint32_t M, uint32_t R, uint32_t C, float inv_bound,
-                              int fp16_coords, const int32_t* n_valid, const int32_t* perm, float* feat,
+                              int fp16_coords, const int32_t* n_valid, const int32_t* perm, void* feat, int feat_fp16,
                               tnl_stream_t stream) {
     if (M == 0) return 0;
     TNL_ARG_CHECK(planes && xyz && feat, "null pointer");
     TNL_ARG_CHECK(C >= 4 && C % 4 == 0 && R >= 2, "C must be a multiple of 4, R >= 2");
     TNL_ARG_CHECK(((uintptr_t)planes & 15) == 0 && ((uintptr_t)feat & 15) == 0, "planes/feat must be 16-byte aligned");
     const uint64_t total = (uint64_t)M * 3 * (C / 4);
-    k_sample_fwd<<<(unsigned)ceil_div(total, (uint64_t)256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        planes, xyz, M, (int)R, (int)C, inv_bound, fp16_coords, n_valid, perm, feat);
+    if (feat_fp16)
+        k_sample_fwd<true><<<(unsigned)ceil_div(total, (uint64_t)256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+            planes, xyz, M, (int)R, (int)C, inv_bound, fp16_coords, n_valid, perm, feat);
+    else
+        k_sample_fwd<false><<<(unsigned)ceil_div(total, (uint64_t)256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+            planes, xyz, M, (int)R, (int)C, inv_bound, fp16_coords, n_valid, perm, feat);
     return finish_launch("sample_planes_forward");
 }
 
-int tnl_sample_planes_backward(const float* g_feat, const float* xyz, uint32_t M, uint32_t R, uint32_t C, float inv_bound,
-                               int fp16_coords, const int32_t* n_valid, const int32_t* perm, float* g_planes,
-                               tnl_stream_t stream) {
+int tnl_sample_planes_backward(const void* g_feat, int feat_fp16, const float* xyz, uint32_t M, uint32_t R, uint32_t C,
+                               float inv_bound, int fp16_coords, const int32_t* n_valid, const int32_t* perm,
+                               float* g_planes, tnl_stream_t stream) {
     if (M == 0) return 0;
     TNL_ARG_CHECK(g_feat && xyz && g_planes, "null pointer");
     TNL_ARG_CHECK(C >= 4 && C % 4 == 0 && R >= 2, "C must be a multiple of 4, R >= 2");
     TNL_ARG_CHECK(((uintptr_t)g_planes & 15) == 0 && ((uintptr_t)g_feat & 15) == 0, "g_planes/g_feat must be 16-byte aligned");
     const uint64_t total = (uint64_t)M * 3 * (C / 4);
-    k_sample_bwd<<<(unsigned)ceil_div(total, (uint64_t)256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        g_feat, xyz, M, (int)R, (int)C, inv_bound, fp16_coords, n_valid, perm, g_planes);
+    if (feat_fp16)
+        k_sample_bwd<true><<<(unsigned)ceil_div(total, (uint64_t)256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+            g_feat, xyz, M, (int)R, (int)C, inv_bound, fp16_coords, n_valid, perm, g_planes);
+    else
+        k_sample_bwd<false><<<(unsigned)ceil_div(total, (uint64_t)256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+            g_feat, xyz, M, (int)R, (int)C, inv_bound, fp16_coords, n_valid, perm, g_planes);
     return finish_launch("sample_planes_backward");
 }
 

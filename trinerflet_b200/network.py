@@ -45,14 +45,17 @@ class _FieldMLP(Function):
 
     @staticmethod
     def forward(ctx, feat, dirs, n_valid, W1, W2, W3, W4, W5):
-        feat = feat.contiguous().float()
+        feat = feat.contiguous()
+        if feat.dtype != torch.float16:
+            feat = feat.float()
+        fh = int(feat.dtype == torch.float16)
         dirs = dirs.detach().contiguous().float()
         M = feat.shape[0]
         dims = MlpDims(W1.shape[1], W1.shape[0], W4.shape[0])
         packed = pack_mlp_weights(dims, (W1, W2, W3, W4, W5))
         sigma = torch.empty(M, device=feat.device, dtype=torch.float32)
         rgb = torch.empty(M, 3, device=feat.device, dtype=torch.float32)
-        call("tnl_mlp_forward", ctypes.byref(dims), ptr(packed), ptr(feat), ptr(dirs), M, ptr(n_valid), ptr(sigma),
+        call("tnl_mlp_forward", ctypes.byref(dims), ptr(packed), ptr(feat), fh, ptr(dirs), M, ptr(n_valid), ptr(sigma),
              ptr(rgb), None, stream())
         ctx.save_for_backward(feat, dirs, packed, n_valid if n_valid is not None else torch.empty(0))
         ctx.dims = (dims.in_dim, dims.hidden, dims.hidden_c, n_valid is not None)
@@ -69,7 +72,7 @@ class _FieldMLP(Function):
         g_rgb = g_rgb.contiguous().float()
         g_feat = torch.empty_like(feat)
         gW = [torch.zeros(s, device=feat.device, dtype=torch.float32) for s in ctx.wshapes]
-        call("tnl_mlp_backward", ctypes.byref(dims), ptr(packed), ptr(feat), ptr(dirs), M,
+        call("tnl_mlp_backward", ctypes.byref(dims), ptr(packed), ptr(feat), int(feat.dtype == torch.float16), ptr(dirs), M,
              ptr(n_valid) if has_nv else None, ptr(g_sigma), ptr(g_rgb), ptr(g_feat), *[ptr(g) for g in gW], stream())
         if has_nv:
             pass  # rows >= *n_valid of g_feat are never read: the sampling backward skips them with the same counter
@@ -81,14 +84,16 @@ class _DensityMLP(Function):
 
     @staticmethod
     def forward(ctx, feat, W1, W2, W3, W4, W5):
-        feat = feat.contiguous().float()
+        feat = feat.contiguous()
+        if feat.dtype != torch.float16:
+            feat = feat.float()
         M = feat.shape[0]
         dims = MlpDims(W1.shape[1], W1.shape[0], W4.shape[0])
         packed = pack_mlp_weights(dims, (W1, W2, W3, W4, W5))
         sigma = torch.empty(M, device=feat.device, dtype=torch.float32)
         geo = torch.empty(M, 15, device=feat.device, dtype=torch.float32)
-        call("tnl_mlp_forward", ctypes.byref(dims), ptr(packed), ptr(feat), None, M, None, ptr(sigma), None, ptr(geo),
-             stream())
+        call("tnl_mlp_forward", ctypes.byref(dims), ptr(packed), ptr(feat), int(feat.dtype == torch.float16), None, M, None,
+             ptr(sigma), None, ptr(geo), stream())
         ctx.mark_non_differentiable(sigma, geo)
         return sigma, geo
 
@@ -142,9 +147,11 @@ class NeRFNetwork(NeRFRenderer):
         if x.is_cuda and x.shape[0] >= self.spatial_sort_min_points and torch.is_grad_enabled():
             from .triplane_encoder import cell_sort
             perm = cell_sort(x, self.bound, n_valid, 64)
-        feat = self.encoder(x, bound=self.bound, n_valid=n_valid, perm=perm)
         need_grad = torch.is_grad_enabled() and any(w.requires_grad for w in self._weights())
-        if self._fused(need_grad):
+        fused = self._fused(need_grad)
+        # fused path: the feature stream between the gather and the MLP kernels is fp16 (the first Linear's own rounding)
+        feat = self.encoder(x, bound=self.bound, n_valid=n_valid, perm=perm, half_out=fused)
+        if fused:
             return _FieldMLP.apply(feat, d, n_valid, *self._weights())
         # reference op sequence (network.py:125-147); precision follows the ambient autocast state
         h = F.relu(self.sigma_net[0](feat))
@@ -158,8 +165,9 @@ class NeRFNetwork(NeRFRenderer):
         return sigma, color
 
     def density(self, x):
-        feat = self.encoder(x, bound=self.bound)
-        if not torch.is_grad_enabled() and self._fused(False):
+        fused = not torch.is_grad_enabled() and self._fused(False)
+        feat = self.encoder(x, bound=self.bound, half_out=fused)
+        if fused:
             sigma, geo = _DensityMLP.apply(feat, *self._weights())
             return {'sigma': sigma, 'geo_feat': geo}
         h = F.relu(self.sigma_net[0](feat))

@@ -188,30 +188,30 @@ def _inv_bound(bound):
 
 class _SamplePlanes(Function):
     @staticmethod
-    def forward(ctx, planes, coords, bound, fp16_coords, n_valid, perm=None):
+    def forward(ctx, planes, coords, bound, fp16_coords, n_valid, perm=None, half_out=False):
         _require_cuda_f32(planes, "planes")
         planes_cl = to_cl_planes(planes.detach())
         coords = coords.detach().contiguous().float()
         M = coords.shape[0]
         C, R = planes.shape[1], planes.shape[2]
-        feat = torch.empty(M, 3 * C, device=planes.device, dtype=torch.float32)
+        feat = torch.empty(M, 3 * C, device=planes.device, dtype=torch.float16 if half_out else torch.float32)
         inv = _inv_bound(bound)
         call("tnl_sample_planes_forward", ptr(planes_cl), ptr(coords), M, R, C, inv, int(bool(fp16_coords)),
-             ptr(n_valid), ptr(perm), ptr(feat), stream())
+             ptr(n_valid), ptr(perm), ptr(feat), int(bool(half_out)), stream())
         ctx.save_for_backward(coords, n_valid if n_valid is not None else torch.empty(0),
                               perm if perm is not None else torch.empty(0))
-        ctx.meta = (M, R, C, inv, int(bool(fp16_coords)), n_valid is not None, perm is not None)
+        ctx.meta = (M, R, C, inv, int(bool(fp16_coords)), n_valid is not None, perm is not None, bool(half_out))
         return feat
 
     @staticmethod
     def backward(ctx, g_feat):
         coords, n_valid, perm = ctx.saved_tensors
-        M, R, C, inv, fp16_coords, has_nv, has_perm = ctx.meta
-        g_feat = g_feat.contiguous().float()
+        M, R, C, inv, fp16_coords, has_nv, has_perm, half = ctx.meta
+        g_feat = g_feat.contiguous().half() if half else g_feat.contiguous().float()
         g_planes = cl_empty_planes(C, R, device=g_feat.device, zero=True)
-        call("tnl_sample_planes_backward", ptr(g_feat), ptr(coords), M, R, C, inv, fp16_coords,
+        call("tnl_sample_planes_backward", ptr(g_feat), int(half), ptr(coords), M, R, C, inv, fp16_coords,
              ptr(n_valid) if has_nv else None, ptr(perm) if has_perm else None, ptr(g_planes), stream())
-        return g_planes, None, None, None, None, None
+        return g_planes, None, None, None, None, None, None
 
 
 def cell_sort(coords, bound, n_valid=None, G=64):
@@ -225,12 +225,12 @@ def cell_sort(coords, bound, n_valid=None, G=64):
     return perm
 
 
-def sample_planes(planes, coords, bound, fp16_coords=None, n_valid=None, perm=None):
+def sample_planes(planes, coords, bound, fp16_coords=None, n_valid=None, perm=None, half_out=False):
     """planes logical [3,C,R,R] -> features [M, 3C] (fp32). fp16_coords=None follows the autocast state, as the
     reference's projection matmul does."""
     if fp16_coords is None:
         fp16_coords = torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.float16
-    return _SamplePlanes.apply(planes, coords, float(bound), bool(fp16_coords), n_valid, perm)
+    return _SamplePlanes.apply(planes, coords, float(bound), bool(fp16_coords), n_valid, perm, bool(half_out))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -384,9 +384,10 @@ class TriPlaneVolume(nn.Module):
         feat = sample_planes(plane_features, coordinates, lbound, n_valid=n_valid)
         return feat.view(feat.shape[0], 3, self.number_of_features)
 
-    def forward(self, coordinates, bound, n_valid=None, perm=None):
-        """coordinates [M,3] in [-bound, bound] -> features [M, 3C] (index p*C + c), fp32."""
-        return sample_planes(self.get_planes(), coordinates, bound, n_valid=n_valid, perm=perm)
+    def forward(self, coordinates, bound, n_valid=None, perm=None, half_out=False):
+        """coordinates [M,3] in [-bound, bound] -> features [M, 3C] (index p*C + c); fp32 as the reference's
+        grid_sample, or fp16 (half_out) for the fused MLP path, which rounds its input to fp16 anyway."""
+        return sample_planes(self.get_planes(), coordinates, bound, n_valid=n_valid, perm=perm, half_out=half_out)
 
     # -- checkpoints: accept reference (NCHW-contiguous) tensors, keep channels-last storage -------------
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
