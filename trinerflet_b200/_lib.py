@@ -101,7 +101,7 @@ def check(rc, what):
 
 
 # number of kernels each ABI call launches (for the launch counter the benchmark reports)
-KERNELS_PER_CALL = {"tnl_march_rays_train": 5, "tnl_compact_alive": 3, "tnl_cell_sort": 3}
+KERNELS_PER_CALL = {"tnl_march_rays_train": 5, "tnl_compact_alive": 3, "tnl_cell_sort": 5}
 launch_count = 0
 _profile = None  # when enabled: name -> list of (start_event, end_event, scalar_args)
 

@@ -76,8 +76,7 @@ k_idwt_bwd(const float* __restrict__ gout, float* __restrict__ g_x, float* __res
     float* mid0 = smem;
     float* stage0 = smem + 2 * Cfg::MID_B;
     const int tid = threadIdx.x;
-    const IdwtGeom g = idwt_geom<Cfg>(tid, IdwtBlock{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z + plane0 * (C / Cfg::CG)}, n, C,
-                                     rows_per_cta);
+    const IdwtGeom g = idwt_geom<Cfg>(tid, IdwtBlock{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z + plane0}, n, C, rows_per_cta);
     BwdState st;
     bwd_state_init<Cfg>(st, g, gout);
     const float reg = (yh != nullptr && reg_grad != nullptr) ? reg_coef * __ldg(reg_grad) : 0.f;
@@ -125,7 +124,7 @@ static int launch_bwd(const float* g, float* g_x, float* g_yh, uint32_t n, uint3
     }
     unsigned gx, gy, gz, rows;
     idwt_grid<Cfg>(n, C, kNumSM, gx, gy, gz, rows);
-    gz = nplanes * (C / Cfg::CG);
+    gz = nplanes;
     k_idwt_bwd<Cfg><<<dim3(gx, gy, gz), Cfg::NT, Cfg::SMEM_B, stream>>>(g, g_x, g_yh, (int)n, (int)C, (int)rows, yh, reg_grad,
                                                                         reg_coef, (int)plane0);
     return finish_launch("idwt_level_backward");

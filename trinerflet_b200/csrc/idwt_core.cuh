@@ -127,10 +127,12 @@ TNL_HD IdwtGeom idwt_geom(int tid, IdwtBlock b, int n, int C, int rows_per_cta) 
     IdwtGeom g;
     g.n = n;
     g.C = C;
+    // channel chunks of the same strip are adjacent in launch order (bx fastest): they read the two halves of the same
+    // 128-byte lines, so the second one hits L2 (ncu: with the chunk in bz every input line came from DRAM twice)
     const int chunks = C / Cfg::CG;
-    g.plane = b.bz / chunks;
-    g.c0 = (b.bz % chunks) * Cfg::CG;
-    g.m0 = b.bx * Cfg::TM;
+    g.plane = b.bz;
+    g.c0 = (b.bx % chunks) * Cfg::CG;
+    g.m0 = (b.bx / chunks) * Cfg::TM;
     g.row_lo = b.by * rows_per_cta;
     g.row_hi = g.row_lo + rows_per_cta < n ? g.row_lo + rows_per_cta : n;
     g.col = tid / Cfg::CG;
@@ -438,8 +440,8 @@ TNL_HD void bwd_phase_b(const IdwtGeom& g, const float* mid, float* g_x, float* 
 // launch geometry shared by the kernel launcher and the emulator
 template <typename Cfg>
 inline void idwt_grid(unsigned n, unsigned C, unsigned num_sm, unsigned& gx, unsigned& gy, unsigned& gz, unsigned& rows) {
-    gx = (n + Cfg::TM - 1) / Cfg::TM;
-    gz = 3 * (C / Cfg::CG);
+    gx = ((n + Cfg::TM - 1) / Cfg::TM) * (C / Cfg::CG);
+    gz = 3;
     rows = 96;  // halo overhead 8/rows; shrink the chunk until the grid covers the machine a few times
     while (rows > 24 && gx * ((n + rows - 1) / rows) * gz < 4 * num_sm) rows /= 2;
     if (rows > n) rows = n;

@@ -43,48 +43,82 @@ __global__ void k_cell_hist(const float* __restrict__ xyz, uint32_t M, const int
     atomicAdd(hist + key, 1u);
 }
 
-// pass 2 (single block): exclusive scan of the histogram in place
-__global__ void k_cell_scan(uint32_t* __restrict__ hist, uint32_t nbins) {
+// pass 2: exclusive scan of the histogram in place, three small kernels (4096 bins per block):
+//   block sums -> scan of the block sums (one block) -> per-block exclusive scan + block offset
+constexpr int kBinsPerBlock = 4096;  // 1024 threads x 4 bins
+
+__device__ __forceinline__ uint32_t block_scan4(uint32_t (&v)[4], uint32_t* sm /*[33]*/, uint32_t& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t tsum = v[0] + v[1] + v[2] + v[3];
+    uint32_t incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) sm[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = (lane < (int)(blockDim.x >> 5)) ? sm[lane] : 0u, wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += u;
+        }
+        sm[lane] = wi - w;
+        if (lane == 31) sm[32] = wi;
+    }
+    __syncthreads();
+    total = sm[32];
+    return sm[warp] + incl - tsum;  // exclusive prefix of this thread's first bin within the block
+}
+
+__global__ void __launch_bounds__(1024) k_cell_block_sums(const uint32_t* __restrict__ hist, uint32_t nbins, uint32_t* __restrict__ sums) {
+    __shared__ uint32_t sm[33];
+    const uint32_t i0 = blockIdx.x * kBinsPerBlock + threadIdx.x * 4;
+    uint32_t v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = (i0 + j < nbins) ? hist[i0 + j] : 0u;
+    uint32_t total;
+    block_scan4(v, sm, total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_cell_scan_sums(uint32_t* __restrict__ sums, uint32_t nblocks) {
     __shared__ uint32_t sm[33];
     __shared__ uint32_t carry_s;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint32_t base = 0; base < nbins; base += blockDim.x * 4) {
-        // each thread scans 4 consecutive bins
+    for (uint32_t base = 0; base < nblocks; base += kBinsPerBlock) {
         const uint32_t i0 = base + threadIdx.x * 4;
         uint32_t v[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = (i0 + j < nbins) ? hist[i0 + j] : 0u;
-        const uint32_t tsum = v[0] + v[1] + v[2] + v[3];
-        uint32_t incl = tsum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += u;
-        }
-        if (lane == 31) sm[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t w = (lane < (int)(blockDim.x >> 5)) ? sm[lane] : 0u, wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t u = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += u;
-            }
-            sm[lane] = wi - w;
-            if (lane == 31) sm[32] = wi;
-        }
-        __syncthreads();
-        uint32_t ex = carry_s + sm[warp] + incl - tsum;
+        for (int j = 0; j < 4; ++j) v[j] = (i0 + j < nblocks) ? sums[i0 + j] : 0u;
+        uint32_t total;
+        uint32_t ex = carry_s + block_scan4(v, sm, total);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (i0 + j < nbins) hist[i0 + j] = ex;
+            if (i0 + j < nblocks) sums[i0 + j] = ex;
             ex += v[j];
         }
         __syncthreads();
-        if (threadIdx.x == 0) carry_s += sm[32];
+        if (threadIdx.x == 0) carry_s += total;
         __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_cell_scan_apply(uint32_t* __restrict__ hist, uint32_t nbins, const uint32_t* __restrict__ sums) {
+    __shared__ uint32_t sm[33];
+    const uint32_t i0 = blockIdx.x * kBinsPerBlock + threadIdx.x * 4;
+    uint32_t v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = (i0 + j < nbins) ? hist[i0 + j] : 0u;
+    uint32_t total;
+    uint32_t ex = sums[blockIdx.x] + block_scan4(v, sm, total);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (i0 + j < nbins) hist[i0 + j] = ex;
+        ex += v[j];
     }
 }
 
@@ -103,7 +137,10 @@ using namespace tnl;
 
 extern "C" {
 
-size_t tnl_cell_sort_workspace(uint32_t M, uint32_t G) { return sizeof(uint32_t) * ((size_t)G * G * G + 1 + M); }
+size_t tnl_cell_sort_workspace(uint32_t M, uint32_t G) {
+    const size_t nbins = (size_t)G * G * G + 1;
+    return sizeof(uint32_t) * (nbins + M + (nbins + kBinsPerBlock - 1) / kBinsPerBlock + 1);
+}
 
 int tnl_cell_sort(const float* xyz, uint32_t M, const int32_t* n_valid, float inv_bound, uint32_t G, int32_t* perm,
                   void* workspace, size_t workspace_bytes, tnl_stream_t stream) {
@@ -118,9 +155,13 @@ int tnl_cell_sort(const float* xyz, uint32_t M, const int32_t* n_valid, float in
     const uint32_t nbins = G * G * G + 1;
     uint32_t* hist = static_cast<uint32_t*>(workspace);
     uint32_t* keys = hist + nbins;
+    uint32_t* sums = keys + M;
+    const uint32_t nblocks = ceil_div(nbins, (uint32_t)kBinsPerBlock);
     cudaMemsetAsync(hist, 0, sizeof(uint32_t) * nbins, s);
     k_cell_hist<<<ceil_div(M, 256u), 256, 0, s>>>(xyz, M, n_valid, inv_bound, (int)G, hist, keys);
-    k_cell_scan<<<1, 1024, 0, s>>>(hist, nbins);
+    k_cell_block_sums<<<nblocks, 1024, 0, s>>>(hist, nbins, sums);
+    k_cell_scan_sums<<<1, 1024, 0, s>>>(sums, nblocks);
+    k_cell_scan_apply<<<nblocks, 1024, 0, s>>>(hist, nbins, sums);
     k_cell_scatter<<<ceil_div(M, 256u), 256, 0, s>>>(keys, M, hist, perm);
     return finish_launch("cell_sort");
 }
