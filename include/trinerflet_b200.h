@@ -165,6 +165,13 @@ int tnl_mlp_backward(const tnl_mlp_dims* dims, const void* packed, const void* f
                      void* g_feat, float* g_W1, float* g_W2, float* g_W3, float* g_W4, float* g_W5,
                      tnl_stream_t stream);
 
+/* Diagnostic: ONE tcgen05.mma product D[M x N] = A B^T with fp16 operands given as plain row-major matrices
+ * (A: [a_rows][a_cols] = [M][K] if a_mn == 0, [K][M] if a_mn != 0; B likewise with N), staged in the un-swizzled
+ * canonical shared-memory layout the fused MLP kernels use; out [128][ncols] = raw dump of the TMEM accumulator
+ * (lane-major).  Pins the descriptor conventions of csrc/umma.cuh on real hardware (tests/test_gpu_umma.py). */
+int tnl_umma_probe(const void* A, int a_rows, int a_cols, const void* B, int b_rows, int b_cols, int a_mn, int b_mn,
+                   int M, int N, int K, float* out, int ncols, tnl_stream_t stream);
+
 /* ------------------------------------------------------------------ density grid ------------- */
 /* Fused pieces of NeRFRenderer.update_extra_state (reconstruction/nerf/renderer.py:448-542). */
 /* cell-centre sample positions for a list of Morton cells of one cascade (renderer.py:474-483):

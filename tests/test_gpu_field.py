@@ -82,6 +82,15 @@ def test_mlp_backward_fp16(C, M):
     ((s_p * gs[:M // 3]).sum() + (rgb_p * grgb[:M // 3]).sum()).backward()
     for a, b in zip(W_h, W_p):
         assert rel_l2(a.grad, b.grad) <= TOL_GRAD
+    # the same through the fp16 feature stream (tcgen05 kernels): rows past n_valid neither produce nor receive anything
+    W_q = [w.cuda().requires_grad_(True) for w in W]
+    f_q = feat.cuda().half().requires_grad_(True)
+    s_q, rgb_q = _FieldMLP.apply(f_q, d.cuda(), nv, *W_q)
+    assert torch.equal(s_q, s_h) and torch.equal(rgb_q, rgb_h)
+    ((s_q * gs.cuda()).sum() + (rgb_q * grgb.cuda()).sum()).backward()
+    assert torch.equal(f_q.grad[:M // 3].float(), f_h.grad[:M // 3])
+    for a, b in zip(W_q, W_h):
+        assert rel_l2(a.grad, b.grad) <= 1e-5
 
 
 def test_oracle_fp16_emulation_matches_cuda_autocast():

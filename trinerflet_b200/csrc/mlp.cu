@@ -21,6 +21,8 @@
 //   color_net[0] cols: internal k < 16 = SH k, 16..30 = geo_feat 0..14, 31 = zero padding
 //   color_net[2] rows: 3 real rows padded with zero rows to 8 (forward) / 16 (backward)
 #include "common.cuh"
+#include "mlp_math.cuh"
+#include "mlp_tc.cuh"
 #include <stdlib.h>
 
 namespace tnl {
@@ -64,11 +66,6 @@ __device__ __forceinline__ float w_internal(int layer, int n, int k, const MlpLa
         case 4: return W4[(size_t)n * L.HC + k];
         default: return n < 3 ? W5[(size_t)n * L.HC + k] : 0.0f;
     }
-}
-
-__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
-    const __half2 h = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<const uint32_t*>(&h);
 }
 
 // one thread per packed uint32
@@ -121,13 +118,6 @@ __device__ __forceinline__ uint2 ldfrag(const uint32_t* __restrict__ wp, int off
     return __ldg(reinterpret_cast<const uint2*>(wp + off) + tile * 32 + lane);
 }
 
-__device__ __forceinline__ uint32_t relu_h2(uint32_t v) {
-    __half2 h = *reinterpret_cast<__half2*>(&v);
-    h = __hmax2(h, __float2half2_rn(0.f));
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ float2 unpack_h2(uint32_t v) { return __half22float2(*reinterpret_cast<__half2*>(&v)); }
-
 // D[16 x 8*NT] (+)= A[16 x 16*KS] * W^T, A as packed fragments a[ks][4], result in acc[nt][4]
 template <int KS, int NT>
 __device__ __forceinline__ void layer_mma(float (&acc)[NT][4], const uint32_t (&a)[KS][4], const uint32_t* __restrict__ wp,
@@ -156,26 +146,6 @@ __device__ __forceinline__ void acc_to_frag(const float (&acc)[NT][4], uint32_t 
     }
 }
 
-__device__ __forceinline__ void sh16(float x, float y, float z, float (&o)[16]) {
-    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
-    o[0] = 0.28209479177387814f;
-    o[1] = -0.48860251190291987f * y;
-    o[2] = 0.48860251190291987f * z;
-    o[3] = -0.48860251190291987f * x;
-    o[4] = 1.0925484305920792f * xy;
-    o[5] = -1.0925484305920792f * yz;
-    o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
-    o[7] = -1.0925484305920792f * xz;
-    o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
-    o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
-    o[10] = 2.8906114426405538f * xy * z;
-    o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
-    o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
-    o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
-    o[14] = 1.4453057213202769f * z * (x2 - y2);
-    o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
-}
-
 // {o[2t+OFF], o[2t+OFF+1]} as packed fp16 without dynamic register indexing
 template <int OFF>
 __device__ __forceinline__ uint32_t sel_pair(const float (&o)[16], int t) {
@@ -185,9 +155,6 @@ __device__ __forceinline__ uint32_t sel_pair(const float (&o)[16], int t) {
     if (t == 3) { lo = o[OFF + 6]; hi = o[OFF + 7]; }
     return pack_h2(lo, hi);
 }
-
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
-__device__ __forceinline__ float r16(float v) { return __half2float(__float2half_rn(v)); }
 
 // per-warp recomputable forward state for one 16-point tile
 template <int K1, int H, int HC>
@@ -679,6 +646,17 @@ static bool dims_supported(const tnl_mlp_dims* d) {
     return k_ok && h_ok;
 }
 
+// the packed block holds the mma.sync fragment layout followed (16-byte aligned) by the tcgen05 tile layout
+static size_t legacy_packed_bytes(const tnl_mlp_dims* d) {
+    const size_t b = sizeof(uint32_t) * (size_t)make_layout((int)d->in_dim, (int)d->hidden, (int)d->hidden_c).total;
+    return (b + 255) & ~(size_t)255;
+}
+// tcgen05 path: fp16 feature stream, 64-wide heads (TNL_MLP_LEGACY=1 forces the mma.sync kernels)
+static bool use_tc(const tnl_mlp_dims* d, int feat_fp16) {
+    static const bool legacy = getenv("TNL_MLP_LEGACY") != nullptr;
+    return !legacy && feat_fp16 && mlp_tc_supported(d->in_dim, d->hidden, d->hidden_c);
+}
+
 #define TNL_MLP_DISPATCH(DIMS, CALL)                                                        \
     do {                                                                                    \
         const uint32_t k_ = (DIMS)->in_dim, h_ = (DIMS)->hidden;                            \
@@ -694,7 +672,7 @@ extern "C" {
 
 size_t tnl_mlp_packed_bytes(const tnl_mlp_dims* dims) {
     if (!dims_supported(dims)) return 0;
-    return sizeof(uint32_t) * (size_t)make_layout((int)dims->in_dim, (int)dims->hidden, (int)dims->hidden_c).total;
+    return legacy_packed_bytes(dims) + (mlp_tc_supported(dims->in_dim, dims->hidden, dims->hidden_c) ? mlp_tc_packed_bytes(dims->in_dim) : 0);
 }
 
 int tnl_mlp_pack_weights(const tnl_mlp_dims* dims, const float* W1, const float* W2, const float* W3, const float* W4,
@@ -707,6 +685,9 @@ int tnl_mlp_pack_weights(const tnl_mlp_dims* dims, const float* W1, const float*
     const MlpLayout L = make_layout((int)dims->in_dim, (int)dims->hidden, (int)dims->hidden_c);
     k_mlp_pack<<<ceil_div(L.total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         L, W1, W2, W3, W4, W5, static_cast<uint32_t*>(packed));
+    if (mlp_tc_supported(dims->in_dim, dims->hidden, dims->hidden_c))
+        mlp_tc_pack(dims->in_dim, W1, W2, W3, W4, W5, static_cast<uint8_t*>(packed) + legacy_packed_bytes(dims),
+                    reinterpret_cast<cudaStream_t>(stream));
     return finish_launch("mlp_pack_weights");
 }
 
@@ -723,6 +704,12 @@ int tnl_mlp_forward(const tnl_mlp_dims* dims, const void* packed, const void* fe
     const uint32_t ntiles = ceil_div(M, 16u);
     const uint32_t blocks = min(ceil_div(ntiles, 4u), (uint32_t)(kNumSM * 16));
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (use_tc(dims, feat_fp16)) {
+        TNL_ARG_CHECK(((uintptr_t)feat & 15) == 0, "feat must be 16-byte aligned");
+        mlp_tc_forward(dims->in_dim, static_cast<const uint8_t*>(packed) + legacy_packed_bytes(dims), feat, dirs, M, n_valid, sigma,
+                       rgb, geo, s);
+        return finish_launch("mlp_forward(tcgen05)");
+    }
 #define CALL(K, HH, HCC)                                                                                                  \
     do {                                                                                                                 \
         if (feat_fp16) k_mlp_fwd<K, HH, HCC, true><<<blocks, 128, 0, s>>>(static_cast<const uint32_t*>(packed), feat, dirs, M, n_valid, sigma, rgb, geo); \
@@ -745,6 +732,12 @@ int tnl_mlp_backward(const tnl_mlp_dims* dims, const void* packed, const void* f
     TNL_ARG_CHECK(((uintptr_t)feat & 7) == 0 && ((uintptr_t)g_feat & 7) == 0, "feat/g_feat must be 8-byte aligned");
     const bool fh = feat_fp16 != 0;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (use_tc(dims, feat_fp16)) {
+        TNL_ARG_CHECK(((uintptr_t)feat & 15) == 0 && ((uintptr_t)g_feat & 15) == 0, "feat/g_feat must be 16-byte aligned");
+        mlp_tc_backward(dims->in_dim, static_cast<const uint8_t*>(packed) + legacy_packed_bytes(dims), feat, dirs, M, n_valid,
+                        g_sigma, g_rgb, g_feat, g_W1, g_W2, g_W3, g_W4, g_W5, s);
+        return finish_launch("mlp_backward(tcgen05)");
+    }
     // two independent 4-warp CTAs per SM: while one is in its latency-bound recompute / dX phase the other runs the
     // shared-memory-bound weight-gradient phase (TNL_MLP_BWD_NW=8 selects the single 8-warp CTA variant)
     static const int nw = getenv("TNL_MLP_BWD_NW") ? atoi(getenv("TNL_MLP_BWD_NW")) : 4;

@@ -1,0 +1,687 @@
+// Sigma / color MLP heads on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM) -- sm_100a only.
+//
+// Same behavioural contract as mlp.cu (NeRFNetwork.forward under fp16 autocast,
+// /root/reference/reconstruction/nerf/network.py:118-166): fp16 operands, fp32 accumulation, fp16-rounded layer
+// outputs, ReLU on the fp16 value, sigma = exp(float(h2[0])), SH degree 4 in fp32 rounded to fp16, fp32 sigmoid of the
+// fp16 logits rounded to fp16; backward = the autocast backward (fp16 activation gradients, fp32 weight gradients).
+//
+// Mapping.  CTA = 128 threads = one 128-point tile per iteration (persistent over tiles); thread t owns point t:
+// it owns TMEM lane t, so after every product it reads its own accumulator row with tcgen05.ld, applies the
+// activation / rounding, and writes the row of the next operand tile into shared memory.  All operand tiles use the
+// un-swizzled canonical layout (umma.cuh) so that one copy of a tile serves every product it takes part in:
+//   forward      h_l  [128 x N]  = act_{l-1} (K-major A) x W_l        (K-major B)      M = 128
+//   input grad   dIn  [128 x K]  = dOut_l    (K-major A) x W_l        (MN-major B)     M = 128
+//   weight grad  dW_l [64  x K] += dOut_l    (MN-major A, contraction over the 128 points) x In_l (MN-major B)   M = 64
+// The five weight-gradient accumulators stay in TMEM for the whole kernel (fp32) and are flushed once per CTA.
+// One elected thread issues the MMAs of a stage, tcgen05.commit arrives on an mbarrier, everybody waits on it.
+#include "common.cuh"
+#include "mlp_math.cuh"
+#include "mlp_tc.cuh"
+#include "umma.cuh"
+#include <stdlib.h>
+
+namespace tnl {
+using namespace umma;
+
+// ------------------------------------------------------------------------------------------------
+// packed weights: the five fp16 weight tiles, in the order / layout they have in shared memory
+//   W1 tile(64, K1) | W2 tile(16, 64) rows = reference rows (0 = sigma logit, 1..15 = geo) | W3 tile(64, 32) columns
+//   0..15 SH, 16..30 geo, 31 zero | W4 tile(64, 64) | W5 tile(16, 64) rows 0..2 real, 3..15 zero
+// ------------------------------------------------------------------------------------------------
+template <int K1>
+struct TcW {
+    static constexpr uint32_t W1 = 0;
+    static constexpr uint32_t W2 = W1 + tile_bytes(64, K1);
+    static constexpr uint32_t W3 = W2 + tile_bytes(16, 64);
+    static constexpr uint32_t W4 = W3 + tile_bytes(64, 32);
+    static constexpr uint32_t W5 = W4 + tile_bytes(64, 64);
+    static constexpr uint32_t END = W5 + tile_bytes(16, 64);
+};
+
+__global__ void k_mlp_tc_pack(int K1, const float* __restrict__ W1, const float* __restrict__ W2, const float* __restrict__ W3,
+                              const float* __restrict__ W4, const float* __restrict__ W5, uint8_t* __restrict__ out) {
+    const uint32_t n1 = 64 * K1, n2 = 16 * 64, n3 = 64 * 32, n4 = 64 * 64, n5 = 16 * 64;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t base = 0, R, Cc;
+    float v;
+    if (i < n1) { R = 64; Cc = K1; v = W1[i]; }
+    else if ((i -= n1, base += n1 * 2, i < n2)) { R = 16; Cc = 64; v = W2[i]; }
+    else if ((i -= n2, base += n2 * 2, i < n3)) { R = 64; Cc = 32; const uint32_t r = i / 32, c = i % 32; v = c < 31 ? W3[r * 31 + c] : 0.f; }
+    else if ((i -= n3, base += n3 * 2, i < n4)) { R = 64; Cc = 64; v = W4[i]; }
+    else if ((i -= n4, base += n4 * 2, i < n5)) { R = 16; Cc = 64; v = (i / 64) < 3 ? W5[i] : 0.f; }
+    else return;
+    const uint32_t r = i / Cc, c = i % Cc;
+    *reinterpret_cast<__half*>(out + base + tile_off(R, r, c)) = __float2half_rn(v);
+}
+
+// 8 fp32 -> 8 fp16 (one 16-byte tile row chunk), optional ReLU on the rounded values
+template <bool RELU>
+__device__ __forceinline__ uint4 pack8(const float* v) {
+    uint4 o;
+    o.x = pack_h2(v[0], v[1]);
+    o.y = pack_h2(v[2], v[3]);
+    o.z = pack_h2(v[4], v[5]);
+    o.w = pack_h2(v[6], v[7]);
+    if (RELU) { o.x = relu_h2(o.x); o.y = relu_h2(o.y); o.z = relu_h2(o.z); o.w = relu_h2(o.w); }
+    return o;
+}
+// zero the fp16 lanes of `d` whose counterpart in `h` (a ReLU output, never negative) is zero
+__device__ __forceinline__ uint32_t mask_h2(uint32_t d, uint32_t h) {
+    const uint32_t m = (((h & 0x7fffu) != 0u) ? 0x0000ffffu : 0u) | (((h & 0x7fff0000u) != 0u) ? 0xffff0000u : 0u);
+    return d & m;
+}
+__device__ __forceinline__ uint4 mask8(uint4 d, uint4 h) {
+    return make_uint4(mask_h2(d.x, h.x), mask_h2(d.y, h.y), mask_h2(d.z, h.z), mask_h2(d.w, h.w));
+}
+__device__ __forceinline__ uint32_t clamp_valid(const int32_t* n_valid_ptr, uint32_t M) {
+    if (!n_valid_ptr) return M;
+    const int32_t nv = *n_valid_ptr;
+    return nv < 0 ? 0u : ((uint32_t)nv < M ? (uint32_t)nv : M);
+}
+
+// K-steps of one product: D[tmem_d] (+)= A x B.  A/B descriptors advance along their contraction dimension.
+template <int KSTEPS, bool A_MN, bool B_MN>
+__device__ __forceinline__ void issue(uint32_t tmem_d, uint32_t a_base, uint32_t a_R, uint32_t a_r0, uint32_t a_c0, uint32_t b_base,
+                                      uint32_t b_R, uint32_t b_r0, uint32_t b_c0, uint32_t M, uint32_t N, bool accumulate_first) {
+    const uint32_t idesc = make_idesc(M, N, A_MN, B_MN);
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+        const uint64_t a = A_MN ? desc_mnmajor(a_base, a_R, a_r0 + 16 * ks, a_c0) : desc_kmajor(a_base, a_R, a_r0, a_c0 + 16 * ks);
+        const uint64_t b = B_MN ? desc_mnmajor(b_base, b_R, b_r0 + 16 * ks, b_c0) : desc_kmajor(b_base, b_R, b_r0, b_c0 + 16 * ks);
+        mma_f16(tmem_d, a, b, idesc, (accumulate_first || ks > 0) ? 1u : 0u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+template <int K1>
+struct TcFwdSmem {
+    static constexpr uint32_t X = TcW<K1>::END;                      // feat tile(128, K1)
+    static constexpr uint32_t ACT = X + tile_bytes(128, K1);         // h1 / h3 / h4 tile(128, 64)
+    static constexpr uint32_t I3 = ACT + tile_bytes(128, 64);        // [SH | geo | 0] tile(128, 32)
+    static constexpr uint32_t BAR = I3 + tile_bytes(128, 32);        // mbarrier (8 B) + TMEM base slot (4 B)
+    static constexpr uint32_t TOTAL = BAR + 16;
+};
+
+template <int K1, bool COLOR>
+__global__ void __launch_bounds__(128)
+k_mlp_tc_fwd(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat, const float* __restrict__ dirs, uint32_t M,
+             const int32_t* __restrict__ n_valid_ptr, float* __restrict__ sigma, float* __restrict__ rgb, float* __restrict__ geo) {
+    using W = TcW<K1>;
+    using S = TcFwdSmem<K1>;
+    constexpr uint32_t TM_A = 0, TM_B = 64, TM_COLS = 128;   // 64-wide and 16-wide accumulators
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::BAR);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + S::BAR + 8);
+    for (uint32_t i = tid * 16; i < W::END; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = __ldg(reinterpret_cast<const uint4*>(wpk + i));
+    if (tid == 0) { mbar_init(bar, 1); mbar_init_fence(); }
+    if (warp == 0) tmem_alloc(tslot, TM_COLS);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *tslot;
+    const uint32_t trow = tmem + ((warp * 32u) << 16);
+    const uint32_t sb = smem_u32(smem);
+    uint32_t phase = 0;
+    const uint32_t nvalid = clamp_valid(n_valid_ptr, M);
+    const uint32_t ntiles = ceil_div(nvalid, 128u);
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint32_t p = tile * 128 + tid;
+        const bool v = p < nvalid;
+        {   // this thread's feature row -> X tile
+            const uint4* src = reinterpret_cast<const uint4*>(feat + (size_t)p * K1);
+            uint4 x[K1 / 8];
+#pragma unroll
+            for (int kc = 0; kc < K1 / 8; ++kc) x[kc] = v ? __ldg(src + kc) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int kc = 0; kc < K1 / 8; ++kc) *reinterpret_cast<uint4*>(smem + S::X + (kc * 128 + tid) * 16) = x[kc];
+        }
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {   // h1 = feat W1^T
+            fence_after_sync();
+            issue<K1 / 16, false, false>(tmem + TM_A, sb + S::X, 128, 0, 0, sb + W::W1, 64, 0, 0, 128, 64, false);
+            commit(bar);
+        }
+        mbar_wait(bar, phase); phase ^= 1;
+        fence_after_sync();
+        {
+            float a[64];
+            tmem_load_row<64>(trow + TM_A, a);
+#pragma unroll
+            for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(smem + S::ACT + (kc * 128 + tid) * 16) = pack8<true>(a + 8 * kc);
+        }
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {   // h2 = relu(h1) W2^T
+            fence_after_sync();
+            issue<4, false, false>(tmem + TM_B, sb + S::ACT, 128, 0, 0, sb + W::W2, 16, 0, 0, 128, 16, false);
+            commit(bar);
+        }
+        mbar_wait(bar, phase); phase ^= 1;
+        fence_after_sync();
+        float h2[16];
+        tmem_load_row<16>(trow + TM_B, h2);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) h2[j] = r16(h2[j]);
+        if (p < M) {
+            sigma[p] = v ? expf(h2[0]) : 0.f;
+            if (geo) {
+#pragma unroll
+                for (int j = 0; j < 15; ++j) geo[15 * (size_t)p + j] = v ? h2[1 + j] : 0.f;
+            }
+        }
+        if (!COLOR) { fence_before_sync(); continue; }
+        {   // color_net input row: [fp16(SH16(d)) | geo | 0]
+            float d[3] = {0.f, 0.f, 0.f};
+            if (v) { d[0] = __ldg(dirs + 3 * (size_t)p); d[1] = __ldg(dirs + 3 * (size_t)p + 1); d[2] = __ldg(dirs + 3 * (size_t)p + 2); }
+            float in3[32];
+            {
+                float sh[16];
+                sh16(d[0], d[1], d[2], sh);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) in3[j] = sh[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 15; ++j) in3[16 + j] = h2[1 + j];
+            in3[31] = 0.f;
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc) *reinterpret_cast<uint4*>(smem + S::I3 + (kc * 128 + tid) * 16) = pack8<false>(in3 + 8 * kc);
+        }
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {   // h3 = in3 W3^T
+            fence_after_sync();
+            issue<2, false, false>(tmem + TM_A, sb + S::I3, 128, 0, 0, sb + W::W3, 64, 0, 0, 128, 64, false);
+            commit(bar);
+        }
+        mbar_wait(bar, phase); phase ^= 1;
+        fence_after_sync();
+        {
+            float a[64];
+            tmem_load_row<64>(trow + TM_A, a);
+#pragma unroll
+            for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(smem + S::ACT + (kc * 128 + tid) * 16) = pack8<true>(a + 8 * kc);
+        }
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {   // h4 = relu(h3) W4^T
+            fence_after_sync();
+            issue<4, false, false>(tmem + TM_A, sb + S::ACT, 128, 0, 0, sb + W::W4, 64, 0, 0, 128, 64, false);
+            commit(bar);
+        }
+        mbar_wait(bar, phase); phase ^= 1;
+        fence_after_sync();
+        {
+            float a[64];
+            tmem_load_row<64>(trow + TM_A, a);
+#pragma unroll
+            for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(smem + S::ACT + (kc * 128 + tid) * 16) = pack8<true>(a + 8 * kc);
+        }
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {   // o5 = relu(h4) W5^T
+            fence_after_sync();
+            issue<4, false, false>(tmem + TM_B, sb + S::ACT, 128, 0, 0, sb + W::W5, 16, 0, 0, 128, 16, false);
+            commit(bar);
+        }
+        mbar_wait(bar, phase); phase ^= 1;
+        fence_after_sync();
+        {
+            float o[8];
+            tmem_load_row<8>(trow + TM_B, o);
+            if (p < M && rgb) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) rgb[3 * (size_t)p + j] = v ? r16(sigmoidf_(r16(o[j]))) : 0.f;
+            }
+        }
+        fence_before_sync();   // orders this iteration's tcgen05.ld before the next iteration's MMAs (via the next __syncthreads)
+    }
+    // rows past the last tile that holds valid points: defined zeros
+    for (uint32_t p = ntiles * 128 + blockIdx.x * 128 + tid; p < M; p += gridDim.x * 128) {
+        sigma[p] = 0.f;
+        if (COLOR && rgb) { rgb[3 * (size_t)p] = 0.f; rgb[3 * (size_t)p + 1] = 0.f; rgb[3 * (size_t)p + 2] = 0.f; }
+        if (geo) for (int j = 0; j < 15; ++j) geo[15 * (size_t)p + j] = 0.f;
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_free(tmem, TM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+template <int K1>
+struct TcBwdSmem {
+    static constexpr uint32_t X = TcW<K1>::END;                   // feat            tile(128, K1)
+    static constexpr uint32_t H1 = X + tile_bytes(128, K1);       // relu(h1) -> dh1 tile(128, 64)
+    static constexpr uint32_t I3 = H1 + tile_bytes(128, 64);      // in3 tile(128, 32) -> dh2 tile(128, 16)
+    static constexpr uint32_t H3 = I3 + tile_bytes(128, 32);      // relu(h3) -> dh3
+    static constexpr uint32_t H4 = H3 + tile_bytes(128, 64);      // relu(h4) -> dh4
+    static constexpr uint32_t D5 = H4 + tile_bytes(128, 64);      // d5 tile(128, 16)
+    static constexpr uint32_t BAR = D5 + tile_bytes(128, 16);
+    static constexpr uint32_t TOTAL = BAR + 16;
+};
+
+// lane of the TMEM accumulator that holds row i of an M = 64 product (cta_group::1): rows 16w .. 16w+15 live in
+// lanes 32w .. 32w+15 (the lower half of every warp's lane quarter)
+__device__ __forceinline__ bool m64_row_of_lane(uint32_t warp, uint32_t lane, uint32_t& row) {
+    row = warp * 16 + lane;
+    return lane < 16;
+}
+
+template <int K1>
+__global__ void __launch_bounds__(128, 1)
+k_mlp_tc_bwd(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat, const float* __restrict__ dirs, uint32_t M,
+             const int32_t* __restrict__ n_valid_ptr, const float* __restrict__ g_sigma, const float* __restrict__ g_rgb,
+             __half* __restrict__ g_feat, float* __restrict__ gW1, float* __restrict__ gW2, float* __restrict__ gW3,
+             float* __restrict__ gW4, float* __restrict__ gW5) {
+    using W = TcW<K1>;
+    using S = TcBwdSmem<K1>;
+    // TMEM columns: chain accumulator | dW1 [64 x K1] | dW4 [64 x 64] | dW3 [64 x 32] | dW2^T [64 x 16] | dW5^T [64 x 16]
+    constexpr uint32_t TM_C = 0, TM_W1 = 160, TM_W4 = TM_W1 + 144, TM_W3 = TM_W4 + 64, TM_W2 = TM_W3 + 32, TM_W5 = TM_W2 + 16;
+    constexpr uint32_t TM_COLS = 512;
+    static_assert(TM_W5 + 16 <= TM_COLS && K1 <= 144, "TMEM column budget");
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::BAR);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + S::BAR + 8);
+    for (uint32_t i = tid * 16; i < W::END; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = __ldg(reinterpret_cast<const uint4*>(wpk + i));
+    if (tid == 0) { mbar_init(bar, 1); mbar_init_fence(); }
+    if (warp == 0) tmem_alloc(tslot, TM_COLS);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *tslot;
+    const uint32_t trow = tmem + ((warp * 32u) << 16);
+    const uint32_t sb = smem_u32(smem);
+    uint32_t phase = 0;
+    const uint32_t nvalid = clamp_valid(n_valid_ptr, M);
+    const uint32_t ntiles = ceil_div(nvalid, 128u);
+    bool first = true;   // the weight-gradient accumulators are initialised by the first tile's first K step
+#define TNL_STAGE_SYNC()    \
+    fence_async_smem();     \
+    fence_before_sync();    \
+    __syncthreads()
+#define TNL_STAGE_WAIT()               \
+    mbar_wait(bar, phase); phase ^= 1; \
+    fence_after_sync()
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint32_t p = tile * 128 + tid;
+        const bool v = p < nvalid;
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(feat + (size_t)p * K1);
+            uint4 x[K1 / 8];
+#pragma unroll
+            for (int kc = 0; kc < K1 / 8; ++kc) x[kc] = v ? __ldg(src + kc) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int kc = 0; kc < K1 / 8; ++kc) *reinterpret_cast<uint4*>(smem + S::X + (kc * 128 + tid) * 16) = x[kc];
+        }
+        // issue the small per-point loads early
+        float d[3] = {0.f, 0.f, 0.f}, gr[3] = {0.f, 0.f, 0.f}, gs = 0.f;
+        if (v) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { d[j] = __ldg(dirs + 3 * (size_t)p + j); gr[j] = __ldg(g_rgb + 3 * (size_t)p + j); }
+            gs = __ldg(g_sigma + p);
+        }
+        // ---------------- forward recompute ----------------
+        TNL_STAGE_SYNC();
+        if (tid == 0) {
+            fence_after_sync();
+            issue<K1 / 16, false, false>(tmem + TM_C, sb + S::X, 128, 0, 0, sb + W::W1, 64, 0, 0, 128, 64, false);
+            commit(bar);
+        }
+        TNL_STAGE_WAIT();
+        {
+            float a[64];
+            tmem_load_row<64>(trow + TM_C, a);
+#pragma unroll
+            for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(smem + S::H1 + (kc * 128 + tid) * 16) = pack8<true>(a + 8 * kc);
+        }
+        TNL_STAGE_SYNC();
+        if (tid == 0) {
+            fence_after_sync();
+            issue<4, false, false>(tmem + TM_C, sb + S::H1, 128, 0, 0, sb + W::W2, 16, 0, 0, 128, 16, false);
+            commit(bar);
+        }
+        TNL_STAGE_WAIT();
+        float logit;
+        {
+            float h2[16];
+            tmem_load_row<16>(trow + TM_C, h2);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) h2[j] = r16(h2[j]);
+            logit = h2[0];
+            float in3[32];
+            {
+                float sh[16];
+                sh16(d[0], d[1], d[2], sh);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) in3[j] = sh[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 15; ++j) in3[16 + j] = h2[1 + j];
+            in3[31] = 0.f;
+#pragma unroll
+            for (int kc = 0; kc < 4; ++kc) *reinterpret_cast<uint4*>(smem + S::I3 + (kc * 128 + tid) * 16) = pack8<false>(in3 + 8 * kc);
+        }
+        TNL_STAGE_SYNC();
+        if (tid == 0) {
+            fence_after_sync();
+            issue<2, false, false>(tmem + TM_C, sb + S::I3, 128, 0, 0, sb + W::W3, 64, 0, 0, 128, 64, false);
+            commit(bar);
+        }
+        TNL_STAGE_WAIT();
+        {
+            float a[64];
+            tmem_load_row<64>(trow + TM_C, a);
+#pragma unroll
+            for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(smem + S::H3 + (kc * 128 + tid) * 16) = pack8<true>(a + 8 * kc);
+        }
+        TNL_STAGE_SYNC();
+        if (tid == 0) {
+            fence_after_sync();
+            issue<4, false, false>(tmem + TM_C, sb + S::H3, 128, 0, 0, sb + W::W4, 64, 0, 0, 128, 64, false);
+            commit(bar);
+        }
+        TNL_STAGE_WAIT();
+        {
+            float a[64];
+            tmem_load_row<64>(trow + TM_C, a);
+#pragma unroll
+            for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(smem + S::H4 + (kc * 128 + tid) * 16) = pack8<true>(a + 8 * kc);
+        }
+        TNL_STAGE_SYNC();
+        if (tid == 0) {
+            fence_after_sync();
+            issue<4, false, false>(tmem + TM_C, sb + S::H4, 128, 0, 0, sb + W::W5, 16, 0, 0, 128, 16, false);
+            commit(bar);
+        }
+        TNL_STAGE_WAIT();
+        {   // d5 = half(g_rgb) * s * (1 - s), rounded to fp16; columns 3..15 zero
+            float o[8];
+            tmem_load_row<8>(trow + TM_C, o);
+            float d5[8];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const float s = r16(sigmoidf_(r16(o[j])));
+                d5[j] = v ? r16(gr[j]) * s * (1.f - s) : 0.f;
+            }
+#pragma unroll
+            for (int j = 3; j < 8; ++j) d5[j] = 0.f;
+            *reinterpret_cast<uint4*>(smem + S::D5 + (0 * 128 + tid) * 16) = pack8<false>(d5);
+            *reinterpret_cast<uint4*>(smem + S::D5 + (1 * 128 + tid) * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        // ---------------- backward chain; every stage also accumulates one weight gradient ----------------
+        TNL_STAGE_SYNC();
+        if (tid == 0) {   // dh4 = d5 W5 ;  dW5^T += h4^T d5
+            fence_after_sync();
+            issue<1, false, true>(tmem + TM_C, sb + S::D5, 128, 0, 0, sb + W::W5, 16, 0, 0, 128, 64, false);
+            issue<8, true, true>(tmem + TM_W5, sb + S::H4, 128, 0, 0, sb + S::D5, 128, 0, 0, 64, 16, !first);
+            commit(bar);
+        }
+        TNL_STAGE_WAIT();
+        {
+            float a[64];
+            tmem_load_row<64>(trow + TM_C, a);
+#pragma unroll
+            for (int kc = 0; kc < 8; ++kc) {
+                uint4* q = reinterpret_cast<uint4*>(smem + S::H4 + (kc * 128 + tid) * 16);
+                *q = mask8(pack8<false>(a + 8 * kc), *q);
+            }
+        }
+        TNL_STAGE_SYNC();
+        if (tid == 0) {   // dh3 = dh4 W4 ;  dW4 += dh4^T h3
+            fence_after_sync();
+            issue<4, false, true>(tmem + TM_C, sb + S::H4, 128, 0, 0, sb + W::W4, 64, 0, 0, 128, 64, false);
+            issue<8, true, true>(tmem + TM_W4, sb + S::H4, 128, 0, 0, sb + S::H3, 128, 0, 0, 64, 64, !first);
+            commit(bar);
+        }
+        TNL_STAGE_WAIT();
+        {
+            float a[64];
+            tmem_load_row<64>(trow + TM_C, a);
+#pragma unroll
+            for (int kc = 0; kc < 8; ++kc) {
+                uint4* q = reinterpret_cast<uint4*>(smem + S::H3 + (kc * 128 + tid) * 16);
+                *q = mask8(pack8<false>(a + 8 * kc), *q);
+            }
+        }
+        TNL_STAGE_SYNC();
+        if (tid == 0) {   // d(in3)[:, 16:32] = dh3 W3[:, 16:32] ;  dW3 += dh3^T in3
+            fence_after_sync();
+            issue<4, false, true>(tmem + TM_C, sb + S::H3, 128, 0, 0, sb + W::W3, 64, 0, 16, 128, 16, false);
+            issue<8, true, true>(tmem + TM_W3, sb + S::H3, 128, 0, 0, sb + S::I3, 128, 0, 0, 64, 32, !first);
+            commit(bar);
+        }
+        TNL_STAGE_WAIT();
+        {   // dh2: column 0 <- g_sigma * exp(clamp(logit, -15, 15)) (trunc_exp backward), columns 1..15 <- d(geo)
+            float a[16];
+            tmem_load_row<16>(trow + TM_C, a);
+            float dh2[16];
+            dh2[0] = gs * expf(fminf(fmaxf(logit, -15.f), 15.f));
+#pragma unroll
+            for (int j = 0; j < 15; ++j) dh2[1 + j] = a[j];
+            *reinterpret_cast<uint4*>(smem + S::I3 + (0 * 128 + tid) * 16) = pack8<false>(dh2);
+            *reinterpret_cast<uint4*>(smem + S::I3 + (1 * 128 + tid) * 16) = pack8<false>(dh2 + 8);
+        }
+        TNL_STAGE_SYNC();
+        if (tid == 0) {   // dh1 = dh2 W2 ;  dW2^T += h1^T dh2
+            fence_after_sync();
+            issue<1, false, true>(tmem + TM_C, sb + S::I3, 128, 0, 0, sb + W::W2, 16, 0, 0, 128, 64, false);
+            issue<8, true, true>(tmem + TM_W2, sb + S::H1, 128, 0, 0, sb + S::I3, 128, 0, 0, 64, 16, !first);
+            commit(bar);
+        }
+        TNL_STAGE_WAIT();
+        {
+            float a[64];
+            tmem_load_row<64>(trow + TM_C, a);
+#pragma unroll
+            for (int kc = 0; kc < 8; ++kc) {
+                uint4* q = reinterpret_cast<uint4*>(smem + S::H1 + (kc * 128 + tid) * 16);
+                *q = mask8(pack8<false>(a + 8 * kc), *q);
+            }
+        }
+        TNL_STAGE_SYNC();
+        if (tid == 0) {   // g_feat = dh1 W1 ;  dW1 += dh1^T feat
+            fence_after_sync();
+            issue<4, false, true>(tmem + TM_C, sb + S::H1, 128, 0, 0, sb + W::W1, 64, 0, 0, 128, K1, false);
+            issue<8, true, true>(tmem + TM_W1, sb + S::H1, 128, 0, 0, sb + S::X, 128, 0, 0, 64, K1, !first);
+            commit(bar);
+        }
+        TNL_STAGE_WAIT();
+        {
+            float a[K1];
+            tmem_load_row<K1>(trow + TM_C, a);
+            if (g_feat && p < M) {
+                uint4* dst = reinterpret_cast<uint4*>(g_feat + (size_t)p * K1);
+#pragma unroll
+                for (int kc = 0; kc < K1 / 8; ++kc) dst[kc] = v ? pack8<false>(a + 8 * kc) : make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        first = false;
+    }
+#undef TNL_STAGE_SYNC
+#undef TNL_STAGE_WAIT
+    // ---------------- flush the weight gradients (fp32, one atomicAdd per element per CTA) ----------------
+    if (!first) {
+        uint32_t row;
+        const bool have = m64_row_of_lane(warp, lane, row);
+        {
+            float a[K1];
+            tmem_load_row<K1>(trow + TM_W1, a);
+            if (have)
+#pragma unroll
+                for (int k = 0; k < K1; ++k) atomicAdd(gW1 + (size_t)row * K1 + k, a[k]);
+        }
+        {
+            float a[64];
+            tmem_load_row<64>(trow + TM_W4, a);
+            if (have)
+#pragma unroll
+                for (int k = 0; k < 64; ++k) atomicAdd(gW4 + (size_t)row * 64 + k, a[k]);
+        }
+        {
+            float a[32];
+            tmem_load_row<32>(trow + TM_W3, a);
+            if (have)
+#pragma unroll
+                for (int k = 0; k < 31; ++k) atomicAdd(gW3 + (size_t)row * 31 + k, a[k]);
+        }
+        {   // transposed accumulators: lane row = input feature k, column = output row n
+            float a[16];
+            tmem_load_row<16>(trow + TM_W2, a);
+            if (have)
+#pragma unroll
+                for (int n = 0; n < 16; ++n) atomicAdd(gW2 + (size_t)n * 64 + row, a[n]);
+            float b[16];
+            tmem_load_row<16>(trow + TM_W5, b);
+            if (have)
+#pragma unroll
+                for (int n = 0; n < 3; ++n) atomicAdd(gW5 + (size_t)n * 64 + row, b[n]);
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_free(tmem, TM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// probe: one product with operands given as plain row-major fp16 matrices, raw TMEM dump.  Used by
+// profiles/probe_umma.py and tests/test_gpu_umma.py to pin the descriptor conventions on real hardware.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_umma_probe(const __half* __restrict__ A, int a_rows, int a_cols, const __half* __restrict__ B, int b_rows, int b_cols, int a_mn,
+             int b_mn, int Mm, int Nn, int Kk, float* __restrict__ out, int ncols) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tslot;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t a_bytes = tile_bytes(a_rows, a_cols);
+    for (int i = tid; i < a_rows * a_cols; i += 128) *reinterpret_cast<__half*>(smem + tile_off(a_rows, i / a_cols, i % a_cols)) = A[i];
+    for (int i = tid; i < b_rows * b_cols; i += 128) *reinterpret_cast<__half*>(smem + a_bytes + tile_off(b_rows, i / b_cols, i % b_cols)) = B[i];
+    if (tid == 0) { mbar_init(&bar, 1); mbar_init_fence(); }
+    if (warp == 0) tmem_alloc(&tslot, 256);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = tslot;
+    const uint32_t sb = smem_u32(smem);
+    if (tid == 0) {
+        const uint32_t idesc = make_idesc(Mm, Nn, a_mn != 0, b_mn != 0);
+        for (int ks = 0; ks < Kk / 16; ++ks) {
+            const uint64_t a = a_mn ? desc_mnmajor(sb, a_rows, 16 * ks, 0) : desc_kmajor(sb, a_rows, 0, 16 * ks);
+            const uint64_t b = b_mn ? desc_mnmajor(sb + a_bytes, b_rows, 16 * ks, 0) : desc_kmajor(sb + a_bytes, b_rows, 0, 16 * ks);
+            mma_f16(tmem, a, b, idesc, ks > 0 ? 1u : 0u);
+        }
+        commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    fence_after_sync();
+    for (int c = 0; c < ncols; c += 8) {
+        uint32_t r[8];
+        tmem_ld8(tmem + ((warp * 32u) << 16) + c, r);
+        tmem_ld_wait();
+        pin<8>(r);
+        for (int j = 0; j < 8; ++j) out[(size_t)tid * ncols + c + j] = __uint_as_float(r[j]);
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_free(tmem, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side (called from mlp.cu's C-ABI entry points)
+// ------------------------------------------------------------------------------------------------
+bool mlp_tc_supported(uint32_t in_dim, uint32_t hidden, uint32_t hidden_c) {
+    return (in_dim == 48 || in_dim == 96 || in_dim == 144) && hidden == 64 && hidden_c == 64;
+}
+
+size_t mlp_tc_packed_bytes(uint32_t in_dim) { return (size_t)64 * in_dim * 2 + 2048 + 4096 + 8192 + 2048; }
+
+void mlp_tc_pack(uint32_t in_dim, const float* W1, const float* W2, const float* W3, const float* W4, const float* W5, void* out,
+                 cudaStream_t s) {
+    const uint32_t total = 64 * in_dim + 16 * 64 + 64 * 32 + 64 * 64 + 16 * 64;
+    k_mlp_tc_pack<<<ceil_div(total, 256u), 256, 0, s>>>((int)in_dim, W1, W2, W3, W4, W5, static_cast<uint8_t*>(out));
+}
+
+template <int K1>
+static void launch_fwd(const void* wpk, const void* feat, const float* dirs, uint32_t M, const int32_t* n_valid, float* sigma,
+                       float* rgb, float* geo, cudaStream_t s) {
+    using S = TcFwdSmem<K1>;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_mlp_tc_fwd<K1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL);
+        cudaFuncSetAttribute(k_mlp_tc_fwd<K1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL);
+        attr = true;
+    }
+    const uint32_t per_sm = (227u * 1024u) / (S::TOTAL + 1024u);
+    const uint32_t blocks = min(ceil_div(M, 128u), (uint32_t)kNumSM * (per_sm < 1 ? 1u : per_sm));
+    if (dirs)
+        k_mlp_tc_fwd<K1, true><<<blocks, 128, S::TOTAL, s>>>(static_cast<const uint8_t*>(wpk), static_cast<const __half*>(feat), dirs, M,
+                                                              n_valid, sigma, rgb, geo);
+    else
+        k_mlp_tc_fwd<K1, false><<<blocks, 128, S::TOTAL, s>>>(static_cast<const uint8_t*>(wpk), static_cast<const __half*>(feat), dirs, M,
+                                                               n_valid, sigma, rgb, geo);
+}
+
+void mlp_tc_forward(uint32_t in_dim, const void* wpk, const void* feat, const float* dirs, uint32_t M, const int32_t* n_valid,
+                    float* sigma, float* rgb, float* geo, cudaStream_t s) {
+    if (in_dim == 48) launch_fwd<48>(wpk, feat, dirs, M, n_valid, sigma, rgb, geo, s);
+    else if (in_dim == 96) launch_fwd<96>(wpk, feat, dirs, M, n_valid, sigma, rgb, geo, s);
+    else launch_fwd<144>(wpk, feat, dirs, M, n_valid, sigma, rgb, geo, s);
+}
+
+template <int K1>
+static void launch_bwd(const void* wpk, const void* feat, const float* dirs, uint32_t M, const int32_t* n_valid, const float* g_sigma,
+                       const float* g_rgb, void* g_feat, float* gW1, float* gW2, float* gW3, float* gW4, float* gW5, cudaStream_t s) {
+    using S = TcBwdSmem<K1>;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_mlp_tc_bwd<K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL);
+        attr = true;
+    }
+    const uint32_t blocks = min(ceil_div(M, 128u), (uint32_t)kNumSM);   // one CTA per SM: it owns all 512 TMEM columns
+    k_mlp_tc_bwd<K1><<<blocks, 128, S::TOTAL, s>>>(static_cast<const uint8_t*>(wpk), static_cast<const __half*>(feat), dirs, M, n_valid,
+                                                   g_sigma, g_rgb, static_cast<__half*>(g_feat), gW1, gW2, gW3, gW4, gW5);
+}
+
+void mlp_tc_backward(uint32_t in_dim, const void* wpk, const void* feat, const float* dirs, uint32_t M, const int32_t* n_valid,
+                     const float* g_sigma, const float* g_rgb, void* g_feat, float* gW1, float* gW2, float* gW3, float* gW4, float* gW5,
+                     cudaStream_t s) {
+    if (in_dim == 48) launch_bwd<48>(wpk, feat, dirs, M, n_valid, g_sigma, g_rgb, g_feat, gW1, gW2, gW3, gW4, gW5, s);
+    else if (in_dim == 96) launch_bwd<96>(wpk, feat, dirs, M, n_valid, g_sigma, g_rgb, g_feat, gW1, gW2, gW3, gW4, gW5, s);
+    else launch_bwd<144>(wpk, feat, dirs, M, n_valid, g_sigma, g_rgb, g_feat, gW1, gW2, gW3, gW4, gW5, s);
+}
+
+}  // namespace tnl
+
+using namespace tnl;
+
+extern "C" int tnl_umma_probe(const void* A, int a_rows, int a_cols, const void* B, int b_rows, int b_cols, int a_mn, int b_mn, int M,
+                              int N, int K, float* out, int ncols, tnl_stream_t stream) {
+    TNL_ARG_CHECK(A && B && out, "null pointer");
+    TNL_ARG_CHECK(a_rows % 8 == 0 && a_cols % 8 == 0 && b_rows % 8 == 0 && b_cols % 8 == 0 && K % 16 == 0 && ncols % 8 == 0 && ncols <= 256,
+                  "probe: dimensions must be multiples of 8 (K of 16), at most 256 columns dumped");
+    const size_t bytes = (size_t)a_rows * a_cols * 2 + (size_t)b_rows * b_cols * 2;
+    TNL_ARG_CHECK(bytes <= 200 * 1024, "probe: operands exceed shared memory");
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_umma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr = true;
+    }
+    k_umma_probe<<<1, 128, bytes, reinterpret_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(A), a_rows, a_cols,
+                                                                            static_cast<const __half*>(B), b_rows, b_cols, a_mn, b_mn, M,
+                                                                            N, K, out, ncols);
+    return finish_launch("umma_probe");
+}

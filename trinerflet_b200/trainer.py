@@ -53,6 +53,9 @@ class TrainStep:
         # eager-mode option: per-plane exchange on a side stream overlapped with the per-plane IDWT backward.  Measured on
         # 8 x B200 it does not beat the sequential exchange (NCCL and the IDWT kernels contend for SMs / HBM), so it is off.
         self.pipelined_tail = False
+        # steady-state steps reconstruct the planes on a second stream, concurrently with the ray marching + cell sort
+        self.prefetch_planes = True
+        self._side = None
         self._graphs = None
 
     # ---- the three segments of a step ---------------------------------------------------------------------------------
@@ -71,8 +74,13 @@ class TrainStep:
         enc = model.encoder
         model.train()
         enc.reset_cahce()
-        planes = enc.get_planes()
         do_update = (self.global_step % opt.update_extra_interval == 0) if update_grid is None else update_grid
+        if self.prefetch_planes and not do_update and rays_o.is_cuda:
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            planes = enc.prefetch_planes(self._side)
+        else:
+            planes = enc.get_planes()
         if do_update:
             with torch.autocast("cuda", dtype=torch.float16, enabled=opt.fp16):
                 model.update_extra_state()
@@ -83,6 +91,7 @@ class TrainStep:
             # single GPU (or dense exchange): one backward through render + IDWT
             with torch.autocast("cuda", dtype=torch.float16, enabled=opt.fp16):
                 loss = self._render_loss(rays_o, rays_d, images)
+                enc._join_prefetch()
                 reg = wavelet_regulariser(enc, opt.wavelet_regularization, getattr(opt, "fused_regulariser", True))
                 if reg is not None:
                     loss = loss + reg
@@ -96,6 +105,7 @@ class TrainStep:
             enc.last_used_planes = leaf
             with torch.autocast("cuda", dtype=torch.float16, enabled=opt.fp16):
                 loss = self._render_loss(rays_o, rays_d, images)
+                enc._join_prefetch()
                 reg = wavelet_regulariser(enc, opt.wavelet_regularization, True)
                 enc.reset_cahce()
                 self.scaler.scale(loss).backward()                    # -> leaf.grad and the MLP gradients of this shard
@@ -114,6 +124,8 @@ class TrainStep:
 
     def _idwt_backward(self):
         planes, leaf, reg = self._cut
+        if self._side is not None:   # the reconstruction's autograd node runs on the prefetch stream
+            self._side.wait_stream(torch.cuda.current_stream())
         if reg is not None:   # identical on every rank: added once, after the exchange
             torch.autograd.backward([planes, self.scaler.scale(reg)], [leaf.grad, None])
         else:

@@ -188,8 +188,9 @@ def _inv_bound(bound):
 
 class _SamplePlanes(Function):
     @staticmethod
-    def forward(ctx, planes, coords, bound, fp16_coords, n_valid, perm=None, half_out=False):
+    def forward(ctx, planes, coords, bound, fp16_coords, n_valid, perm=None, half_out=False, grad_buf=None):
         _require_cuda_f32(planes, "planes")
+        ctx.grad_buf = grad_buf
         planes_cl = to_cl_planes(planes.detach())
         coords = coords.detach().contiguous().float()
         M = coords.shape[0]
@@ -208,10 +209,15 @@ class _SamplePlanes(Function):
         coords, n_valid, perm = ctx.saved_tensors
         M, R, C, inv, fp16_coords, has_nv, has_perm, half = ctx.meta
         g_feat = g_feat.contiguous().half() if half else g_feat.contiguous().float()
-        g_planes = cl_empty_planes(C, R, device=g_feat.device, zero=True)
+        if ctx.grad_buf is not None:     # zero-filled ahead of time on the prefetch stream (TriPlaneVolume.prefetch_planes)
+            g_planes, ready = ctx.grad_buf
+            ctx.grad_buf = None
+            torch.cuda.current_stream().wait_event(ready)
+        else:
+            g_planes = cl_empty_planes(C, R, device=g_feat.device, zero=True)
         call("tnl_sample_planes_backward", ptr(g_feat), int(half), ptr(coords), M, R, C, inv, fp16_coords,
              ptr(n_valid) if has_nv else None, ptr(perm) if has_perm else None, ptr(g_planes), stream())
-        return g_planes, None, None, None, None, None, None
+        return g_planes, None, None, None, None, None, None, None
 
 
 def cell_sort(coords, bound, n_valid=None, G=64):
@@ -225,12 +231,12 @@ def cell_sort(coords, bound, n_valid=None, G=64):
     return perm
 
 
-def sample_planes(planes, coords, bound, fp16_coords=None, n_valid=None, perm=None, half_out=False):
+def sample_planes(planes, coords, bound, fp16_coords=None, n_valid=None, perm=None, half_out=False, grad_buf=None):
     """planes logical [3,C,R,R] -> features [M, 3C] (fp32). fp16_coords=None follows the autocast state, as the
     reference's projection matmul does."""
     if fp16_coords is None:
         fp16_coords = torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.float16
-    return _SamplePlanes.apply(planes, coords, float(bound), bool(fp16_coords), n_valid, perm, bool(half_out))
+    return _SamplePlanes.apply(planes, coords, float(bound), bool(fp16_coords), n_valid, perm, bool(half_out), grad_buf)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -346,6 +352,36 @@ class TriPlaneVolume(nn.Module):
 
     reset_cache = reset_cahce
 
+    def prefetch_planes(self, side):
+        """Reconstruct the planes on stream `side` while the caller's stream goes on with work that does not need them
+        (ray marching, the cell sort); the first sampling call waits for them.  Also zero-fills the plane-gradient buffer
+        of this step's sampling backward there.  Same result as get_planes(); the autograd node of the reconstruction
+        runs its backward on `side` too (torch's stream-aware engine orders it after the sampling backward)."""
+        main = torch.cuda.current_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            planes = self.get_planes()
+            ready = torch.cuda.Event()
+            ready.record(side)
+            gbuf = None
+            if torch.is_grad_enabled() and planes.requires_grad:
+                gbuf = cl_empty_planes(self.number_of_features, self.plane_resolution, device=planes.device, zero=True)
+                gready = torch.cuda.Event()
+                gready.record(side)
+                gbuf = (gbuf, gready)
+        self._prefetch = (ready, gbuf)
+        return planes
+
+    def _join_prefetch(self):
+        """-> the pre-zeroed gradient buffer (once per prefetch) after making the current stream wait for the planes."""
+        pf = getattr(self, "_prefetch", None)
+        if pf is None:
+            return None
+        ready, gbuf = pf
+        torch.cuda.current_stream().wait_event(ready)
+        self._prefetch = None
+        return gbuf
+
     def build_planes(self, planes_features=None, coefs=None):
         planes_features = self.planes_features if planes_features is None else planes_features
         coefs = list(self.planes_features_wavelet_coefs) if coefs is None else coefs
@@ -365,6 +401,7 @@ class TriPlaneVolume(nn.Module):
         return planes
 
     def wavelet_l1(self, lam):
+        self._join_prefetch()
         """lam * (sum_l mean|yh_l| * numel_l / numel_all) / L -- the regulariser of nerf/utils.py:640-655 (unweighted
         branch), taken from the |yh| sums the plane reconstruction produced; its gradient is applied inside the IDWT
         backward kernels (no extra pass over the coefficients).  Call after get_planes() of the same step."""
@@ -387,7 +424,11 @@ class TriPlaneVolume(nn.Module):
     def forward(self, coordinates, bound, n_valid=None, perm=None, half_out=False):
         """coordinates [M,3] in [-bound, bound] -> features [M, 3C] (index p*C + c); fp32 as the reference's
         grid_sample, or fp16 (half_out) for the fused MLP path, which rounds its input to fp16 anyway."""
-        return sample_planes(self.get_planes(), coordinates, bound, n_valid=n_valid, perm=perm, half_out=half_out)
+        planes = self.get_planes()
+        gbuf = self._join_prefetch()
+        if gbuf is not None and not torch.is_grad_enabled():
+            gbuf = None
+        return sample_planes(planes, coordinates, bound, n_valid=n_valid, perm=perm, half_out=half_out, grad_buf=gbuf)
 
     # -- checkpoints: accept reference (NCHW-contiguous) tensors, keep channels-last storage -------------
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
