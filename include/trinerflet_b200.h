@@ -172,6 +172,20 @@ int tnl_mlp_backward(const tnl_mlp_dims* dims, const void* packed, const void* f
 int tnl_umma_probe(const void* A, int a_rows, int a_cols, const void* B, int b_rows, int b_cols, int a_mn, int b_mn,
                    int M, int N, int K, float* out, int ncols, tnl_stream_t stream);
 
+/* Diagnostic: tensor-pipe cost of one product shape / operand layout: `reps` x (K/16) tcgen05.mma issued back to back;
+ * out2[0] = cycles until completion, out2[1] = cycles spent issuing. */
+int tnl_umma_bench(int a_rows, int b_rows, int a_mn, int b_mn, int M, int N, int K, int reps, long long* out2,
+                   tnl_stream_t stream);
+/* Diagnostic: as tnl_umma_bench with free descriptor fields (LBO / SBO / K-step in 16-byte units, layout type 0 = none,
+ * 2 = 128B swizzle, 4 = 64B, 6 = 32B), issued by a converged warp; zero operands. */
+int tnl_umma_bench2(uint32_t a_lbo, uint32_t a_sbo, uint32_t a_step, uint32_t a_type, uint32_t b_lbo, uint32_t b_sbo,
+                    uint32_t b_step, uint32_t b_type, int a_mn, int b_mn, int M, int N, int ksteps, int reps, long long* out2,
+                    tnl_stream_t stream);
+/* Diagnostic: counters64 = device buffer of 64 uint64 (zero-filled by the caller) that CTA 0 of the tcgen05 MLP
+ * backward fills with cycle counts per pipeline stage ([0..9] warpgroup wait, [10..19] warpgroup epilogue,
+ * [20..39] issuer wait (stage*2+wg), [40..59] issuer issue); NULL switches it off (default). */
+int tnl_mlp_tc_profile(unsigned long long* counters64);
+
 /* ------------------------------------------------------------------ density grid ------------- */
 /* Fused pieces of NeRFRenderer.update_extra_state (reconstruction/nerf/renderer.py:448-542). */
 /* cell-centre sample positions for a list of Morton cells of one cascade (renderer.py:474-483):

@@ -51,6 +51,9 @@ SIGNATURES = {
     "tnl_mlp_pack_weights": (_int, [_DP, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tnl_mlp_forward": (_int, [_DP, _vp, _vp, _int, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
     "tnl_mlp_backward": (_int, [_DP, _vp, _vp, _int, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tnl_mlp_tc_profile": (_int, [_vp]),
+    "tnl_umma_bench": (_int, [_int] * 8 + [_vp, _vp]),
+    "tnl_umma_bench2": (_int, [_u32] * 8 + [_int] * 6 + [_vp, _vp]),
     "tnl_umma_probe": (_int, [_vp, _int, _int, _vp, _int, _int, _int, _int, _int, _int, _int, _vp, _int, _vp]),
     "tnl_mark_dirty_tiles": (_int, [_vp, _u32, _u32, _f32, _u32, _u32, _u32, _vp, _vp]),
     "tnl_tiles_pack": (_int, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _int, _vp]),

@@ -79,28 +79,16 @@ __device__ __forceinline__ uint32_t clamp_valid(const int32_t* n_valid_ptr, uint
     return nv < 0 ? 0u : ((uint32_t)nv < M ? (uint32_t)nv : M);
 }
 
-// K-steps of one product: D[tmem_d] (+)= A x B.  A/B descriptors advance along their contraction dimension.
-template <int KSTEPS, bool A_MN, bool B_MN>
-__device__ __forceinline__ void issue(uint32_t tmem_d, uint32_t a_base, uint32_t a_R, uint32_t a_r0, uint32_t a_c0, uint32_t b_base,
-                                      uint32_t b_R, uint32_t b_r0, uint32_t b_c0, uint32_t M, uint32_t N, bool accumulate_first) {
-    const uint32_t idesc = make_idesc(M, N, A_MN, B_MN);
-#pragma unroll
-    for (int ks = 0; ks < KSTEPS; ++ks) {
-        const uint64_t a = A_MN ? desc_mnmajor(a_base, a_R, a_r0 + 16 * ks, a_c0) : desc_kmajor(a_base, a_R, a_r0, a_c0 + 16 * ks);
-        const uint64_t b = B_MN ? desc_mnmajor(b_base, b_R, b_r0 + 16 * ks, b_c0) : desc_kmajor(b_base, b_R, b_r0, b_c0 + 16 * ks);
-        mma_f16(tmem_d, a, b, idesc, (accumulate_first || ks > 0) ? 1u : 0u);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
 template <int K1>
 struct TcFwdSmem {
-    static constexpr uint32_t X = TcW<K1>::END;                      // feat tile(128, K1)
-    static constexpr uint32_t ACT = X + tile_bytes(128, K1);         // h1 / h3 / h4 tile(128, 64)
-    static constexpr uint32_t I3 = ACT + tile_bytes(128, 64);        // [SH | geo | 0] tile(128, 32)
-    static constexpr uint32_t BAR = I3 + tile_bytes(128, 32);        // mbarrier (8 B) + TMEM base slot (4 B)
+    static constexpr uint32_t X = TcW<K1>::END;                      // feat tile(128, K1); reused for [SH | geo | 0] tile(128, 32)
+    static constexpr uint32_t I3 = X;                                //   (the feature tile is dead once h1 has been computed)
+    static constexpr uint32_t XB = tile_bytes(128, K1) > tile_bytes(128, 32) ? tile_bytes(128, K1) : tile_bytes(128, 32);
+    static constexpr uint32_t ACT = X + XB;                          // h1 / h3 / h4 tile(128, 64)
+    static constexpr uint32_t BAR = ACT + tile_bytes(128, 64);       // mbarrier (8 B) + TMEM base slot (4 B)
     static constexpr uint32_t TOTAL = BAR + 16;
 };
 
@@ -124,47 +112,54 @@ k_mlp_tc_fwd(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat, c
     fence_after_sync();
     const uint32_t tmem = *tslot;
     const uint32_t trow = tmem + ((warp * 32u) << 16);
-    const uint32_t sb = smem_u32(smem);
+    const uint32_t sb4 = smem_u32(smem) >> 4;
+    const uint32_t X4 = sb4 + (S::X >> 4), A4 = sb4 + (S::ACT >> 4);
+    const uint32_t W14 = sb4 + (W::W1 >> 4), W24 = sb4 + (W::W2 >> 4), W34 = sb4 + (W::W3 >> 4), W44 = sb4 + (W::W4 >> 4), W54 = sb4 + (W::W5 >> 4);
     uint32_t phase = 0;
     const uint32_t nvalid = clamp_valid(n_valid_ptr, M);
     const uint32_t ntiles = ceil_div(nvalid, 128u);
+#define TNL_STAGE(ISSUE)                   \
+    fence_async_smem();                    \
+    fence_before_sync();                   \
+    __syncthreads();                       \
+    if (warp == 0) {                       \
+        fence_after_sync();                \
+        ISSUE;                             \
+        commit_elected(bar);               \
+    }                                      \
+    mbar_wait(bar, phase); phase ^= 1;     \
+    fence_after_sync()
+    uint4 x[K1 / 8];
+    {
+        const uint32_t p0 = blockIdx.x * 128 + tid;
+        const uint4* src = reinterpret_cast<const uint4*>(feat + (size_t)p0 * K1);
+#pragma unroll
+        for (int kc = 0; kc < K1 / 8; ++kc) x[kc] = p0 < nvalid ? __ldg(src + kc) : make_uint4(0u, 0u, 0u, 0u);
+    }
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint32_t p = tile * 128 + tid;
         const bool v = p < nvalid;
-        {   // this thread's feature row -> X tile
-            const uint4* src = reinterpret_cast<const uint4*>(feat + (size_t)p * K1);
-            uint4 x[K1 / 8];
 #pragma unroll
-            for (int kc = 0; kc < K1 / 8; ++kc) x[kc] = v ? __ldg(src + kc) : make_uint4(0u, 0u, 0u, 0u);
+        for (int kc = 0; kc < K1 / 8; ++kc) *reinterpret_cast<uint4*>(smem + S::X + (kc * 128 + tid) * 16) = x[kc];
+        float d[3] = {0.f, 0.f, 0.f};
+        if (COLOR && v) { d[0] = __ldg(dirs + 3 * (size_t)p); d[1] = __ldg(dirs + 3 * (size_t)p + 1); d[2] = __ldg(dirs + 3 * (size_t)p + 2); }
+        // h1 = feat W1^T
+        TNL_STAGE(mma_group<K1 / 16>(tmem + TM_A, op_kmajor(X4, 128, 0, 0), op_kmajor(W14, 64, 0, 0), make_idesc(128, 64, false, false), false));
+        {   // prefetch the next tile's feature row; consumed at the top of the next iteration
+            const uint32_t pn = (tile + gridDim.x) * 128 + tid;
+            const uint4* src = reinterpret_cast<const uint4*>(feat + (size_t)pn * K1);
+            const bool vn = pn < nvalid;
 #pragma unroll
-            for (int kc = 0; kc < K1 / 8; ++kc) *reinterpret_cast<uint4*>(smem + S::X + (kc * 128 + tid) * 16) = x[kc];
+            for (int kc = 0; kc < K1 / 8; ++kc) x[kc] = vn ? __ldg(src + kc) : make_uint4(0u, 0u, 0u, 0u);
         }
-        fence_async_smem();
-        fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {   // h1 = feat W1^T
-            fence_after_sync();
-            issue<K1 / 16, false, false>(tmem + TM_A, sb + S::X, 128, 0, 0, sb + W::W1, 64, 0, 0, 128, 64, false);
-            commit(bar);
-        }
-        mbar_wait(bar, phase); phase ^= 1;
-        fence_after_sync();
         {
             float a[64];
             tmem_load_row<64>(trow + TM_A, a);
 #pragma unroll
             for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(smem + S::ACT + (kc * 128 + tid) * 16) = pack8<true>(a + 8 * kc);
         }
-        fence_async_smem();
-        fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {   // h2 = relu(h1) W2^T
-            fence_after_sync();
-            issue<4, false, false>(tmem + TM_B, sb + S::ACT, 128, 0, 0, sb + W::W2, 16, 0, 0, 128, 16, false);
-            commit(bar);
-        }
-        mbar_wait(bar, phase); phase ^= 1;
-        fence_after_sync();
+        // h2 = relu(h1) W2^T
+        TNL_STAGE(mma_group<4>(tmem + TM_B, op_kmajor(A4, 128, 0, 0), op_kmajor(W24, 16, 0, 0), make_idesc(128, 16, false, false), false));
         float h2[16];
         tmem_load_row<16>(trow + TM_B, h2);
 #pragma unroll
@@ -176,10 +171,8 @@ k_mlp_tc_fwd(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat, c
                 for (int j = 0; j < 15; ++j) geo[15 * (size_t)p + j] = v ? h2[1 + j] : 0.f;
             }
         }
-        if (!COLOR) { fence_before_sync(); continue; }
+        if (!COLOR) continue;
         {   // color_net input row: [fp16(SH16(d)) | geo | 0]
-            float d[3] = {0.f, 0.f, 0.f};
-            if (v) { d[0] = __ldg(dirs + 3 * (size_t)p); d[1] = __ldg(dirs + 3 * (size_t)p + 1); d[2] = __ldg(dirs + 3 * (size_t)p + 2); }
             float in3[32];
             {
                 float sh[16];
@@ -193,48 +186,24 @@ k_mlp_tc_fwd(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat, c
 #pragma unroll
             for (int kc = 0; kc < 4; ++kc) *reinterpret_cast<uint4*>(smem + S::I3 + (kc * 128 + tid) * 16) = pack8<false>(in3 + 8 * kc);
         }
-        fence_async_smem();
-        fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {   // h3 = in3 W3^T
-            fence_after_sync();
-            issue<2, false, false>(tmem + TM_A, sb + S::I3, 128, 0, 0, sb + W::W3, 64, 0, 0, 128, 64, false);
-            commit(bar);
-        }
-        mbar_wait(bar, phase); phase ^= 1;
-        fence_after_sync();
+        // h3 = in3 W3^T
+        TNL_STAGE(mma_group<2>(tmem + TM_A, op_kmajor(X4, 128, 0, 0), op_kmajor(W34, 64, 0, 0), make_idesc(128, 64, false, false), false));
         {
             float a[64];
             tmem_load_row<64>(trow + TM_A, a);
 #pragma unroll
             for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(smem + S::ACT + (kc * 128 + tid) * 16) = pack8<true>(a + 8 * kc);
         }
-        fence_async_smem();
-        fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {   // h4 = relu(h3) W4^T
-            fence_after_sync();
-            issue<4, false, false>(tmem + TM_A, sb + S::ACT, 128, 0, 0, sb + W::W4, 64, 0, 0, 128, 64, false);
-            commit(bar);
-        }
-        mbar_wait(bar, phase); phase ^= 1;
-        fence_after_sync();
+        // h4 = relu(h3) W4^T
+        TNL_STAGE(mma_group<4>(tmem + TM_A, op_kmajor(A4, 128, 0, 0), op_kmajor(W44, 64, 0, 0), make_idesc(128, 64, false, false), false));
         {
             float a[64];
             tmem_load_row<64>(trow + TM_A, a);
 #pragma unroll
             for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(smem + S::ACT + (kc * 128 + tid) * 16) = pack8<true>(a + 8 * kc);
         }
-        fence_async_smem();
-        fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {   // o5 = relu(h4) W5^T
-            fence_after_sync();
-            issue<4, false, false>(tmem + TM_B, sb + S::ACT, 128, 0, 0, sb + W::W5, 16, 0, 0, 128, 16, false);
-            commit(bar);
-        }
-        mbar_wait(bar, phase); phase ^= 1;
-        fence_after_sync();
+        // o5 = relu(h4) W5^T
+        TNL_STAGE(mma_group<4>(tmem + TM_B, op_kmajor(A4, 128, 0, 0), op_kmajor(W54, 16, 0, 0), make_idesc(128, 16, false, false), false));
         {
             float o[8];
             tmem_load_row<8>(trow + TM_B, o);
@@ -243,8 +212,8 @@ k_mlp_tc_fwd(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat, c
                 for (int j = 0; j < 3; ++j) rgb[3 * (size_t)p + j] = v ? r16(sigmoidf_(r16(o[j]))) : 0.f;
             }
         }
-        fence_before_sync();   // orders this iteration's tcgen05.ld before the next iteration's MMAs (via the next __syncthreads)
     }
+#undef TNL_STAGE
     // rows past the last tile that holds valid points: defined zeros
     for (uint32_t p = ntiles * 128 + blockIdx.x * 128 + tid; p < M; p += gridDim.x * 128) {
         sigma[p] = 0.f;
@@ -257,294 +226,327 @@ k_mlp_tc_fwd(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat, c
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward
+// backward.  CTA = 9 warps: two warpgroups, each working on its own 128-point sub-tile (own shared-memory tiles, own
+// chain accumulator in TMEM), and one MMA-issuer warp.  A warpgroup hands a stage to the issuer through an mbarrier
+// (`ready`, 128 arrivals), the issuer's tcgen05.commit arrives on the warpgroup's `done` barrier.  The issuer serves
+// the warpgroups alternately, so the tensor core works on one sub-tile while the other warpgroup runs its epilogue;
+// being the only issuer it also keeps the accumulation order of the shared weight-gradient accumulators defined.
 // ------------------------------------------------------------------------------------------------
 template <int K1>
 struct TcBwdSmem {
-    static constexpr uint32_t X = TcW<K1>::END;                   // feat            tile(128, K1)
+    // one sub-tile
+    static constexpr uint32_t X = 0;                              // feat            tile(128, K1)
     static constexpr uint32_t H1 = X + tile_bytes(128, K1);       // relu(h1) -> dh1 tile(128, 64)
     static constexpr uint32_t I3 = H1 + tile_bytes(128, 64);      // in3 tile(128, 32) -> dh2 tile(128, 16)
     static constexpr uint32_t H3 = I3 + tile_bytes(128, 32);      // relu(h3) -> dh3
     static constexpr uint32_t H4 = H3 + tile_bytes(128, 64);      // relu(h4) -> dh4
     static constexpr uint32_t D5 = H4 + tile_bytes(128, 64);      // d5 tile(128, 16)
-    static constexpr uint32_t BAR = D5 + tile_bytes(128, 16);
-    static constexpr uint32_t TOTAL = BAR + 16;
+    static constexpr uint32_t SUB = D5 + tile_bytes(128, 16);
+    // whole CTA
+    static constexpr uint32_t SUB0 = TcW<K1>::END;
+    static constexpr uint32_t BAR = SUB0 + 2 * SUB;               // ready[2], done[2] (8 B each), TMEM base slot
+    static constexpr uint32_t TOTAL = BAR + 48;
 };
 
 // lane of the TMEM accumulator that holds row i of an M = 64 product (cta_group::1): rows 16w .. 16w+15 live in
-// lanes 32w .. 32w+15 (the lower half of every warp's lane quarter)
+// lanes 32w .. 32w+15 (the lower half of every warp's lane quarter) -- pinned by tests/test_gpu_umma.py
 __device__ __forceinline__ bool m64_row_of_lane(uint32_t warp, uint32_t lane, uint32_t& row) {
     row = warp * 16 + lane;
     return lane < 16;
 }
 
+constexpr int kBwdStages = 10;
+
 template <int K1>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(288, 1)
 k_mlp_tc_bwd(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat, const float* __restrict__ dirs, uint32_t M,
              const int32_t* __restrict__ n_valid_ptr, const float* __restrict__ g_sigma, const float* __restrict__ g_rgb,
              __half* __restrict__ g_feat, float* __restrict__ gW1, float* __restrict__ gW2, float* __restrict__ gW3,
-             float* __restrict__ gW4, float* __restrict__ gW5) {
+             float* __restrict__ gW4, float* __restrict__ gW5, unsigned long long* __restrict__ dbg) {
     using W = TcW<K1>;
     using S = TcBwdSmem<K1>;
-    // TMEM columns: chain accumulator | dW1 [64 x K1] | dW4 [64 x 64] | dW3 [64 x 32] | dW2^T [64 x 16] | dW5^T [64 x 16]
-    constexpr uint32_t TM_C = 0, TM_W1 = 160, TM_W4 = TM_W1 + 144, TM_W3 = TM_W4 + 64, TM_W2 = TM_W3 + 32, TM_W5 = TM_W2 + 16;
+    // TMEM columns: chain accumulators of the two warpgroups | dW1 [64 x K1] | dW4 [64 x 64] | dW3 [64 x 32] | dW2^T, dW5^T [64 x 16]
+    constexpr uint32_t CW = K1 < 64 ? 64 : K1;
+    constexpr uint32_t TM_C = 0, TM_W1 = 2 * CW, TM_W4 = TM_W1 + K1, TM_W3 = TM_W4 + 64, TM_W2 = TM_W3 + 32, TM_W5 = TM_W2 + 16;
     constexpr uint32_t TM_COLS = 512;
-    static_assert(TM_W5 + 16 <= TM_COLS && K1 <= 144, "TMEM column budget");
+    static_assert(TM_W5 + 16 <= TM_COLS, "TMEM column budget");
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::BAR);
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + S::BAR + 8);
-    for (uint32_t i = tid * 16; i < W::END; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = __ldg(reinterpret_cast<const uint4*>(wpk + i));
-    if (tid == 0) { mbar_init(bar, 1); mbar_init_fence(); }
-    if (warp == 0) tmem_alloc(tslot, TM_COLS);
+    uint64_t* ready = reinterpret_cast<uint64_t*>(smem + S::BAR);
+    uint64_t* done = reinterpret_cast<uint64_t*>(smem + S::BAR + 16);
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + S::BAR + 32);
+    for (uint32_t i = tid * 16; i < W::END; i += 288 * 16) *reinterpret_cast<uint4*>(smem + i) = __ldg(reinterpret_cast<const uint4*>(wpk + i));
+    if (tid == 0) {
+        mbar_init(&ready[0], 128); mbar_init(&ready[1], 128);
+        mbar_init(&done[0], 1); mbar_init(&done[1], 1);
+        mbar_init_fence();
+    }
+    if (warp == 8) tmem_alloc(tslot, TM_COLS);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem = *tslot;
-    const uint32_t trow = tmem + ((warp * 32u) << 16);
-    const uint32_t sb = smem_u32(smem);
-    uint32_t phase = 0;
     const uint32_t nvalid = clamp_valid(n_valid_ptr, M);
     const uint32_t ntiles = ceil_div(nvalid, 128u);
-    bool first = true;   // the weight-gradient accumulators are initialised by the first tile's first K step
-#define TNL_STAGE_SYNC()    \
-    fence_async_smem();     \
-    fence_before_sync();    \
-    __syncthreads()
-#define TNL_STAGE_WAIT()               \
-    mbar_wait(bar, phase); phase ^= 1; \
-    fence_after_sync()
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint32_t p = tile * 128 + tid;
-        const bool v = p < nvalid;
+    const uint32_t npairs = ceil_div(ntiles, 2u);
+    const uint32_t my_pairs = blockIdx.x < npairs ? (npairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+
+    __shared__ unsigned long long sdbg[64];
+    const bool profiling = dbg != nullptr && blockIdx.x == 0;
+    if (profiling && tid < 64) sdbg[tid] = 0ull;
+    if (profiling) __syncthreads();
+    if (warp == 8) {
+        // ============================== MMA issuer (whole warp, converged; one elected lane issues) ==============================
+        const uint32_t sb4 = smem_u32(smem) >> 4;
+        const uint32_t W14 = sb4 + (W::W1 >> 4), W24 = sb4 + (W::W2 >> 4), W34 = sb4 + (W::W3 >> 4), W44 = sb4 + (W::W4 >> 4),
+                       W54 = sb4 + (W::W5 >> 4);
+        uint32_t ph[2] = {0u, 0u};
+        for (uint32_t it = 0; it < my_pairs; ++it) {
+#pragma unroll
+            for (int st = 0; st < kBwdStages; ++st) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const uint32_t sub = sb4 + ((S::SUB0 + g * S::SUB) >> 4);
+                    const uint32_t tc = tmem + TM_C + g * CW;
+                    const bool accw = !(it == 0 && g == 0);   // weight-gradient accumulators: initialised by the very first product
+                    const uint32_t X4 = sub + (S::X >> 4), H14 = sub + (S::H1 >> 4), I34 = sub + (S::I3 >> 4), H34 = sub + (S::H3 >> 4),
+                                   H44 = sub + (S::H4 >> 4), D54 = sub + (S::D5 >> 4);
+                    long long c0 = 0, c1 = 0;
+                    if (profiling) c0 = clock64();
+                    mbar_wait(&ready[g], ph[g]); ph[g] ^= 1;
+                    fence_after_sync();
+                    if (profiling) c1 = clock64();
+                    if (st == 0) {          // h1 = feat W1^T
+                        mma_group<K1 / 16>(tc, op_kmajor(X4, 128, 0, 0), op_kmajor(W14, 64, 0, 0), make_idesc(128, 64, false, false), false);
+                    } else if (st == 1) {   // h2 = relu(h1) W2^T
+                        mma_group<4>(tc, op_kmajor(H14, 128, 0, 0), op_kmajor(W24, 16, 0, 0), make_idesc(128, 16, false, false), false);
+                    } else if (st == 2) {   // h3 = in3 W3^T
+                        mma_group<2>(tc, op_kmajor(I34, 128, 0, 0), op_kmajor(W34, 64, 0, 0), make_idesc(128, 64, false, false), false);
+                    } else if (st == 3) {   // h4 = relu(h3) W4^T
+                        mma_group<4>(tc, op_kmajor(H34, 128, 0, 0), op_kmajor(W44, 64, 0, 0), make_idesc(128, 64, false, false), false);
+                    } else if (st == 4) {   // o5 = relu(h4) W5^T
+                        mma_group<4>(tc, op_kmajor(H44, 128, 0, 0), op_kmajor(W54, 16, 0, 0), make_idesc(128, 16, false, false), false);
+                    } else if (st == 5) {   // dh4 = d5 W5 ;  dW5^T += h4^T d5
+                        mma_group<1>(tc, op_kmajor(D54, 128, 0, 0), op_mnmajor(W54, 16, 0, 0), make_idesc(128, 64, false, true), false);
+                        mma_group<8>(tmem + TM_W5, op_mnmajor(H44, 128, 0, 0), op_mnmajor(D54, 128, 0, 0), make_idesc(64, 16, true, true), accw);
+                    } else if (st == 6) {   // dh3 = dh4 W4 ;  dW4 += dh4^T h3
+                        mma_group<4>(tc, op_kmajor(H44, 128, 0, 0), op_mnmajor(W44, 64, 0, 0), make_idesc(128, 64, false, true), false);
+                        mma_group<8>(tmem + TM_W4, op_mnmajor(H44, 128, 0, 0), op_mnmajor(H34, 128, 0, 0), make_idesc(64, 64, true, true), accw);
+                    } else if (st == 7) {   // d(in3)[:, 16:32] = dh3 W3[:, 16:32] ;  dW3 += dh3^T in3
+                        mma_group<4>(tc, op_kmajor(H34, 128, 0, 0), op_mnmajor(W34, 64, 0, 16), make_idesc(128, 16, false, true), false);
+                        mma_group<8>(tmem + TM_W3, op_mnmajor(H34, 128, 0, 0), op_mnmajor(I34, 128, 0, 0), make_idesc(64, 32, true, true), accw);
+                    } else if (st == 8) {   // dh1 = dh2 W2 ;  dW2^T += h1^T dh2
+                        mma_group<1>(tc, op_kmajor(I34, 128, 0, 0), op_mnmajor(W24, 16, 0, 0), make_idesc(128, 64, false, true), false);
+                        mma_group<8>(tmem + TM_W2, op_mnmajor(H14, 128, 0, 0), op_mnmajor(I34, 128, 0, 0), make_idesc(64, 16, true, true), accw);
+                    } else {                // g_feat = dh1 W1 ;  dW1 += dh1^T feat
+                        mma_group<4>(tc, op_kmajor(H14, 128, 0, 0), op_mnmajor(W14, 64, 0, 0), make_idesc(128, K1, false, true), false);
+                        mma_group<8>(tmem + TM_W1, op_mnmajor(H14, 128, 0, 0), op_mnmajor(X4, 128, 0, 0), make_idesc(64, K1, true, true), accw);
+                    }
+                    commit_elected(&done[g]);
+                    if (profiling && lane == 0) {
+                        sdbg[20 + st * 2 + g] += (unsigned long long)(c1 - c0);
+                        sdbg[40 + st * 2 + g] += (unsigned long long)(clock64() - c1);
+                    }
+                }
+            }
+        }
+    } else {
+        // ============================== warpgroups ==============================
+        const uint32_t g = warp >> 2, t = tid & 127;
+        uint8_t* sub = smem + S::SUB0 + g * S::SUB;
+        const uint32_t trow = tmem + (((warp & 3u) * 32u) << 16) + TM_C + g * CW;
+        uint32_t phase = 0;
+        long long tprev = 0;
+        int stg = 0;
+        const bool prof = profiling && tid == 0;
+        if (prof) tprev = clock64();
+#define TNL_HANDOFF()                                \
+    fence_async_smem();                              \
+    fence_before_sync();                             \
+    if (prof) { const long long c = clock64(); sdbg[10 + stg] += (unsigned long long)(c - tprev); tprev = c; } \
+    mbar_arrive(&ready[g]);                          \
+    mbar_wait(&done[g], phase); phase ^= 1;          \
+    fence_after_sync();                              \
+    if (prof) { const long long c = clock64(); sdbg[stg] += (unsigned long long)(c - tprev); tprev = c; stg = (stg + 1) % kBwdStages; }
+        // first tile's feature row
+        uint4 x[K1 / 8];
         {
-            const uint4* src = reinterpret_cast<const uint4*>(feat + (size_t)p * K1);
-            uint4 x[K1 / 8];
+            const uint32_t p0 = (2 * blockIdx.x + g) * 128 + t;
+            const uint4* src = reinterpret_cast<const uint4*>(feat + (size_t)p0 * K1);
 #pragma unroll
-            for (int kc = 0; kc < K1 / 8; ++kc) x[kc] = v ? __ldg(src + kc) : make_uint4(0u, 0u, 0u, 0u);
+            for (int kc = 0; kc < K1 / 8; ++kc) x[kc] = (my_pairs > 0 && p0 < nvalid) ? __ldg(src + kc) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        for (uint32_t it = 0; it < my_pairs; ++it) {
+            const uint32_t tile = 2 * (blockIdx.x + it * gridDim.x) + g;
+            const uint32_t p = tile * 128 + t;
+            const bool v = p < nvalid;
 #pragma unroll
-            for (int kc = 0; kc < K1 / 8; ++kc) *reinterpret_cast<uint4*>(smem + S::X + (kc * 128 + tid) * 16) = x[kc];
-        }
-        // issue the small per-point loads early
-        float d[3] = {0.f, 0.f, 0.f}, gr[3] = {0.f, 0.f, 0.f}, gs = 0.f;
-        if (v) {
+            for (int kc = 0; kc < K1 / 8; ++kc) *reinterpret_cast<uint4*>(sub + S::X + (kc * 128 + t) * 16) = x[kc];
+            float d[3] = {0.f, 0.f, 0.f}, gr[3] = {0.f, 0.f, 0.f}, gs = 0.f;
+            if (v) {
 #pragma unroll
-            for (int j = 0; j < 3; ++j) { d[j] = __ldg(dirs + 3 * (size_t)p + j); gr[j] = __ldg(g_rgb + 3 * (size_t)p + j); }
-            gs = __ldg(g_sigma + p);
-        }
-        // ---------------- forward recompute ----------------
-        TNL_STAGE_SYNC();
-        if (tid == 0) {
-            fence_after_sync();
-            issue<K1 / 16, false, false>(tmem + TM_C, sb + S::X, 128, 0, 0, sb + W::W1, 64, 0, 0, 128, 64, false);
-            commit(bar);
-        }
-        TNL_STAGE_WAIT();
-        {
-            float a[64];
-            tmem_load_row<64>(trow + TM_C, a);
+                for (int j = 0; j < 3; ++j) { d[j] = __ldg(dirs + 3 * (size_t)p + j); gr[j] = __ldg(g_rgb + 3 * (size_t)p + j); }
+                gs = __ldg(g_sigma + p);
+            }
+            TNL_HANDOFF();   // stage 0
+            {   // prefetch the next tile's feature row; it is consumed at the top of the next iteration
+                const uint32_t pn = (2 * (blockIdx.x + (it + 1) * gridDim.x) + g) * 128 + t;
+                const uint4* src = reinterpret_cast<const uint4*>(feat + (size_t)pn * K1);
+                const bool vn = (it + 1 < my_pairs) && pn < nvalid;
 #pragma unroll
-            for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(smem + S::H1 + (kc * 128 + tid) * 16) = pack8<true>(a + 8 * kc);
-        }
-        TNL_STAGE_SYNC();
-        if (tid == 0) {
-            fence_after_sync();
-            issue<4, false, false>(tmem + TM_C, sb + S::H1, 128, 0, 0, sb + W::W2, 16, 0, 0, 128, 16, false);
-            commit(bar);
-        }
-        TNL_STAGE_WAIT();
-        float logit;
-        {
-            float h2[16];
-            tmem_load_row<16>(trow + TM_C, h2);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) h2[j] = r16(h2[j]);
-            logit = h2[0];
-            float in3[32];
+                for (int kc = 0; kc < K1 / 8; ++kc) x[kc] = vn ? __ldg(src + kc) : make_uint4(0u, 0u, 0u, 0u);
+            }
             {
-                float sh[16];
-                sh16(d[0], d[1], d[2], sh);
+                float a[64];
+                tmem_load_row<64>(trow, a);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) in3[j] = sh[j];
+                for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(sub + S::H1 + (kc * 128 + t) * 16) = pack8<true>(a + 8 * kc);
             }
+            TNL_HANDOFF();   // stage 1
+            float logit;
+            {
+                float h2[16];
+                tmem_load_row<16>(trow, h2);
 #pragma unroll
-            for (int j = 0; j < 15; ++j) in3[16 + j] = h2[1 + j];
-            in3[31] = 0.f;
+                for (int j = 0; j < 16; ++j) h2[j] = r16(h2[j]);
+                logit = h2[0];
+                float in3[32];
+                {
+                    float sh[16];
+                    sh16(d[0], d[1], d[2], sh);
 #pragma unroll
-            for (int kc = 0; kc < 4; ++kc) *reinterpret_cast<uint4*>(smem + S::I3 + (kc * 128 + tid) * 16) = pack8<false>(in3 + 8 * kc);
-        }
-        TNL_STAGE_SYNC();
-        if (tid == 0) {
-            fence_after_sync();
-            issue<2, false, false>(tmem + TM_C, sb + S::I3, 128, 0, 0, sb + W::W3, 64, 0, 0, 128, 64, false);
-            commit(bar);
-        }
-        TNL_STAGE_WAIT();
-        {
-            float a[64];
-            tmem_load_row<64>(trow + TM_C, a);
+                    for (int j = 0; j < 16; ++j) in3[j] = sh[j];
+                }
 #pragma unroll
-            for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(smem + S::H3 + (kc * 128 + tid) * 16) = pack8<true>(a + 8 * kc);
-        }
-        TNL_STAGE_SYNC();
-        if (tid == 0) {
-            fence_after_sync();
-            issue<4, false, false>(tmem + TM_C, sb + S::H3, 128, 0, 0, sb + W::W4, 64, 0, 0, 128, 64, false);
-            commit(bar);
-        }
-        TNL_STAGE_WAIT();
-        {
-            float a[64];
-            tmem_load_row<64>(trow + TM_C, a);
+                for (int j = 0; j < 15; ++j) in3[16 + j] = h2[1 + j];
+                in3[31] = 0.f;
 #pragma unroll
-            for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(smem + S::H4 + (kc * 128 + tid) * 16) = pack8<true>(a + 8 * kc);
-        }
-        TNL_STAGE_SYNC();
-        if (tid == 0) {
-            fence_after_sync();
-            issue<4, false, false>(tmem + TM_C, sb + S::H4, 128, 0, 0, sb + W::W5, 16, 0, 0, 128, 16, false);
-            commit(bar);
-        }
-        TNL_STAGE_WAIT();
-        {   // d5 = half(g_rgb) * s * (1 - s), rounded to fp16; columns 3..15 zero
-            float o[8];
-            tmem_load_row<8>(trow + TM_C, o);
-            float d5[8];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const float s = r16(sigmoidf_(r16(o[j])));
-                d5[j] = v ? r16(gr[j]) * s * (1.f - s) : 0.f;
+                for (int kc = 0; kc < 4; ++kc) *reinterpret_cast<uint4*>(sub + S::I3 + (kc * 128 + t) * 16) = pack8<false>(in3 + 8 * kc);
             }
+            TNL_HANDOFF();   // stage 2
+            {
+                float a[64];
+                tmem_load_row<64>(trow, a);
 #pragma unroll
-            for (int j = 3; j < 8; ++j) d5[j] = 0.f;
-            *reinterpret_cast<uint4*>(smem + S::D5 + (0 * 128 + tid) * 16) = pack8<false>(d5);
-            *reinterpret_cast<uint4*>(smem + S::D5 + (1 * 128 + tid) * 16) = make_uint4(0u, 0u, 0u, 0u);
-        }
-        // ---------------- backward chain; every stage also accumulates one weight gradient ----------------
-        TNL_STAGE_SYNC();
-        if (tid == 0) {   // dh4 = d5 W5 ;  dW5^T += h4^T d5
-            fence_after_sync();
-            issue<1, false, true>(tmem + TM_C, sb + S::D5, 128, 0, 0, sb + W::W5, 16, 0, 0, 128, 64, false);
-            issue<8, true, true>(tmem + TM_W5, sb + S::H4, 128, 0, 0, sb + S::D5, 128, 0, 0, 64, 16, !first);
-            commit(bar);
-        }
-        TNL_STAGE_WAIT();
-        {
-            float a[64];
-            tmem_load_row<64>(trow + TM_C, a);
-#pragma unroll
-            for (int kc = 0; kc < 8; ++kc) {
-                uint4* q = reinterpret_cast<uint4*>(smem + S::H4 + (kc * 128 + tid) * 16);
-                *q = mask8(pack8<false>(a + 8 * kc), *q);
+                for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(sub + S::H3 + (kc * 128 + t) * 16) = pack8<true>(a + 8 * kc);
             }
-        }
-        TNL_STAGE_SYNC();
-        if (tid == 0) {   // dh3 = dh4 W4 ;  dW4 += dh4^T h3
-            fence_after_sync();
-            issue<4, false, true>(tmem + TM_C, sb + S::H4, 128, 0, 0, sb + W::W4, 64, 0, 0, 128, 64, false);
-            issue<8, true, true>(tmem + TM_W4, sb + S::H4, 128, 0, 0, sb + S::H3, 128, 0, 0, 64, 64, !first);
-            commit(bar);
-        }
-        TNL_STAGE_WAIT();
-        {
-            float a[64];
-            tmem_load_row<64>(trow + TM_C, a);
+            TNL_HANDOFF();   // stage 3
+            {
+                float a[64];
+                tmem_load_row<64>(trow, a);
 #pragma unroll
-            for (int kc = 0; kc < 8; ++kc) {
-                uint4* q = reinterpret_cast<uint4*>(smem + S::H3 + (kc * 128 + tid) * 16);
-                *q = mask8(pack8<false>(a + 8 * kc), *q);
+                for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(sub + S::H4 + (kc * 128 + t) * 16) = pack8<true>(a + 8 * kc);
             }
-        }
-        TNL_STAGE_SYNC();
-        if (tid == 0) {   // d(in3)[:, 16:32] = dh3 W3[:, 16:32] ;  dW3 += dh3^T in3
-            fence_after_sync();
-            issue<4, false, true>(tmem + TM_C, sb + S::H3, 128, 0, 0, sb + W::W3, 64, 0, 16, 128, 16, false);
-            issue<8, true, true>(tmem + TM_W3, sb + S::H3, 128, 0, 0, sb + S::I3, 128, 0, 0, 64, 32, !first);
-            commit(bar);
-        }
-        TNL_STAGE_WAIT();
-        {   // dh2: column 0 <- g_sigma * exp(clamp(logit, -15, 15)) (trunc_exp backward), columns 1..15 <- d(geo)
-            float a[16];
-            tmem_load_row<16>(trow + TM_C, a);
-            float dh2[16];
-            dh2[0] = gs * expf(fminf(fmaxf(logit, -15.f), 15.f));
+            TNL_HANDOFF();   // stage 4
+            {   // d5 = half(g_rgb) * s * (1 - s), rounded to fp16; columns 3..15 zero
+                float o[8];
+                tmem_load_row<8>(trow, o);
+                float d5[8];
 #pragma unroll
-            for (int j = 0; j < 15; ++j) dh2[1 + j] = a[j];
-            *reinterpret_cast<uint4*>(smem + S::I3 + (0 * 128 + tid) * 16) = pack8<false>(dh2);
-            *reinterpret_cast<uint4*>(smem + S::I3 + (1 * 128 + tid) * 16) = pack8<false>(dh2 + 8);
-        }
-        TNL_STAGE_SYNC();
-        if (tid == 0) {   // dh1 = dh2 W2 ;  dW2^T += h1^T dh2
-            fence_after_sync();
-            issue<1, false, true>(tmem + TM_C, sb + S::I3, 128, 0, 0, sb + W::W2, 16, 0, 0, 128, 64, false);
-            issue<8, true, true>(tmem + TM_W2, sb + S::H1, 128, 0, 0, sb + S::I3, 128, 0, 0, 64, 16, !first);
-            commit(bar);
-        }
-        TNL_STAGE_WAIT();
-        {
-            float a[64];
-            tmem_load_row<64>(trow + TM_C, a);
+                for (int j = 0; j < 3; ++j) {
+                    const float sg = r16(sigmoidf_(r16(o[j])));
+                    d5[j] = v ? r16(gr[j]) * sg * (1.f - sg) : 0.f;
+                }
 #pragma unroll
-            for (int kc = 0; kc < 8; ++kc) {
-                uint4* q = reinterpret_cast<uint4*>(smem + S::H1 + (kc * 128 + tid) * 16);
-                *q = mask8(pack8<false>(a + 8 * kc), *q);
+                for (int j = 3; j < 8; ++j) d5[j] = 0.f;
+                *reinterpret_cast<uint4*>(sub + S::D5 + (0 * 128 + t) * 16) = pack8<false>(d5);
+                *reinterpret_cast<uint4*>(sub + S::D5 + (1 * 128 + t) * 16) = make_uint4(0u, 0u, 0u, 0u);
             }
-        }
-        TNL_STAGE_SYNC();
-        if (tid == 0) {   // g_feat = dh1 W1 ;  dW1 += dh1^T feat
-            fence_after_sync();
-            issue<4, false, true>(tmem + TM_C, sb + S::H1, 128, 0, 0, sb + W::W1, 64, 0, 0, 128, K1, false);
-            issue<8, true, true>(tmem + TM_W1, sb + S::H1, 128, 0, 0, sb + S::X, 128, 0, 0, 64, K1, !first);
-            commit(bar);
-        }
-        TNL_STAGE_WAIT();
-        {
-            float a[K1];
-            tmem_load_row<K1>(trow + TM_C, a);
-            if (g_feat && p < M) {
-                uint4* dst = reinterpret_cast<uint4*>(g_feat + (size_t)p * K1);
+            TNL_HANDOFF();   // stage 5
+            {
+                float a[64];
+                tmem_load_row<64>(trow, a);
 #pragma unroll
-                for (int kc = 0; kc < K1 / 8; ++kc) dst[kc] = v ? pack8<false>(a + 8 * kc) : make_uint4(0u, 0u, 0u, 0u);
+                for (int kc = 0; kc < 8; ++kc) {
+                    uint4* q = reinterpret_cast<uint4*>(sub + S::H4 + (kc * 128 + t) * 16);
+                    *q = mask8(pack8<false>(a + 8 * kc), *q);
+                }
             }
+            TNL_HANDOFF();   // stage 6
+            {
+                float a[64];
+                tmem_load_row<64>(trow, a);
+#pragma unroll
+                for (int kc = 0; kc < 8; ++kc) {
+                    uint4* q = reinterpret_cast<uint4*>(sub + S::H3 + (kc * 128 + t) * 16);
+                    *q = mask8(pack8<false>(a + 8 * kc), *q);
+                }
+            }
+            TNL_HANDOFF();   // stage 7
+            {   // dh2: column 0 <- g_sigma * exp(clamp(logit, -15, 15)) (trunc_exp backward), columns 1..15 <- d(geo)
+                float a[16];
+                tmem_load_row<16>(trow, a);
+                float dh2[16];
+                dh2[0] = gs * expf(fminf(fmaxf(logit, -15.f), 15.f));
+#pragma unroll
+                for (int j = 0; j < 15; ++j) dh2[1 + j] = a[j];
+                *reinterpret_cast<uint4*>(sub + S::I3 + (0 * 128 + t) * 16) = pack8<false>(dh2);
+                *reinterpret_cast<uint4*>(sub + S::I3 + (1 * 128 + t) * 16) = pack8<false>(dh2 + 8);
+            }
+            TNL_HANDOFF();   // stage 8
+            {
+                float a[64];
+                tmem_load_row<64>(trow, a);
+#pragma unroll
+                for (int kc = 0; kc < 8; ++kc) {
+                    uint4* q = reinterpret_cast<uint4*>(sub + S::H1 + (kc * 128 + t) * 16);
+                    *q = mask8(pack8<false>(a + 8 * kc), *q);
+                }
+            }
+            TNL_HANDOFF();   // stage 9
+            {
+                float a[K1];
+                tmem_load_row<K1>(trow, a);
+                if (g_feat && p < M) {
+                    uint4* dst = reinterpret_cast<uint4*>(g_feat + (size_t)p * K1);
+#pragma unroll
+                    for (int kc = 0; kc < K1 / 8; ++kc) dst[kc] = v ? pack8<false>(a + 8 * kc) : make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+            // the next sub-tile's stage-0 hand-off is ordered behind these loads, so the issuer cannot overwrite the accumulator early
         }
-        first = false;
+#undef TNL_HANDOFF
     }
-#undef TNL_STAGE_SYNC
-#undef TNL_STAGE_WAIT
+    // every product has completed: each warpgroup waited on the commit that followed its last one
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (profiling && tid < 64) dbg[tid] += sdbg[tid];
     // ---------------- flush the weight gradients (fp32, one atomicAdd per element per CTA) ----------------
-    if (!first) {
+    if (warp < 4 && my_pairs > 0) {
+        const uint32_t tl = tmem + ((warp * 32u) << 16);
         uint32_t row;
         const bool have = m64_row_of_lane(warp, lane, row);
         {
             float a[K1];
-            tmem_load_row<K1>(trow + TM_W1, a);
+            tmem_load_row<K1>(tl + TM_W1, a);
             if (have)
 #pragma unroll
                 for (int k = 0; k < K1; ++k) atomicAdd(gW1 + (size_t)row * K1 + k, a[k]);
         }
         {
             float a[64];
-            tmem_load_row<64>(trow + TM_W4, a);
+            tmem_load_row<64>(tl + TM_W4, a);
             if (have)
 #pragma unroll
                 for (int k = 0; k < 64; ++k) atomicAdd(gW4 + (size_t)row * 64 + k, a[k]);
         }
         {
             float a[32];
-            tmem_load_row<32>(trow + TM_W3, a);
+            tmem_load_row<32>(tl + TM_W3, a);
             if (have)
 #pragma unroll
                 for (int k = 0; k < 31; ++k) atomicAdd(gW3 + (size_t)row * 31 + k, a[k]);
         }
         {   // transposed accumulators: lane row = input feature k, column = output row n
             float a[16];
-            tmem_load_row<16>(trow + TM_W2, a);
+            tmem_load_row<16>(tl + TM_W2, a);
             if (have)
 #pragma unroll
                 for (int n = 0; n < 16; ++n) atomicAdd(gW2 + (size_t)n * 64 + row, a[n]);
             float b[16];
-            tmem_load_row<16>(trow + TM_W5, b);
+            tmem_load_row<16>(tl + TM_W5, b);
             if (have)
 #pragma unroll
                 for (int n = 0; n < 3; ++n) atomicAdd(gW5 + (size_t)n * 64 + row, b[n]);
@@ -552,7 +554,7 @@ k_mlp_tc_bwd(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat, c
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_free(tmem, TM_COLS);
+    if (warp == 8) tmem_free(tmem, TM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -600,11 +602,84 @@ k_umma_probe(const __half* __restrict__ A, int a_rows, int a_cols, const __half*
     if (warp == 0) tmem_free(tmem, 256);
 }
 
+// micro-benchmark: `reps` rounds of one product's K loop issued back to back by one thread; cycles from first issue to
+// completion -> out[0] (tensor-pipe cost of one shape / operand layout, profiles/bench_umma.py)
+__global__ void __launch_bounds__(128)
+k_umma_bench(int a_rows, int b_rows, int a_mn, int b_mn, int Mm, int Nn, int Kk, int reps, long long* __restrict__ out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tslot;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    for (uint32_t i = tid * 16; i < 160 * 1024; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_init_fence(); }
+    if (warp == 0) tmem_alloc(&tslot, 256);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = tslot;
+    const uint32_t sb4 = smem_u32(smem) >> 4;
+    if (tid == 0) {
+        const uint32_t idesc = make_idesc(Mm, Nn, a_mn != 0, b_mn != 0);
+        const Operand a = a_mn ? op_mnmajor(sb4, a_rows, 0, 0) : op_kmajor(sb4, a_rows, 0, 0);
+        const Operand b = b_mn ? op_mnmajor(sb4 + 4096, b_rows, 0, 0) : op_kmajor(sb4 + 4096, b_rows, 0, 0);
+        const long long c0 = clock64();
+        for (int r = 0; r < reps; ++r) mma_steps(tmem, a, b, idesc, Kk / 16, r > 0);
+        const long long c1 = clock64();
+        commit(&bar);
+        mbar_wait(&bar, 0);
+        const long long c2 = clock64();
+        out[0] = c2 - c0;
+        out[1] = c1 - c0;
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_free(tmem, 256);
+}
+
+// same with free descriptor fields (16-byte units) and layout type, to compare swizzle modes; operand contents are zero
+__global__ void __launch_bounds__(128)
+k_umma_bench2(uint32_t a_lbo, uint32_t a_sbo, uint32_t a_step, uint32_t a_type, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_step,
+              uint32_t b_type, int a_mn, int b_mn, int Mm, int Nn, int ksteps, int reps, long long* __restrict__ out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tslot;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    for (uint32_t i = tid * 16; i < 160 * 1024; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_init_fence(); }
+    if (warp == 0) tmem_alloc(&tslot, 256);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = tslot;
+    const uint32_t sb4 = smem_u32(smem) >> 4;
+    if (warp == 0) {
+        const uint32_t idesc = make_idesc(Mm, Nn, a_mn != 0, b_mn != 0);
+        Operand a, b;
+        a.lo = (sb4 & 0x3FFFu) | (a_lbo << 16); a.hi = a_sbo | (1u << 14) | (a_type << 29); a.step = a_step;
+        b.lo = ((sb4 + 4096) & 0x3FFFu) | (b_lbo << 16); b.hi = b_sbo | (1u << 14) | (b_type << 29); b.step = b_step;
+        const long long c0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+            if (ksteps == 4) mma_group<4>(tmem, a, b, idesc, r > 0);
+            else mma_group<8>(tmem, a, b, idesc, r > 0);
+        }
+        const long long c1 = clock64();
+        commit_elected(&bar);
+        mbar_wait(&bar, 0);
+        const long long c2 = clock64();
+        if (tid == 0) { out[0] = c2 - c0; out[1] = c1 - c0; }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_free(tmem, 256);
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side (called from mlp.cu's C-ABI entry points)
 // ------------------------------------------------------------------------------------------------
 bool mlp_tc_supported(uint32_t in_dim, uint32_t hidden, uint32_t hidden_c) {
-    return (in_dim == 48 || in_dim == 96 || in_dim == 144) && hidden == 64 && hidden_c == 64;
+    return (in_dim == 48 || in_dim == 96) && hidden == 64 && hidden_c == 64;   // C = 16 / 32 with 64-wide heads
 }
 
 size_t mlp_tc_packed_bytes(uint32_t in_dim) { return (size_t)64 * in_dim * 2 + 2048 + 4096 + 8192 + 2048; }
@@ -638,9 +713,11 @@ static void launch_fwd(const void* wpk, const void* feat, const float* dirs, uin
 void mlp_tc_forward(uint32_t in_dim, const void* wpk, const void* feat, const float* dirs, uint32_t M, const int32_t* n_valid,
                     float* sigma, float* rgb, float* geo, cudaStream_t s) {
     if (in_dim == 48) launch_fwd<48>(wpk, feat, dirs, M, n_valid, sigma, rgb, geo, s);
-    else if (in_dim == 96) launch_fwd<96>(wpk, feat, dirs, M, n_valid, sigma, rgb, geo, s);
-    else launch_fwd<144>(wpk, feat, dirs, M, n_valid, sigma, rgb, geo, s);
+    else launch_fwd<96>(wpk, feat, dirs, M, n_valid, sigma, rgb, geo, s);
 }
+
+// optional device buffer of 64 cycle counters (tnl_mlp_tc_profile); nullptr in normal operation
+static unsigned long long* g_tc_dbg = nullptr;
 
 template <int K1>
 static void launch_bwd(const void* wpk, const void* feat, const float* dirs, uint32_t M, const int32_t* n_valid, const float* g_sigma,
@@ -651,22 +728,52 @@ static void launch_bwd(const void* wpk, const void* feat, const float* dirs, uin
         cudaFuncSetAttribute(k_mlp_tc_bwd<K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL);
         attr = true;
     }
-    const uint32_t blocks = min(ceil_div(M, 128u), (uint32_t)kNumSM);   // one CTA per SM: it owns all 512 TMEM columns
-    k_mlp_tc_bwd<K1><<<blocks, 128, S::TOTAL, s>>>(static_cast<const uint8_t*>(wpk), static_cast<const __half*>(feat), dirs, M, n_valid,
-                                                   g_sigma, g_rgb, static_cast<__half*>(g_feat), gW1, gW2, gW3, gW4, gW5);
+    const uint32_t blocks = min(ceil_div(M, 256u), (uint32_t)kNumSM);   // one CTA per SM: it owns all 512 TMEM columns
+    k_mlp_tc_bwd<K1><<<blocks, 288, S::TOTAL, s>>>(static_cast<const uint8_t*>(wpk), static_cast<const __half*>(feat), dirs, M, n_valid,
+                                                   g_sigma, g_rgb, static_cast<__half*>(g_feat), gW1, gW2, gW3, gW4, gW5, g_tc_dbg);
 }
 
 void mlp_tc_backward(uint32_t in_dim, const void* wpk, const void* feat, const float* dirs, uint32_t M, const int32_t* n_valid,
                      const float* g_sigma, const float* g_rgb, void* g_feat, float* gW1, float* gW2, float* gW3, float* gW4, float* gW5,
                      cudaStream_t s) {
     if (in_dim == 48) launch_bwd<48>(wpk, feat, dirs, M, n_valid, g_sigma, g_rgb, g_feat, gW1, gW2, gW3, gW4, gW5, s);
-    else if (in_dim == 96) launch_bwd<96>(wpk, feat, dirs, M, n_valid, g_sigma, g_rgb, g_feat, gW1, gW2, gW3, gW4, gW5, s);
-    else launch_bwd<144>(wpk, feat, dirs, M, n_valid, g_sigma, g_rgb, g_feat, gW1, gW2, gW3, gW4, gW5, s);
+    else launch_bwd<96>(wpk, feat, dirs, M, n_valid, g_sigma, g_rgb, g_feat, gW1, gW2, gW3, gW4, gW5, s);
 }
 
 }  // namespace tnl
 
 using namespace tnl;
+
+extern "C" int tnl_mlp_tc_profile(unsigned long long* counters64) {
+    g_tc_dbg = counters64;
+    return 0;
+}
+
+extern "C" int tnl_umma_bench(int a_rows, int b_rows, int a_mn, int b_mn, int M, int N, int K, int reps, long long* out2,
+                              tnl_stream_t stream) {
+    TNL_ARG_CHECK(out2, "null pointer");
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_umma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr = true;
+    }
+    k_umma_bench<<<1, 128, 160 * 1024, reinterpret_cast<cudaStream_t>(stream)>>>(a_rows, b_rows, a_mn, b_mn, M, N, K, reps, out2);
+    return finish_launch("umma_bench");
+}
+
+extern "C" int tnl_umma_bench2(uint32_t a_lbo, uint32_t a_sbo, uint32_t a_step, uint32_t a_type, uint32_t b_lbo, uint32_t b_sbo,
+                               uint32_t b_step, uint32_t b_type, int a_mn, int b_mn, int M, int N, int ksteps, int reps, long long* out2,
+                               tnl_stream_t stream) {
+    TNL_ARG_CHECK(out2 && (ksteps == 4 || ksteps == 8), "bench2: ksteps must be 4 or 8");
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_umma_bench2, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr = true;
+    }
+    k_umma_bench2<<<1, 128, 160 * 1024, reinterpret_cast<cudaStream_t>(stream)>>>(a_lbo, a_sbo, a_step, a_type, b_lbo, b_sbo, b_step, b_type,
+                                                                                  a_mn, b_mn, M, N, ksteps, reps, out2);
+    return finish_launch("umma_bench2");
+}
 
 extern "C" int tnl_umma_probe(const void* A, int a_rows, int a_cols, const void* B, int b_rows, int b_cols, int a_mn, int b_mn, int M,
                               int N, int K, float* out, int ncols, tnl_stream_t stream) {

@@ -113,6 +113,41 @@ __device__ __forceinline__ Operand op_mnmajor(uint32_t a4, uint32_t R, uint32_t 
     o.step = 16;                                                           // 16 rows
     return o;
 }
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+// KSTEPS products D (+)= A_k B_k^T and, optionally, the commit that tracks them.  Called by a CONVERGED warp: the
+// descriptors are computed by all lanes (warp-uniform values the compiler can keep in uniform registers), one elected
+// lane issues.  A single issuing thread pays ~85 cycles per tcgen05.mma when it also does the descriptor arithmetic in
+// a divergent branch (measured, profiles/bench_umma.py), more than the 32-cycle tensor-pipe floor of a 128x64x16 product.
+template <int KSTEPS>
+__device__ __forceinline__ void mma_group(uint32_t d_tmem, Operand a, Operand b, uint32_t idesc, bool accumulate_first) {
+    uint64_t ad[KSTEPS], bd[KSTEPS];
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+        ad[ks] = ((uint64_t)a.hi << 32) | (a.lo + ks * a.step);
+        bd[ks] = ((uint64_t)b.hi << 32) | (b.lo + ks * b.step);
+    }
+    if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) mma_f16(d_tmem, ad[ks], bd[ks], idesc, (accumulate_first || ks > 0) ? 1u : 0u);
+    }
+    __syncwarp();
+}
+__device__ __forceinline__ void commit_elected(uint64_t* bar) {
+    if (elect_one()) commit(bar);
+    __syncwarp();
+}
+// runtime K-step count, issued by the calling thread alone (diagnostics)
 __device__ __forceinline__ void mma_steps(uint32_t d_tmem, Operand a, Operand b, uint32_t idesc, int ksteps, bool accumulate_first) {
     for (int ks = 0; ks < ksteps; ++ks) {
         const uint64_t ad = ((uint64_t)a.hi << 32) | (a.lo + ks * a.step);
