@@ -15,6 +15,7 @@ the CUDA-only extensions cannot run on a CPU here) on the host cores, on bounded
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -91,11 +92,24 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # algorithmic bytes per ABI call, from the scalar arguments the profiler hook records
 # ---------------------------------------------------------------------------------------------------------
-def algorithmic_bytes(name, meta, C, m_valid):
+def algorithmic_bytes(name, meta, C, m_valid, plan=None):
     g = 12 * C * 4
     if name in ("tnl_idwt_level_forward", "tnl_idwt_level_backward"):
         n, c = meta[0], meta[1]
         return 2 * (3 * c * (2 * n) ** 2 * 4)            # read all coefficients of the level + write its planes (= 2 P_level)
+    if name in ("tnl_idwt_level_forward_sparse", "tnl_idwt_level_backward_sparse") and plan is not None:
+        # work-list mode: px = one (plane, channel) layer of n x n coefficients.  Forward reads x + 3 bands on the active
+        # blocks, the 3 bands only (|yh| sum) on the clean ones, writes 4 px of planes per active coefficient position;
+        # backward reads the 4 px of incoming gradient on the active blocks + the 3 bands everywhere (regulariser sign),
+        # writes all 4 gradient layers.
+        n, c = meta[0], meta[1]
+        lvl = int(round(math.log2(n / plan.n0)))
+        px = 3 * c * n * n * 4
+        if name.endswith("forward_sparse"):
+            a = plan.stats["active_fraction_forward"][lvl]
+            return px * (a * (4 + 4) + (1 - a) * 3)
+        b = plan.stats["active_fraction_backward"][lvl]
+        return px * (b * 4 + 3 + 4)
     if name == "tnl_sample_planes_forward":
         return m_valid * (12 + g)
     if name == "tnl_sample_planes_backward":
@@ -293,6 +307,7 @@ def main():
         ts.world_size = 1          # rank-0-only section: no collectives from here on
         if ts.reducer is not None:
             ts.reducer.world_size = 1
+        ts.prefetch_planes = False   # per-kernel events must not overlap kernels of two streams
         _lib.profile_start()
         nprof = min(args.steps, 5)
         for i in range(nprof):
@@ -301,7 +316,7 @@ def main():
         kernels = {}
         for name, recs in prof.items():
             t = sum(r[0] for r in recs) / nprof
-            by = sum((algorithmic_bytes(name, r[1], C, m_valid) or 0) for r in recs) / nprof
+            by = sum((algorithmic_bytes(name, r[1], C, m_valid, ts._plan) or 0) for r in recs) / nprof
             kernels[name] = {"ms_per_step": round(t, 4), "calls_per_step": len(recs) / nprof,
                              "algorithmic_GB_per_step": round(by / 1e9, 4),
                              "achieved_GBps": round(by / 1e9 / (t * 1e-3), 1) if t > 0 and by else None}
@@ -316,8 +331,11 @@ def main():
         roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_GBps"], "peak": peak, "unit": "GB/s",
                     "frac": round(kernels[dom]["achieved_GBps"] / peak, 4), "traffic": None, "peak_source": peak_src,
                     "launch_ms": round(kernels[dom]["ms_per_step"] / kernels[dom]["calls_per_step"], 4)}
+        # B_step: what the reference's (dense) data flow has to move per step; the work-list IDWT moves less
+        # plane data than that, so this fraction is "dense-equivalent" throughput, not DRAM utilisation
         Bstep = step_bytes(P, C, m_valid, n_rays)
         extras = {"sparse_allreduce_tile_fraction": (round(ts.reducer.fraction, 4) if ts.reducer is not None else None),
+                  "idwt_worklist": (ts._plan.stats if ts._plan is not None else None),
                   "M_samples_per_step": m_valid, "B_step_GB": round(Bstep / 1e9, 3),
                   "step_achieved_GBps": round(Bstep / 1e9 / (ms_per_step * 1e-3), 1),
                   "step_frac_of_hbm_roofline": round(Bstep / 1e9 / (ms_per_step * 1e-3) / peak, 4), "kernels": kernels}

@@ -113,6 +113,24 @@ int tnl_idwt_level_forward(const float* x, const float* yh, float* out, uint32_t
 int tnl_idwt_level_backward(const float* g_out, float* g_x, float* g_yh, uint32_t n, uint32_t C, const float* yh,
                             const float* reg_grad, float reg_coef, uint32_t plane0, uint32_t nplanes, tnl_stream_t stream);
 
+/* Work-list variants of the two calls above for the training hot path, where the planes are only sampled (and only
+ * receive gradient) inside the tiles the occupancy grid marks (tnl_mark_dirty_tiles); n % 16 == 0.
+ *   active / clean: int32 [max][4] = {plane, m0, row_lo, row_hi}: blocks of 16 coarse columns [m0, m0+16) x rows
+ *   [row_lo, row_hi); together the two lists tile the level exactly once.  counts (device int32[2]) = number of valid
+ *   entries of (active, clean); the grids are sized by max_active / max_clean, so the lists may be rewritten in place
+ *   between launches (and CUDA-graph replays) when the occupancy grid changes.
+ * forward : active blocks are reconstructed exactly as by the dense call (their part of `out`, fine pixels
+ *   [2*m0, 2*m0+32) x [2*row_lo, 2*row_hi)); the part of `out` that belongs to clean blocks is NOT written; clean
+ *   blocks only contribute their |yh| to abs_sum.  The caller marks as active every block whose output is read later.
+ * backward: active blocks as the dense call; clean blocks (g_out == 0 on their whole input window):
+ *   g_x = 0, g_yh = reg_coef * (*reg_grad) * sign(yh) (or 0 without the regulariser). */
+int tnl_idwt_level_forward_sparse(const float* x, const float* yh, float* out, uint32_t n, uint32_t C, float* abs_sum,
+                                  const int32_t* active, const int32_t* clean, const int32_t* counts, uint32_t max_active,
+                                  uint32_t max_clean, tnl_stream_t stream);
+int tnl_idwt_level_backward_sparse(const float* g_out, float* g_x, float* g_yh, uint32_t n, uint32_t C, const float* yh,
+                                   const float* reg_grad, float reg_coef, const int32_t* active, const int32_t* clean,
+                                   const int32_t* counts, uint32_t max_active, uint32_t max_clean, tnl_stream_t stream);
+
 /* Bilinear tri-plane sampling: replaces F.grid_sample(bilinear, border, align_corners=True) +
  * permute/concat of TriPlaneVolume.forward (triplane_encoder.py:314-332, 523-530).
  * planes [3][R][R][C]; xyz [M][3]; feat [M][3C] with feature index p*C + c.

@@ -32,7 +32,9 @@ def test_version_and_argument_errors_need_no_gpu():
     dims = _lib.MlpDims(50, 64, 64)
     assert lib.tnl_mlp_packed_bytes(ctypes.byref(dims)) == 0      # unsupported width
     dims = _lib.MlpDims(96, 64, 64)
-    assert lib.tnl_mlp_packed_bytes(ctypes.byref(dims)) == 2 * 2 * (96 * 64 + 64 * 16 + 32 * 64 + 64 * 64) + 2 * (8 + 16) * 64
+    legacy = 2 * 2 * (96 * 64 + 64 * 16 + 32 * 64 + 64 * 64) + 2 * (8 + 16) * 64      # mma.sync fragment layout (fwd + dX)
+    tc = 2 * (64 * 96 + 16 * 64 + 64 * 32 + 64 * 64 + 16 * 64)                         # tcgen05 operand tiles
+    assert lib.tnl_mlp_packed_bytes(ctypes.byref(dims)) == (legacy + 255) // 256 * 256 + tc
     assert lib.tnl_march_rays_train_workspace(60000) >= 4 * 59
     assert lib.tnl_idwt_level_forward(ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), 12, 32, None, None) == -1
 

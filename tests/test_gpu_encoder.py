@@ -160,3 +160,43 @@ def test_full_size_properties():
     lhs = (y.detach().double() * gy.double()).sum().item()     # <A x, g>
     rhs = sum((t.detach().double() * t.grad.double()).sum().item() for t in xs)   # <x, A^T g>
     assert abs(lhs - rhs) <= 1e-5 * abs(lhs)
+
+
+def _plan_for(flags, R, n0, levels, C):
+    from trinerflet_b200.idwt_plan import IdwtPlan
+    return IdwtPlan(R, n0, levels, C, "cuda").update(flags.cuda())
+
+
+@pytest.mark.parametrize("C,n0,levels,density", [(16, 64, 2, 0.05), (32, 32, 3, 0.02), (24, 16, 1, 0.3), (16, 16, 2, 0.0)])
+def test_worklist_idwt_equals_dense_on_the_marked_tiles(C, n0, levels, density):
+    """Work-list reconstruction (idwt_plan.py): bit-identical to the dense kernels inside the marked tiles, identical
+    |yh| sums up to the order of the float atomics; the adjoint, fed a gradient that vanishes outside the marked tiles
+    (what the sampler's scatter produces), is bit-identical everywhere, regulariser gradient included."""
+    from trinerflet_b200.triplane_encoder import build_planes_with_abs
+    R = n0 * 2 ** levels
+    T = R // 32
+    g = torch.Generator().manual_seed(5)
+    flags = torch.rand(3, T, T, generator=g) < density
+    if density > 0:
+        flags[:, T // 4: T // 2 + 1, T // 3: T // 2 + 1] = True
+    plan = _plan_for(flags, R, n0, levels, C)
+    pf, coefs = _rand_coefs(C, n0, levels, seed=2)
+    with torch.no_grad():
+        coefs[-1][:, :, :, ::3, ::4] = 0.0                      # exact zeros: sign(0) = 0 in the regulariser gradient
+    mask = flags.cuda().repeat_interleave(32, 1).repeat_interleave(32, 2)[:, None]       # [3,1,R,R]
+    gout = torch.randn(3, C, R, R, generator=g).cuda() * mask
+    w_abs = torch.rand(levels, generator=g).cuda()
+    res = []
+    for p in (None, plan):
+        pf_g = cl_planes(pf.cuda()).requires_grad_(True)
+        coefs_g = [cl_coefs(c.cuda()).requires_grad_(True) for c in coefs]
+        out, abs_sums = build_planes_with_abs(pf_g, coefs_g, p)
+        ((out * gout).sum() + (abs_sums * w_abs).sum()).backward()
+        res.append((out.detach(), abs_sums.detach(), pf_g.grad, [c.grad for c in coefs_g]))
+    (o_d, a_d, gp_d, gc_d), (o_s, a_s, gp_s, gc_s) = res
+    assert torch.equal(torch.where(mask, o_s, 0.0), torch.where(mask, o_d, 0.0))
+    assert rel_l2(a_s, a_d) <= 1e-5
+    assert torch.equal(gp_s, gp_d)
+    for a, b in zip(gc_s, gc_d):
+        assert torch.equal(a, b)
+    assert plan.stats["tile_fraction"] == pytest.approx(float(flags.float().mean()))

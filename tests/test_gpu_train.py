@@ -134,3 +134,25 @@ def test_sparse_plane_gradient_exchange_single_rank():
         for a, b in zip(grads[0][1], grads[k][1]):
             # fp32 transport is exact; bf16 transport rounds the plane gradient to 8 mantissa bits (stated bound 1e-2)
             assert rel_l2(a, b) <= (1e-5 if k < 3 else 1e-2)
+
+
+def test_worklist_idwt_training_step_equals_dense():
+    """A steady-state training step with the plane reconstruction restricted to the occupied tiles (TrainStep.sparse_idwt)
+    produces the same loss and bit-identical parameter gradients as the dense reconstruction."""
+    from trinerflet_b200 import scene, trainer
+    sc = scene.make_scene()
+    ro, rd, tgt = (t.cuda() for t in scene.sample_batch(sc, 4096, torch.Generator().manual_seed(3)))
+    out = []
+    for sparse in (False, True):
+        net = _model("cpu")
+        ts = trainer.TrainStep(net, trainer.default_opt(), None, world_size=1)
+        ts.sparse_idwt = sparse
+        torch.manual_seed(0)
+        loss = ts.forward_backward(ro, rd, tgt, update_grid=False)
+        out.append((float(loss), [p.grad.clone() for p in net.parameters()]))
+        if sparse:
+            assert 0.0 < ts._plan.stats["tile_fraction"] < 0.9
+            assert net.encoder.idwt_plan is None          # later reconstructions are dense again
+    assert abs(out[0][0] - out[1][0]) <= 1e-6 * abs(out[0][0])
+    for a, b in zip(out[0][1], out[1][1]):
+        assert rel_l2(a, b) <= 1e-6       # the scatter's float atomics are the only run-to-run freedom

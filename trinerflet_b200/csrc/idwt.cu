@@ -27,12 +27,21 @@ namespace tnl {
 template <typename Cfg>
 __global__ void __launch_bounds__(Cfg::NT, (768 / Cfg::NT) > 0 ? (768 / Cfg::NT) : 1)
 k_idwt_fwd(const float* __restrict__ x, const float* __restrict__ yh, float* __restrict__ out, int n, int C,
-           int rows_per_cta, float* __restrict__ abs_sum) {
+           int rows_per_cta, float* __restrict__ abs_sum, const int4* __restrict__ items, const int* __restrict__ n_items) {
     extern __shared__ __align__(16) float smem[];
     float* mid0 = smem;
     float* stage0 = smem + 2 * Cfg::MID_F;
     const int tid = threadIdx.x;
-    const IdwtGeom g = idwt_geom<Cfg>(tid, IdwtBlock{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z}, n, C, rows_per_cta);
+    IdwtGeom g;
+    if (items != nullptr) {   // work-list mode: blockIdx.x = item * chunks + chunk
+        const int chunks = C / Cfg::CG;
+        const int idx = blockIdx.x / chunks;
+        if (idx >= __ldg(n_items)) return;
+        const int4 it = __ldg(items + idx);
+        g = idwt_geom_item<Cfg>(tid, blockIdx.x % chunks, IdwtItem{it.x, it.y, it.z, it.w}, n, C);
+    } else {
+        g = idwt_geom<Cfg>(tid, IdwtBlock{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z}, n, C, rows_per_cta);
+    }
     FwdState st;
     fwd_state_init<Cfg>(st, g, x, yh, tid);
     fwd_issue_stage<Cfg>(g, st, stage0, tid);
@@ -71,12 +80,22 @@ k_idwt_fwd(const float* __restrict__ x, const float* __restrict__ yh, float* __r
 template <typename Cfg>
 __global__ void __launch_bounds__(Cfg::NT, (768 / Cfg::NT) > 0 ? (768 / Cfg::NT) : 1)
 k_idwt_bwd(const float* __restrict__ gout, float* __restrict__ g_x, float* __restrict__ g_yh, int n, int C,
-           int rows_per_cta, const float* __restrict__ yh, const float* __restrict__ reg_grad, float reg_coef, int plane0) {
+           int rows_per_cta, const float* __restrict__ yh, const float* __restrict__ reg_grad, float reg_coef, int plane0,
+           const int4* __restrict__ items, const int* __restrict__ n_items) {
     extern __shared__ __align__(16) float smem[];
     float* mid0 = smem;
     float* stage0 = smem + 2 * Cfg::MID_B;
     const int tid = threadIdx.x;
-    const IdwtGeom g = idwt_geom<Cfg>(tid, IdwtBlock{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z + plane0}, n, C, rows_per_cta);
+    IdwtGeom g;
+    if (items != nullptr) {
+        const int chunks = C / Cfg::CG;
+        const int idx = blockIdx.x / chunks;
+        if (idx >= __ldg(n_items)) return;
+        const int4 it = __ldg(items + idx);
+        g = idwt_geom_item<Cfg>(tid, blockIdx.x % chunks, IdwtItem{it.x, it.y, it.z, it.w}, n, C);
+    } else {
+        g = idwt_geom<Cfg>(tid, IdwtBlock{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z + plane0}, n, C, rows_per_cta);
+    }
     BwdState st;
     bwd_state_init<Cfg>(st, g, gout);
     const float reg = (yh != nullptr && reg_grad != nullptr) ? reg_coef * __ldg(reg_grad) : 0.f;
@@ -100,6 +119,110 @@ k_idwt_bwd(const float* __restrict__ gout, float* __restrict__ g_x, float* __res
     cp_async_wait<0>();
 }
 
+// ---- clean blocks of the work-list mode: nothing to reconstruct / no incoming gradient -------------------------------
+// item = {plane, m0, row_lo, row_hi}: 16 coarse columns x rows; every (row, band) is one contiguous run of 16*C floats
+__global__ void __launch_bounds__(256)
+k_idwt_clean_fwd(const float* __restrict__ yh, int n, int C, const int4* __restrict__ items, const int* __restrict__ n_items,
+                 float* __restrict__ abs_sum) {
+    __shared__ float red[8];
+    const int cnt = __ldg(n_items);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float acc = 0.f;
+    const int run4 = 16 * C / 4;
+    for (int idx = blockIdx.x; idx < cnt; idx += gridDim.x) {
+        const int4 it = __ldg(items + idx);
+        const int rows = min(it.w, n) - it.z;
+        for (int rb = warp; rb < 3 * rows; rb += 8) {          // one warp per (band, row) run of 16*C contiguous floats
+            const int b = rb / rows, r = rb - b * rows;
+            const float4* src = reinterpret_cast<const float4*>(yh + (((size_t)(it.x * 3 + b) * n + it.z + r) * n + it.y) * C);
+            for (int q = lane; q < run4; q += 32) {
+                const float4 v = __ldg(src + q);
+                acc += fabsf(v.x) + fabsf(v.y) + fabsf(v.z) + fabsf(v.w);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float w = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+        if (threadIdx.x == 0 && w != 0.f) atomicAdd(abs_sum, w);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_idwt_clean_bwd(const float* __restrict__ yh, float* __restrict__ g_x, float* __restrict__ g_yh, int n, int C,
+                 const int4* __restrict__ items, const int* __restrict__ n_items, const float* __restrict__ reg_grad, float reg_coef) {
+    const int cnt = __ldg(n_items);
+    const bool use_reg = yh != nullptr && reg_grad != nullptr;
+    const float reg = use_reg ? reg_coef * __ldg(reg_grad) : 0.f;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int run4 = 16 * C / 4;
+    for (int idx = blockIdx.x; idx < cnt; idx += gridDim.x) {
+        const int4 it = __ldg(items + idx);
+        const int rows = min(it.w, n) - it.z;
+        for (int rb = warp; rb < 4 * rows; rb += 8) {          // bands 0..2: coefficient gradients; 3: the low-pass gradient
+            const int b = rb / rows, r = rb - b * rows;
+            if (b == 3) {
+                float4* dst = reinterpret_cast<float4*>(g_x + (((size_t)it.x * n + it.z + r) * n + it.y) * C);
+                for (int q = lane; q < run4; q += 32) dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                const size_t off = (((size_t)(it.x * 3 + b) * n + it.z + r) * n + it.y) * C;
+                float4* dst = reinterpret_cast<float4*>(g_yh + off);
+                if (use_reg) {   // 0 + reg * sign(yh): the same fmaf the active blocks apply to their accumulated gradient
+                    const float4* src = reinterpret_cast<const float4*>(yh + off);
+                    for (int q = lane; q < run4; q += 32) {
+                        const float4 v = __ldg(src + q);
+                        dst[q] = make_float4(fmaf(reg, signf_(v.x), 0.f), fmaf(reg, signf_(v.y), 0.f), fmaf(reg, signf_(v.z), 0.f),
+                                             fmaf(reg, signf_(v.w), 0.f));
+                    }
+                } else {
+                    for (int q = lane; q < run4; q += 32) dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+    }
+}
+
+template <typename Cfg>
+static int launch_fwd_sparse(const float* x, const float* yh, float* out, uint32_t n, uint32_t C, float* abs_sum, const int32_t* active,
+                             const int32_t* clean, const int32_t* counts, uint32_t max_active, uint32_t max_clean, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_idwt_fwd<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_F);
+        attr_set = true;
+    }
+    if (max_active > 0)
+        k_idwt_fwd<Cfg><<<max_active * (C / Cfg::CG), Cfg::NT, Cfg::SMEM_F, stream>>>(x, yh, out, (int)n, (int)C, 0, abs_sum,
+                                                                                     reinterpret_cast<const int4*>(active), counts);
+    if (abs_sum != nullptr && max_clean > 0)
+        k_idwt_clean_fwd<<<min(max_clean, (uint32_t)kNumSM * 8u), 256, 0, stream>>>(yh, (int)n, (int)C, reinterpret_cast<const int4*>(clean),
+                                                                                   counts + 1, abs_sum);
+    return finish_launch("idwt_level_forward_sparse");
+}
+
+template <typename Cfg>
+static int launch_bwd_sparse(const float* g, float* g_x, float* g_yh, uint32_t n, uint32_t C, const float* yh, const float* reg_grad,
+                             float reg_coef, const int32_t* active, const int32_t* clean, const int32_t* counts, uint32_t max_active,
+                             uint32_t max_clean, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_idwt_bwd<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_B);
+        attr_set = true;
+    }
+    if (max_active > 0)
+        k_idwt_bwd<Cfg><<<max_active * (C / Cfg::CG), Cfg::NT, Cfg::SMEM_B, stream>>>(g, g_x, g_yh, (int)n, (int)C, 0, yh, reg_grad, reg_coef,
+                                                                                     0, reinterpret_cast<const int4*>(active), counts);
+    if (max_clean > 0)
+        k_idwt_clean_bwd<<<min(max_clean, (uint32_t)kNumSM * 8u), 256, 0, stream>>>(yh, g_x, g_yh, (int)n, (int)C,
+                                                                                   reinterpret_cast<const int4*>(clean), counts + 1, reg_grad,
+                                                                                   reg_coef);
+    return finish_launch("idwt_level_backward_sparse");
+}
+
 template <typename Cfg>
 static int launch_fwd(const float* x, const float* yh, float* out, uint32_t n, uint32_t C, float* abs_sum,
                       cudaStream_t stream) {
@@ -110,7 +233,7 @@ static int launch_fwd(const float* x, const float* yh, float* out, uint32_t n, u
     }
     unsigned gx, gy, gz, rows;
     idwt_grid<Cfg>(n, C, kNumSM, gx, gy, gz, rows);
-    k_idwt_fwd<Cfg><<<dim3(gx, gy, gz), Cfg::NT, Cfg::SMEM_F, stream>>>(x, yh, out, (int)n, (int)C, (int)rows, abs_sum);
+    k_idwt_fwd<Cfg><<<dim3(gx, gy, gz), Cfg::NT, Cfg::SMEM_F, stream>>>(x, yh, out, (int)n, (int)C, (int)rows, abs_sum, nullptr, nullptr);
     return finish_launch("idwt_level_forward");
 }
 
@@ -126,7 +249,7 @@ static int launch_bwd(const float* g, float* g_x, float* g_yh, uint32_t n, uint3
     idwt_grid<Cfg>(n, C, kNumSM, gx, gy, gz, rows);
     gz = nplanes;
     k_idwt_bwd<Cfg><<<dim3(gx, gy, gz), Cfg::NT, Cfg::SMEM_B, stream>>>(g, g_x, g_yh, (int)n, (int)C, (int)rows, yh, reg_grad,
-                                                                        reg_coef, (int)plane0);
+                                                                        reg_coef, (int)plane0, nullptr, nullptr);
     return finish_launch("idwt_level_backward");
 }
 
@@ -159,6 +282,32 @@ int tnl_idwt_level_backward(const float* g_out, float* g_x, float* g_yh, uint32_
     if (C % 24 == 0) return launch_bwd<IdwtCfg<24, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, plane0, nplanes, s);
     if (C % 16 == 0) return launch_bwd<IdwtCfg<16, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, plane0, nplanes, s);
     return launch_bwd<IdwtCfg<8, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, plane0, nplanes, s);
+}
+
+int tnl_idwt_level_forward_sparse(const float* x, const float* yh, float* out, uint32_t n, uint32_t C, float* abs_sum,
+                                  const int32_t* active, const int32_t* clean, const int32_t* counts, uint32_t max_active,
+                                  uint32_t max_clean, tnl_stream_t stream) {
+    TNL_ARG_CHECK(x && yh && out && counts, "null pointer");
+    TNL_ARG_CHECK((max_active == 0 || active) && (max_clean == 0 || clean), "null work list");
+    TNL_ARG_CHECK(n >= 16 && n % 16 == 0 && n <= 16384, "work-list mode: n must be a multiple of 16 in [16, 16384]");
+    TNL_ARG_CHECK(C >= 8 && C % 8 == 0, "C must be a multiple of 8");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (C % 24 == 0) return launch_fwd_sparse<IdwtCfg<24, 32>>(x, yh, out, n, C, abs_sum, active, clean, counts, max_active, max_clean, s);
+    if (C % 16 == 0) return launch_fwd_sparse<IdwtCfg<16, 32>>(x, yh, out, n, C, abs_sum, active, clean, counts, max_active, max_clean, s);
+    return launch_fwd_sparse<IdwtCfg<8, 32>>(x, yh, out, n, C, abs_sum, active, clean, counts, max_active, max_clean, s);
+}
+
+int tnl_idwt_level_backward_sparse(const float* g_out, float* g_x, float* g_yh, uint32_t n, uint32_t C, const float* yh,
+                                   const float* reg_grad, float reg_coef, const int32_t* active, const int32_t* clean,
+                                   const int32_t* counts, uint32_t max_active, uint32_t max_clean, tnl_stream_t stream) {
+    TNL_ARG_CHECK(g_out && g_x && g_yh && counts, "null pointer");
+    TNL_ARG_CHECK((max_active == 0 || active) && (max_clean == 0 || clean), "null work list");
+    TNL_ARG_CHECK(n >= 16 && n % 16 == 0 && n <= 16384, "work-list mode: n must be a multiple of 16 in [16, 16384]");
+    TNL_ARG_CHECK(C >= 8 && C % 8 == 0, "C must be a multiple of 8");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (C % 24 == 0) return launch_bwd_sparse<IdwtCfg<24, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, active, clean, counts, max_active, max_clean, s);
+    if (C % 16 == 0) return launch_bwd_sparse<IdwtCfg<16, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, active, clean, counts, max_active, max_clean, s);
+    return launch_bwd_sparse<IdwtCfg<8, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, active, clean, counts, max_active, max_clean, s);
 }
 
 }  // extern "C"

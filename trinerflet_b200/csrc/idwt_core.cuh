@@ -144,6 +144,29 @@ TNL_HD IdwtGeom idwt_geom(int tid, IdwtBlock b, int n, int C, int rows_per_cta) 
     return g;
 }
 
+// work-list mode: the CTA's block comes from an item {plane, first coarse column, row_lo, row_hi} instead of the grid
+struct IdwtItem {
+    int plane, m0, row_lo, row_hi;
+};
+
+template <typename Cfg>
+TNL_HD IdwtGeom idwt_geom_item(int tid, int chunk, IdwtItem it, int n, int C) {
+    IdwtGeom g;
+    g.n = n;
+    g.C = C;
+    g.plane = it.plane;
+    g.c0 = chunk * Cfg::CG;
+    g.m0 = it.m0;
+    g.row_lo = it.row_lo;
+    g.row_hi = it.row_hi < n ? it.row_hi : n;
+    g.col = tid / Cfg::CG;
+    g.chan = g.c0 + tid % Cfg::CG;
+    g.begin = g.row_lo - 4;
+    g.end = g.row_hi + 4;
+    g.nsteps = (g.end - g.begin + Cfg::RA - 1) / Cfg::RA;
+    return g;
+}
+
 // ================================================================================================
 // forward
 // ================================================================================================

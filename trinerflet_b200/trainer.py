@@ -56,6 +56,10 @@ class TrainStep:
         # steady-state steps reconstruct the planes on a second stream, concurrently with the ray marching + cell sort
         self.prefetch_planes = True
         self._side = None
+        # steady-state steps reconstruct / differentiate the planes only where the occupancy grid puts samples
+        # (idwt_plan.py); steps that refresh the density grid query the field everywhere and stay dense
+        self.sparse_idwt = True
+        self._plan = None
         self._graphs = None
 
     # ---- the three segments of a step ---------------------------------------------------------------------------------
@@ -75,17 +79,25 @@ class TrainStep:
         model.train()
         enc.reset_cahce()
         do_update = (self.global_step % opt.update_extra_interval == 0) if update_grid is None else update_grid
+        enc.idwt_plan = None
+        if self.sparse_idwt and not do_update and rays_o.is_cuda and model.cuda_ray and self._plan_supported():
+            if self._plan is None:
+                self.refresh_plan()
+            enc.idwt_plan = self._plan
         if self.prefetch_planes and not do_update and rays_o.is_cuda:
             if self._side is None:
                 self._side = torch.cuda.Stream()
             planes = enc.prefetch_planes(self._side)
         else:
             planes = enc.get_planes()
+        enc.idwt_plan = None   # the cached planes of this step are built; anything reconstructed later is dense again
         if do_update:
             with torch.autocast("cuda", dtype=torch.float16, enabled=opt.fp16):
                 model.update_extra_state()
             if self.reducer is not None:
                 self.reducer.refresh()
+            if self._plan is not None:
+                self.refresh_plan()
         capturing = torch.cuda.is_current_stream_capturing()
         if self.reducer is None:
             # single GPU (or dense exchange): one backward through render + IDWT
@@ -115,6 +127,17 @@ class TrainStep:
             loss = loss.detach() + (reg.detach() if reg is not None else 0.0)
         self.global_step += 1
         return loss.detach()
+
+    def _plan_supported(self):
+        enc = self.model.encoder
+        n0 = enc.planes_features.shape[2]
+        return len(enc.planes_features_wavelet_coefs) >= 1 and n0 % 16 == 0 and enc.plane_resolution % 32 == 0
+
+    def refresh_plan(self):
+        """(Re)build the IDWT work lists from the current density bitfield; must follow every change of the bitfield."""
+        from .idwt_plan import IdwtPlan
+        self._plan = IdwtPlan.from_model(self.model, plan=self._plan)
+        return self._plan
 
     def _exchange(self):
         planes, leaf, reg = self._cut
@@ -188,6 +211,8 @@ class TrainStep:
         self._static = tuple(t.clone() for t in (rays_o, rays_d, images))
         if self.reducer is not None:
             self.reducer.refresh()
+        if self.sparse_idwt and self._plan_supported():
+            self.refresh_plan()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -208,6 +233,7 @@ class TrainStep:
             with torch.cuda.graph(gB, pool=gA.pool(), stream=side):
                 self._idwt_backward()
         self._graphs = (gA, gB)
+        self._graph_plan_version = self._plan.version if self._plan is not None else None
         return self
 
     def replay(self, rays_o, rays_d, images):
@@ -215,6 +241,8 @@ class TrainStep:
         for dst, src in zip(self._static, (rays_o, rays_d, images)):
             dst.copy_(src, non_blocking=True)
         gA, gB = self._graphs
+        if self._plan is not None and self._plan.version != self._graph_plan_version:
+            raise RuntimeError("the IDWT work lists were reallocated after capture(): capture the step again")
         gA.replay()
         if gB is not None:
             self._exchange()

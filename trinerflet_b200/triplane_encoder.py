@@ -92,11 +92,16 @@ class _BuildPlanes(Function):
     gradient  g_abs[l] * sign(yh_l)  folded into the coefficient-gradient store."""
 
     @staticmethod
-    def forward(ctx, planes_features, *coefs):
+    def forward(ctx, planes_features, plan, *coefs):
+        """plan: None = dense (reference semantics); an idwt_plan.IdwtPlan = reconstruct only the blocks the training-step
+        sampler reads (the rest of the returned planes is undefined) and restrict the adjoint to where gradient arrives."""
         _require_cuda_f32(planes_features, "planes_features")
         x = to_cl_planes(planes_features.detach())
         C, n = x.shape[1], x.shape[2]
         ctx.n0, ctx.C, ctx.levels = n, C, len(coefs)
+        if plan is not None and (plan.levels != len(coefs) or plan.n0 != n or plan.C != C):
+            raise RuntimeError("IdwtPlan does not match the encoder geometry")
+        ctx.plan = plan
         ctx.set_materialize_grads(False)   # an unused abs_sums output must not cost a pass over the coefficients
         abs_sums = torch.zeros(max(len(coefs), 1), device=x.device, dtype=torch.float32)
         saved = []
@@ -107,7 +112,10 @@ class _BuildPlanes(Function):
             yh = to_cl_coefs(yh.detach())
             saved.append(yh)
             out = cl_empty_planes(C, 2 * n, device=x.device)
-            call("tnl_idwt_level_forward", ptr(x), ptr(yh), ptr(out), n, C, ptr(abs_sums[l:l + 1]), stream())
+            if plan is None:
+                call("tnl_idwt_level_forward", ptr(x), ptr(yh), ptr(out), n, C, ptr(abs_sums[l:l + 1]), stream())
+            else:
+                plan.forward_level(l, x, yh, out, n, abs_sums[l:l + 1])
             x, n = out, 2 * n
         ctx.save_for_backward(*saved)
         return x, abs_sums
@@ -127,14 +135,19 @@ class _BuildPlanes(Function):
             n //= 2
             g_x = cl_empty_planes(C, n, device=g.device)
             g_yh = cl_empty_coefs(C, n, device=g.device)
-            if g_abs is not None:
+            if ctx.plan is not None:
+                if g_abs is not None:
+                    ctx.plan.backward_level(l, g, g_x, g_yh, n, yhs[l], g_abs[l:l + 1], 1.0)
+                else:
+                    ctx.plan.backward_level(l, g, g_x, g_yh, n, None, None, 0.0)
+            elif g_abs is not None:
                 call("tnl_idwt_level_backward", ptr(g), ptr(g_x), ptr(g_yh), n, C, ptr(yhs[l]), ptr(g_abs[l:l + 1]), 1.0,
                      0, 3, stream())
             else:
                 call("tnl_idwt_level_backward", ptr(g), ptr(g_x), ptr(g_yh), n, C, None, None, 0.0, 0, 3, stream())
             grads.append(g_yh)
             g = g_x
-        return (g, *reversed(grads))
+        return (g, None, *reversed(grads))
 
 
 class PlanewiseIdwtBackward:
@@ -169,13 +182,13 @@ class PlanewiseIdwtBackward:
             p.grad = g
 
 
-def build_planes_with_abs(planes_features, coefs):
+def build_planes_with_abs(planes_features, coefs, plan=None):
     """-> (planes [3,C,R,R], abs_sums [L] with abs_sums[l] = sum |coefs[l]|), both differentiable."""
-    return _BuildPlanes.apply(planes_features, *coefs)
+    return _BuildPlanes.apply(planes_features, plan, *coefs)
 
 
-def build_planes(planes_features, coefs):
-    return _BuildPlanes.apply(planes_features, *coefs)[0]
+def build_planes(planes_features, coefs, plan=None):
+    return _BuildPlanes.apply(planes_features, plan, *coefs)[0]
 
 
 # ----------------------------------------------------------------------------------------------
@@ -298,6 +311,9 @@ class TriPlaneVolume(nn.Module):
 
         self.last_used_planes = None
         self._last_abs_sums = None
+        # training hot path only: an idwt_plan.IdwtPlan restricts the next reconstructions to the occupied tiles
+        # (see idwt_plan.py); None = dense planes, the reference's semantics
+        self.idwt_plan = None
         self._init_plane_features(planes_features)
 
     # -- parameters (triplane_encoder.py:155-231) --------------------------------------------------
@@ -387,7 +403,7 @@ class TriPlaneVolume(nn.Module):
         coefs = list(self.planes_features_wavelet_coefs) if coefs is None else coefs
         if self.inner_wavelet_scale <= 1 or len(coefs) == 0:
             return planes_features
-        planes, abs_sums = build_planes_with_abs(planes_features, coefs)
+        planes, abs_sums = build_planes_with_abs(planes_features, coefs, self.idwt_plan)
         self._last_abs_sums = abs_sums
         return planes
 
