@@ -123,13 +123,16 @@ int tnl_idwt_level_backward(const float* g_out, float* g_x, float* g_yh, uint32_
  *   [2*m0, 2*m0+32) x [2*row_lo, 2*row_hi)); the part of `out` that belongs to clean blocks is NOT written; clean
  *   blocks only contribute their |yh| to abs_sum.  The caller marks as active every block whose output is read later.
  * backward: active blocks as the dense call; clean blocks (g_out == 0 on their whole input window):
- *   g_x = 0, g_yh = reg_coef * (*reg_grad) * sign(yh) (or 0 without the regulariser). */
+ *   g_x = 0, g_yh = reg_coef * (*reg_grad) * sign(yh) (or 0 without the regulariser).
+ *   parts: bit 0 = process the active blocks, bit 1 = the clean blocks (3 = both).  The clean part does not depend on
+ *   g_out (may be NULL), so the multi-GPU path runs it while the plane gradient is still being exchanged. */
 int tnl_idwt_level_forward_sparse(const float* x, const float* yh, float* out, uint32_t n, uint32_t C, float* abs_sum,
                                   const int32_t* active, const int32_t* clean, const int32_t* counts, uint32_t max_active,
                                   uint32_t max_clean, tnl_stream_t stream);
 int tnl_idwt_level_backward_sparse(const float* g_out, float* g_x, float* g_yh, uint32_t n, uint32_t C, const float* yh,
                                    const float* reg_grad, float reg_coef, const int32_t* active, const int32_t* clean,
-                                   const int32_t* counts, uint32_t max_active, uint32_t max_clean, tnl_stream_t stream);
+                                   const int32_t* counts, uint32_t max_active, uint32_t max_clean, uint32_t parts,
+                                   tnl_stream_t stream);
 
 /* Bilinear tri-plane sampling: replaces F.grid_sample(bilinear, border, align_corners=True) +
  * permute/concat of TriPlaneVolume.forward (triplane_encoder.py:314-332, 523-530).

@@ -207,16 +207,16 @@ static int launch_fwd_sparse(const float* x, const float* yh, float* out, uint32
 template <typename Cfg>
 static int launch_bwd_sparse(const float* g, float* g_x, float* g_yh, uint32_t n, uint32_t C, const float* yh, const float* reg_grad,
                              float reg_coef, const int32_t* active, const int32_t* clean, const int32_t* counts, uint32_t max_active,
-                             uint32_t max_clean, cudaStream_t stream) {
+                             uint32_t max_clean, uint32_t parts, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_idwt_bwd<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_B);
         attr_set = true;
     }
-    if (max_active > 0)
+    if (max_active > 0 && (parts & 1u))
         k_idwt_bwd<Cfg><<<max_active * (C / Cfg::CG), Cfg::NT, Cfg::SMEM_B, stream>>>(g, g_x, g_yh, (int)n, (int)C, 0, yh, reg_grad, reg_coef,
                                                                                      0, reinterpret_cast<const int4*>(active), counts);
-    if (max_clean > 0)
+    if (max_clean > 0 && (parts & 2u))
         k_idwt_clean_bwd<<<min(max_clean, (uint32_t)kNumSM * 8u), 256, 0, stream>>>(yh, g_x, g_yh, (int)n, (int)C,
                                                                                    reinterpret_cast<const int4*>(clean), counts + 1, reg_grad,
                                                                                    reg_coef);
@@ -299,15 +299,16 @@ int tnl_idwt_level_forward_sparse(const float* x, const float* yh, float* out, u
 
 int tnl_idwt_level_backward_sparse(const float* g_out, float* g_x, float* g_yh, uint32_t n, uint32_t C, const float* yh,
                                    const float* reg_grad, float reg_coef, const int32_t* active, const int32_t* clean,
-                                   const int32_t* counts, uint32_t max_active, uint32_t max_clean, tnl_stream_t stream) {
-    TNL_ARG_CHECK(g_out && g_x && g_yh && counts, "null pointer");
+                                   const int32_t* counts, uint32_t max_active, uint32_t max_clean, uint32_t parts, tnl_stream_t stream) {
+    TNL_ARG_CHECK((g_out || !(parts & 1u)) && g_x && g_yh && counts, "null pointer");
+    TNL_ARG_CHECK(parts >= 1 && parts <= 3, "parts: bit 0 = active blocks, bit 1 = clean blocks");
     TNL_ARG_CHECK((max_active == 0 || active) && (max_clean == 0 || clean), "null work list");
     TNL_ARG_CHECK(n >= 16 && n % 16 == 0 && n <= 16384, "work-list mode: n must be a multiple of 16 in [16, 16384]");
     TNL_ARG_CHECK(C >= 8 && C % 8 == 0, "C must be a multiple of 8");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (C % 24 == 0) return launch_bwd_sparse<IdwtCfg<24, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, active, clean, counts, max_active, max_clean, s);
-    if (C % 16 == 0) return launch_bwd_sparse<IdwtCfg<16, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, active, clean, counts, max_active, max_clean, s);
-    return launch_bwd_sparse<IdwtCfg<8, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, active, clean, counts, max_active, max_clean, s);
+    if (C % 24 == 0) return launch_bwd_sparse<IdwtCfg<24, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, active, clean, counts, max_active, max_clean, parts, s);
+    if (C % 16 == 0) return launch_bwd_sparse<IdwtCfg<16, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, active, clean, counts, max_active, max_clean, parts, s);
+    return launch_bwd_sparse<IdwtCfg<8, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, active, clean, counts, max_active, max_clean, parts, s);
 }
 
 }  // extern "C"

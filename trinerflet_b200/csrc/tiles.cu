@@ -50,19 +50,22 @@ __global__ void k_mark_dirty_tiles(const uint8_t* __restrict__ bitfield, uint32_
             for (int tx = lo[ax[p][0]]; tx <= hi[ax[p][0]]; ++tx) flags[(p * nt + ty) * nt + tx] = 1;
 }
 
-// tile id = (p * nt + ty) * nt + tx ; compact layout [n][T][T][C]; one CTA per (tile, row).
+// tile id = (p * nt + ty) * nt + tx ; compact layout [n][T][T][C]; one CTA per (tile, group of rows).
 // BF16: the compact buffer holds bfloat16 (halves the bytes on NVLink; the plane gradient itself stays fp32).
 template <bool PACK, bool BF16>
 __global__ void __launch_bounds__(256)
 k_tiles_copy(float* __restrict__ planes, void* __restrict__ compact, const int32_t* __restrict__ tile_ids, int R, int C, int T,
              float scale) {
-    const int tile = blockIdx.x, row = blockIdx.y;
+    const int tile = blockIdx.x;
     const int id = tile_ids[tile];
     const int nt = R / T;
     const int p = id / (nt * nt), ty = (id / nt) % nt, tx = id % nt;
+    const int n4 = T * C / 4;
+    const int rows_per_cta = (T + gridDim.y - 1) / gridDim.y;
+    const int row_end = min(T, (int)(blockIdx.y + 1) * rows_per_cta);
+    for (int row = blockIdx.y * rows_per_cta; row < row_end; ++row) {
     float4* src = reinterpret_cast<float4*>(planes + (((size_t)p * R + (size_t)ty * T + row) * R + (size_t)tx * T) * C);
     const size_t off4 = (((size_t)tile * T + row) * T) * C / 4;
-    const int n4 = T * C / 4;
     for (int i = threadIdx.x; i < n4; i += blockDim.x) {
         if (BF16) {
             uint2* dst = reinterpret_cast<uint2*>(compact) + off4;
@@ -85,6 +88,7 @@ k_tiles_copy(float* __restrict__ planes, void* __restrict__ compact, const int32
                 src[i] = v;
             }
         }
+    }
     }
 }
 
@@ -112,8 +116,8 @@ int tnl_tiles_pack(const float* planes, const int32_t* tile_ids, uint32_t n_tile
     TNL_ARG_CHECK(planes && tile_ids && compact, "null pointer");
     TNL_ARG_CHECK(R % T == 0 && (T * C) % 4 == 0, "bad tile geometry");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (bf16) k_tiles_copy<true, true><<<dim3(n_tiles, T), 256, 0, s>>>(const_cast<float*>(planes), compact, tile_ids, (int)R, (int)C, (int)T, 1.0f);
-    else k_tiles_copy<true, false><<<dim3(n_tiles, T), 256, 0, s>>>(const_cast<float*>(planes), compact, tile_ids, (int)R, (int)C, (int)T, 1.0f);
+    if (bf16) k_tiles_copy<true, true><<<dim3(n_tiles, 4), 256, 0, s>>>(const_cast<float*>(planes), compact, tile_ids, (int)R, (int)C, (int)T, 1.0f);
+    else k_tiles_copy<true, false><<<dim3(n_tiles, 4), 256, 0, s>>>(const_cast<float*>(planes), compact, tile_ids, (int)R, (int)C, (int)T, 1.0f);
     return finish_launch("tiles_pack");
 }
 
@@ -123,8 +127,8 @@ int tnl_tiles_unpack(const void* compact, const int32_t* tile_ids, uint32_t n_ti
     TNL_ARG_CHECK(planes && tile_ids && compact, "null pointer");
     TNL_ARG_CHECK(R % T == 0 && (T * C) % 4 == 0, "bad tile geometry");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (bf16) k_tiles_copy<false, true><<<dim3(n_tiles, T), 256, 0, s>>>(planes, const_cast<void*>(compact), tile_ids, (int)R, (int)C, (int)T, scale);
-    else k_tiles_copy<false, false><<<dim3(n_tiles, T), 256, 0, s>>>(planes, const_cast<void*>(compact), tile_ids, (int)R, (int)C, (int)T, scale);
+    if (bf16) k_tiles_copy<false, true><<<dim3(n_tiles, 4), 256, 0, s>>>(planes, const_cast<void*>(compact), tile_ids, (int)R, (int)C, (int)T, scale);
+    else k_tiles_copy<false, false><<<dim3(n_tiles, 4), 256, 0, s>>>(planes, const_cast<void*>(compact), tile_ids, (int)R, (int)C, (int)T, scale);
     return finish_launch("tiles_unpack");
 }
 

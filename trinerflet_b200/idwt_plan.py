@@ -141,8 +141,9 @@ class IdwtPlan:
         call("tnl_idwt_level_forward_sparse", ptr(x), ptr(yh), ptr(out), n, self.C, ptr(abs_sum), ptr(s["active"]), ptr(s["clean"]),
              ptr(s["counts"]), s["cap_active"], s["cap_clean"], stream())
 
-    def backward_level(self, l, g, g_x, g_yh, n, yh, reg_grad, reg_coef):
+    def backward_level(self, l, g, g_x, g_yh, n, yh, reg_grad, reg_coef, parts=3):
+        """parts: 1 = active blocks only, 2 = clean blocks only (independent of g), 3 = both."""
         s = self.bwd[l]
-        call("tnl_idwt_level_backward_sparse", ptr(g), ptr(g_x), ptr(g_yh), n, self.C, ptr(yh) if yh is not None else None,
-             ptr(reg_grad) if reg_grad is not None else None, float(reg_coef), ptr(s["active"]), ptr(s["clean"]), ptr(s["counts"]),
-             s["cap_active"], s["cap_clean"], stream())
+        call("tnl_idwt_level_backward_sparse", ptr(g) if g is not None else None, ptr(g_x), ptr(g_yh), n, self.C,
+             ptr(yh) if yh is not None else None, ptr(reg_grad) if reg_grad is not None else None, float(reg_coef), ptr(s["active"]),
+             ptr(s["clean"]), ptr(s["counts"]), s["cap_active"], s["cap_clean"], int(parts), stream())

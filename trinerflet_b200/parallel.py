@@ -96,6 +96,11 @@ class PlaneGradReducer:
 
     def reduce_(self, g_planes):
         """In place: g_planes (logical [3,C,R,R], channels-last storage) <- average over ranks."""
+        return self.finish_(g_planes, self.start_(g_planes))
+
+    def start_(self, g_planes):
+        """Pack the dirty tiles and start their all-reduce; returns the NCCL work handle (None with one rank).  Kernels
+        issued on the current stream before finish_() overlap the transfer."""
         from ._lib import call, ptr, stream
         if self.tile_ids is None:
             self.refresh()
@@ -109,7 +114,15 @@ class PlaneGradReducer:
             if not torch.allclose(total, inside, rtol=1e-4 if not self.bf16 else 1e-2):
                 raise RuntimeError("PlaneGradReducer: plane gradient found outside the dirty tiles")
         if self.world_size > 1 and dist.is_initialized():
-            dist.all_reduce(self.compact, op=dist.ReduceOp.SUM)
+            return dist.all_reduce(self.compact, op=dist.ReduceOp.SUM, async_op=True)
+        return None
+
+    def finish_(self, g_planes, work):
+        from ._lib import call, ptr, stream
+        if work is not None:
+            work.wait()          # the current stream waits for the all-reduce; the host does not
+        R, C, T = g_planes.shape[2], g_planes.shape[1], self.tile
+        dense = _dense_view(g_planes)
         call("tnl_tiles_unpack", ptr(self.compact), ptr(self.tile_ids), self.n_tiles, R, C, T, 1.0 / self.world_size,
              self.bf16, ptr(dense), stream())
         return g_planes

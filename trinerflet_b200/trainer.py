@@ -80,17 +80,27 @@ class TrainStep:
         enc.reset_cahce()
         do_update = (self.global_step % opt.update_extra_interval == 0) if update_grid is None else update_grid
         enc.idwt_plan = None
-        if self.sparse_idwt and not do_update and rays_o.is_cuda and model.cuda_ray and self._plan_supported():
+        use_plan = self.sparse_idwt and not do_update and rays_o.is_cuda and model.cuda_ray and self._plan_supported()
+        if use_plan:
             if self._plan is None:
                 self.refresh_plan()
             enc.idwt_plan = self._plan
-        if self.prefetch_planes and not do_update and rays_o.is_cuda:
+        prefetch = self.prefetch_planes and not do_update and rays_o.is_cuda
+        if prefetch:
             if self._side is None:
                 self._side = torch.cuda.Stream()
             planes = enc.prefetch_planes(self._side)
         else:
             planes = enc.get_planes()
         enc.idwt_plan = None   # the cached planes of this step are built; anything reconstructed later is dense again
+        # work-list steps drive the IDWT backward themselves (two parts, see SplitIdwtBackward); its gradient-independent
+        # part goes to the prefetch stream right away and overlaps the render
+        self._split = None
+        if use_plan and all(p.grad is None for p in enc.parameters()):
+            self._split = self._make_split(enc, opt)
+            if prefetch and self._split.reg_ready:
+                with torch.cuda.stream(self._side):
+                    self._split.run_clean()
         if do_update:
             with torch.autocast("cuda", dtype=torch.float16, enabled=opt.fp16):
                 model.update_extra_state()
@@ -99,8 +109,8 @@ class TrainStep:
             if self._plan is not None:
                 self.refresh_plan()
         capturing = torch.cuda.is_current_stream_capturing()
-        if self.reducer is None:
-            # single GPU (or dense exchange): one backward through render + IDWT
+        if self.reducer is None and self._split is None:
+            # single GPU, dense planes: one backward through render + IDWT
             with torch.autocast("cuda", dtype=torch.float16, enabled=opt.fp16):
                 loss = self._render_loss(rays_o, rays_d, images)
                 enc._join_prefetch()
@@ -112,7 +122,7 @@ class TrainStep:
             if self.world_size > 1 and not capturing:
                 parallel.allreduce_gradients(model, self.world_size)
         else:
-            # ray-sharded DP: cut the graph at the planes, exchange the (sparse) plane gradient, then run the IDWT backward
+            # cut the graph at the planes: render backward -> plane gradient; (N > 1: exchange its dirty tiles;) IDWT backward
             leaf = planes.detach().requires_grad_(True)
             enc.last_used_planes = leaf
             with torch.autocast("cuda", dtype=torch.float16, enabled=opt.fp16):
@@ -122,11 +132,36 @@ class TrainStep:
                 enc.reset_cahce()
                 self.scaler.scale(loss).backward()                    # -> leaf.grad and the MLP gradients of this shard
             self._cut = (planes, leaf, reg)
-            if not capturing:
-                self._exchange_and_finish()
+            if self.reducer is None:
+                self._idwt_backward()
+                self._cut = None
+                self._split = None
+                if self.world_size > 1 and not capturing:
+                    parallel.allreduce_gradients(model, self.world_size)
+            else:
+                if prefetch:   # the early part of the IDWT backward belongs to this segment of the step (graph A)
+                    torch.cuda.current_stream().wait_stream(self._side)
+                if not capturing:
+                    self._exchange_and_finish()
             loss = loss.detach() + (reg.detach() if reg is not None else 0.0)
         self.global_step += 1
         return loss.detach()
+
+    def _make_split(self, enc, opt):
+        from .triplane_encoder import SplitIdwtBackward
+        feats = enc.get_wavelet_features()
+        lam = opt.wavelet_regularization
+        reg_coef = lam / (sum(v.numel() for v in feats) * len(feats)) if (lam > 0 and len(feats) > 0) else 0.0
+        if not self.scaler.is_enabled():
+            if getattr(self, "_one", None) is None:
+                self._one = torch.ones(1, device=enc.planes_features.device)
+            scale_t = self._one
+        else:
+            scale_t = getattr(self.scaler, "_scale", None)    # created lazily by the first scaler.scale() call
+        sp = SplitIdwtBackward(enc, self._plan, scale_t, reg_coef)
+        sp.reg_ready = reg_coef == 0.0 or scale_t is not None
+        sp.clean_done = False
+        return sp
 
     def _plan_supported(self):
         enc = self.model.encoder
@@ -140,13 +175,32 @@ class TrainStep:
         return self._plan
 
     def _exchange(self):
+        self._exchange_finish(self._exchange_start())
+
+    def _exchange_start(self):
+        """pack the dirty tiles of the plane gradient and start their all-reduce (asynchronous: NCCL's own stream)."""
         planes, leaf, reg = self._cut
-        self.reducer.reduce_(leaf.grad)
+        return self.reducer.start_(leaf.grad)
+
+    def _exchange_finish(self, work):
+        planes, leaf, reg = self._cut
+        self.reducer.finish_(leaf.grad, work)
         mlp = [p for n, p in self.model.named_parameters() if not n.startswith("encoder.")]
         parallel.allreduce_small(mlp, self.world_size)
 
     def _idwt_backward(self):
         planes, leaf, reg = self._cut
+        sp = self._split
+        if sp is not None:
+            if not sp.clean_done:     # first step of a run: the loss scale did not exist yet when the step started
+                if sp.reg_scale is None and sp.reg_coef != 0.0:
+                    sp.reg_scale = self.scaler._scale
+                sp.run_clean()
+            if self._side is not None and self.reducer is None:   # (N > 1: forward_backward has already joined the stream)
+                torch.cuda.current_stream().wait_stream(self._side)
+            sp.run_active(leaf.grad)
+            sp.assign()
+            return
         if self._side is not None:   # the reconstruction's autograd node runs on the prefetch stream
             self._side.wait_stream(torch.cuda.current_stream())
         if reg is not None:   # identical on every rank: added once, after the exchange
@@ -200,6 +254,7 @@ class TrainStep:
             self._exchange()
             self._idwt_backward()
         self._cut = None   # drop the autograd graph (and the AccumulateGrad nodes it keeps alive) of this step
+        self._split = None
 
     # ---- CUDA-graph mode: a steady-state step is one (N = 1) or two (N > 1, NCCL in between) graph launches ----------
     def capture(self, rays_o, rays_d, images, warmup=3):

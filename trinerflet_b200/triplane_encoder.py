@@ -182,6 +182,44 @@ class PlanewiseIdwtBackward:
             p.grad = g
 
 
+class SplitIdwtBackward:
+    """The adjoint of a work-list plane reconstruction in two parts (multi-GPU path): `run_clean()` covers the blocks that
+    receive no plane gradient (regulariser gradient / zeros only) and needs nothing from the render backward, so it runs
+    while the plane gradient is still being exchanged between the ranks; `run_active(g_planes)` pushes the exchanged
+    gradient through the remaining blocks.  `assign()` installs the results as parameter gradients."""
+
+    def __init__(self, encoder, plan, reg_scale=None, reg_coef=0.0):
+        self.enc, self.plan = encoder, plan
+        self.C, self.levels = encoder.number_of_features, len(encoder.planes_features_wavelet_coefs)
+        self.n0 = encoder.planes_features.shape[2]
+        self.reg_scale, self.reg_coef = reg_scale, float(reg_coef)
+        dev = encoder.planes_features.device
+        self.g_x = [cl_empty_planes(self.C, self.n0 * 2 ** l, device=dev) for l in range(self.levels)]
+        self.g_yh = [cl_empty_coefs(self.C, self.n0 * 2 ** l, device=dev) for l in range(self.levels)]
+
+    def _level(self, l, g, parts):
+        use_reg = self.reg_scale is not None and self.reg_coef != 0.0
+        yh = self.enc.planes_features_wavelet_coefs[l].detach()
+        self.plan.backward_level(l, g, self.g_x[l], self.g_yh[l], self.n0 * 2 ** l, yh if use_reg else None,
+                                 self.reg_scale if use_reg else None, self.reg_coef, parts)
+
+    def run_clean(self):
+        for l in range(self.levels):
+            self._level(l, None, 2)
+        self.clean_done = True
+
+    def run_active(self, g_planes):
+        g = to_cl_planes(g_planes)
+        for l in reversed(range(self.levels)):
+            self._level(l, g, 1)
+            g = self.g_x[l]
+
+    def assign(self):
+        self.enc.planes_features.grad = self.g_x[0]
+        for p, g in zip(self.enc.planes_features_wavelet_coefs, self.g_yh):
+            p.grad = g
+
+
 def build_planes_with_abs(planes_features, coefs, plan=None):
     """-> (planes [3,C,R,R], abs_sums [L] with abs_sums[l] = sum |coefs[l]|), both differentiable."""
     return _BuildPlanes.apply(planes_features, plan, *coefs)
