@@ -48,28 +48,66 @@ def parse():
 # clocks
 # ---------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed regions (NVML, every 2 ms in a thread; a timed region of a few
+    steps is shorter than nvidia-smi's start-up time, so the CLI loop of the profiling recipe is only the fallback)."""
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.gpu, self.sm, self.mask, self.max_mhz = gpu_index, [], 0, None
+        self.h = self.nv = self.proc = None
+        self.active = False
+        self.stop_flag = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[gpu_index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            if self.active:
+                try:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                except Exception:
+                    pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nv is not None:
+            self.active = True
+            return
         try:
+            self.rows = []
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            threading.Thread(target=lambda: [self.rows.append([c.strip() for c in ln.split(",")]) for ln in self.proc.stdout],
+                             daemon=True).start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def pause(self):
+        self.active = False
 
     def stop(self):
+        self.active = False
+        self.stop_flag = True
+        if self.nv is not None:
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(n for b, n in self.REASONS if self.mask & b), "samples": len(sm), "source": "nvml"}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -86,7 +124,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -109,7 +147,8 @@ def algorithmic_bytes(name, meta, C, m_valid, plan=None):
             a = plan.stats["active_fraction_forward"][lvl]
             return px * (a * (4 + 4) + (1 - a) * 3)
         b = plan.stats["active_fraction_backward"][lvl]
-        return px * (b * 4 + 3 + 4)
+        parts = int(meta[-1])            # bit 0: active blocks, bit 1: clean blocks (they may be separate calls)
+        return px * (((parts & 1) and b * (4 + 3 + 4)) + ((parts & 2) and (1 - b) * (3 + 4)))
     if name == "tnl_sample_planes_forward":
         return m_valid * (12 + g)
     if name == "tnl_sample_planes_backward":
@@ -257,7 +296,7 @@ def main():
     for i in range(args.warmup):
         one_step(devb[i])
     # ---- timed region: device-resident inputs ----
-    clocks = ClockSampler(local_rank)
+    clocks = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     if rank == 0:
         clocks.start()
@@ -271,7 +310,8 @@ def main():
     launches = _lib.launch_count - launches0
     if use_graph:   # replays do not pass through the Python launch counter: kernels per captured step x steps
         launches = ts._graph_kernel_count * args.steps
-    clk = clocks.stop() if rank == 0 else None
+    if rank == 0:
+        clocks.pause()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     counts = net.step_counter[:, 0].float().max().reshape(1)     # samples of the (graph-captured) step slot
     if world > 1:
@@ -284,6 +324,8 @@ def main():
 
     # ---- e2e: host (pinned) buffers in, loss out, every step ----
     barrier()
+    if rank == 0:
+        clocks.start()       # the end-to-end region is a timed region under load too
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     h2d = d2h = 0
@@ -296,6 +338,7 @@ def main():
         d2h = 4
     f1.record()
     barrier()
+    clk = clocks.stop() if rank == 0 else None
     ms2 = torch.tensor([f0.elapsed_time(f1)], device=dev)
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)

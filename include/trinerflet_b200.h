@@ -125,14 +125,17 @@ int tnl_idwt_level_backward(const float* g_out, float* g_x, float* g_yh, uint32_
  * backward: active blocks as the dense call; clean blocks (g_out == 0 on their whole input window):
  *   g_x = 0, g_yh = reg_coef * (*reg_grad) * sign(yh) (or 0 without the regulariser).
  *   parts: bit 0 = process the active blocks, bit 1 = the clean blocks (3 = both).  The clean part does not depend on
- *   g_out (may be NULL), so the multi-GPU path runs it while the plane gradient is still being exchanged. */
+ *   g_out (may be NULL), so the training step issues it early on a second stream.  abs_sum (may be NULL): the clean
+ *   part adds sum |yh| over its blocks, so a forward that ran with parts = 1 (active blocks only) gets the complete
+ *   regulariser value without a second pass over the coefficients.
+ * forward parts: bit 0 = reconstruct the active blocks, bit 1 = add the clean blocks' |yh| to abs_sum. */
 int tnl_idwt_level_forward_sparse(const float* x, const float* yh, float* out, uint32_t n, uint32_t C, float* abs_sum,
                                   const int32_t* active, const int32_t* clean, const int32_t* counts, uint32_t max_active,
-                                  uint32_t max_clean, tnl_stream_t stream);
+                                  uint32_t max_clean, uint32_t parts, tnl_stream_t stream);
 int tnl_idwt_level_backward_sparse(const float* g_out, float* g_x, float* g_yh, uint32_t n, uint32_t C, const float* yh,
                                    const float* reg_grad, float reg_coef, const int32_t* active, const int32_t* clean,
                                    const int32_t* counts, uint32_t max_active, uint32_t max_clean, uint32_t parts,
-                                   tnl_stream_t stream);
+                                   float* abs_sum, tnl_stream_t stream);
 
 /* Bilinear tri-plane sampling: replaces F.grid_sample(bilinear, border, align_corners=True) +
  * permute/concat of TriPlaneVolume.forward (triplane_encoder.py:314-332, 523-530).
@@ -226,6 +229,10 @@ int tnl_mark_dirty_tiles(const uint8_t* bitfield, uint32_t cascade, uint32_t H, 
 /* gather / scatter the listed tiles between planes [3][R][R][C] and a compact buffer [n_tiles][T][T][C]
  * (tile id = (p * R/T + ty) * R/T + tx); unpack multiplies by `scale` (1/world_size for an average).
  * bf16 != 0: the compact (transport) buffer is bfloat16 -- half the NVLink bytes; planes stay fp32. */
+/* Zero the listed tiles of planes [3][R][R][C] (the part of the plane-gradient buffer the work-list IDWT backward reads);
+ * *count (device) = number of valid ids, the grid is sized by `capacity`. */
+int tnl_tiles_zero(float* planes, const int32_t* tile_ids, const int32_t* count, uint32_t capacity, uint32_t R, uint32_t C,
+                   uint32_t T, tnl_stream_t stream);
 int tnl_tiles_pack(const float* planes, const int32_t* tile_ids, uint32_t n_tiles, uint32_t R, uint32_t C, uint32_t T,
                    void* compact, int bf16, tnl_stream_t stream);
 int tnl_tiles_unpack(const void* compact, const int32_t* tile_ids, uint32_t n_tiles, uint32_t R, uint32_t C, uint32_t T,

@@ -155,12 +155,15 @@ k_idwt_clean_fwd(const float* __restrict__ yh, int n, int C, const int4* __restr
 
 __global__ void __launch_bounds__(256)
 k_idwt_clean_bwd(const float* __restrict__ yh, float* __restrict__ g_x, float* __restrict__ g_yh, int n, int C,
-                 const int4* __restrict__ items, const int* __restrict__ n_items, const float* __restrict__ reg_grad, float reg_coef) {
+                 const int4* __restrict__ items, const int* __restrict__ n_items, const float* __restrict__ reg_grad, float reg_coef,
+                 float* __restrict__ abs_sum) {
+    __shared__ float red[8];
     const int cnt = __ldg(n_items);
     const bool use_reg = yh != nullptr && reg_grad != nullptr;
     const float reg = use_reg ? reg_coef * __ldg(reg_grad) : 0.f;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int run4 = 16 * C / 4;
+    float acc = 0.f;   // sum |yh| over the clean blocks (the forward value of the regulariser, read here anyway)
     for (int idx = blockIdx.x; idx < cnt; idx += gridDim.x) {
         const int4 it = __ldg(items + idx);
         const int rows = min(it.w, n) - it.z;
@@ -176,6 +179,7 @@ k_idwt_clean_bwd(const float* __restrict__ yh, float* __restrict__ g_x, float* _
                     const float4* src = reinterpret_cast<const float4*>(yh + off);
                     for (int q = lane; q < run4; q += 32) {
                         const float4 v = __ldg(src + q);
+                        acc += fabsf(v.x) + fabsf(v.y) + fabsf(v.z) + fabsf(v.w);
                         dst[q] = make_float4(fmaf(reg, signf_(v.x), 0.f), fmaf(reg, signf_(v.y), 0.f), fmaf(reg, signf_(v.z), 0.f),
                                              fmaf(reg, signf_(v.w), 0.f));
                     }
@@ -185,20 +189,33 @@ k_idwt_clean_bwd(const float* __restrict__ yh, float* __restrict__ g_x, float* _
             }
         }
     }
+    if (abs_sum != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) red[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float w = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+            if (threadIdx.x == 0 && w != 0.f) atomicAdd(abs_sum, w);
+        }
+    }
 }
 
 template <typename Cfg>
 static int launch_fwd_sparse(const float* x, const float* yh, float* out, uint32_t n, uint32_t C, float* abs_sum, const int32_t* active,
-                             const int32_t* clean, const int32_t* counts, uint32_t max_active, uint32_t max_clean, cudaStream_t stream) {
+                             const int32_t* clean, const int32_t* counts, uint32_t max_active, uint32_t max_clean, uint32_t parts,
+                             cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_idwt_fwd<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_F);
         attr_set = true;
     }
-    if (max_active > 0)
+    if (max_active > 0 && (parts & 1u))
         k_idwt_fwd<Cfg><<<max_active * (C / Cfg::CG), Cfg::NT, Cfg::SMEM_F, stream>>>(x, yh, out, (int)n, (int)C, 0, abs_sum,
                                                                                      reinterpret_cast<const int4*>(active), counts);
-    if (abs_sum != nullptr && max_clean > 0)
+    if (abs_sum != nullptr && max_clean > 0 && (parts & 2u))
         k_idwt_clean_fwd<<<min(max_clean, (uint32_t)kNumSM * 8u), 256, 0, stream>>>(yh, (int)n, (int)C, reinterpret_cast<const int4*>(clean),
                                                                                    counts + 1, abs_sum);
     return finish_launch("idwt_level_forward_sparse");
@@ -207,7 +224,7 @@ static int launch_fwd_sparse(const float* x, const float* yh, float* out, uint32
 template <typename Cfg>
 static int launch_bwd_sparse(const float* g, float* g_x, float* g_yh, uint32_t n, uint32_t C, const float* yh, const float* reg_grad,
                              float reg_coef, const int32_t* active, const int32_t* clean, const int32_t* counts, uint32_t max_active,
-                             uint32_t max_clean, uint32_t parts, cudaStream_t stream) {
+                             uint32_t max_clean, uint32_t parts, float* abs_sum, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(k_idwt_bwd<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_B);
@@ -219,7 +236,7 @@ static int launch_bwd_sparse(const float* g, float* g_x, float* g_yh, uint32_t n
     if (max_clean > 0 && (parts & 2u))
         k_idwt_clean_bwd<<<min(max_clean, (uint32_t)kNumSM * 8u), 256, 0, stream>>>(yh, g_x, g_yh, (int)n, (int)C,
                                                                                    reinterpret_cast<const int4*>(clean), counts + 1, reg_grad,
-                                                                                   reg_coef);
+                                                                                   reg_coef, abs_sum);
     return finish_launch("idwt_level_backward_sparse");
 }
 
@@ -286,29 +303,31 @@ int tnl_idwt_level_backward(const float* g_out, float* g_x, float* g_yh, uint32_
 
 int tnl_idwt_level_forward_sparse(const float* x, const float* yh, float* out, uint32_t n, uint32_t C, float* abs_sum,
                                   const int32_t* active, const int32_t* clean, const int32_t* counts, uint32_t max_active,
-                                  uint32_t max_clean, tnl_stream_t stream) {
+                                  uint32_t max_clean, uint32_t parts, tnl_stream_t stream) {
     TNL_ARG_CHECK(x && yh && out && counts, "null pointer");
+    TNL_ARG_CHECK(parts >= 1 && parts <= 3, "parts: bit 0 = active blocks, bit 1 = |yh| sum of the clean blocks");
     TNL_ARG_CHECK((max_active == 0 || active) && (max_clean == 0 || clean), "null work list");
     TNL_ARG_CHECK(n >= 16 && n % 16 == 0 && n <= 16384, "work-list mode: n must be a multiple of 16 in [16, 16384]");
     TNL_ARG_CHECK(C >= 8 && C % 8 == 0, "C must be a multiple of 8");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (C % 24 == 0) return launch_fwd_sparse<IdwtCfg<24, 32>>(x, yh, out, n, C, abs_sum, active, clean, counts, max_active, max_clean, s);
-    if (C % 16 == 0) return launch_fwd_sparse<IdwtCfg<16, 32>>(x, yh, out, n, C, abs_sum, active, clean, counts, max_active, max_clean, s);
-    return launch_fwd_sparse<IdwtCfg<8, 32>>(x, yh, out, n, C, abs_sum, active, clean, counts, max_active, max_clean, s);
+    if (C % 24 == 0) return launch_fwd_sparse<IdwtCfg<24, 32>>(x, yh, out, n, C, abs_sum, active, clean, counts, max_active, max_clean, parts, s);
+    if (C % 16 == 0) return launch_fwd_sparse<IdwtCfg<16, 32>>(x, yh, out, n, C, abs_sum, active, clean, counts, max_active, max_clean, parts, s);
+    return launch_fwd_sparse<IdwtCfg<8, 32>>(x, yh, out, n, C, abs_sum, active, clean, counts, max_active, max_clean, parts, s);
 }
 
 int tnl_idwt_level_backward_sparse(const float* g_out, float* g_x, float* g_yh, uint32_t n, uint32_t C, const float* yh,
                                    const float* reg_grad, float reg_coef, const int32_t* active, const int32_t* clean,
-                                   const int32_t* counts, uint32_t max_active, uint32_t max_clean, uint32_t parts, tnl_stream_t stream) {
+                                   const int32_t* counts, uint32_t max_active, uint32_t max_clean, uint32_t parts, float* abs_sum,
+                                   tnl_stream_t stream) {
     TNL_ARG_CHECK((g_out || !(parts & 1u)) && g_x && g_yh && counts, "null pointer");
     TNL_ARG_CHECK(parts >= 1 && parts <= 3, "parts: bit 0 = active blocks, bit 1 = clean blocks");
     TNL_ARG_CHECK((max_active == 0 || active) && (max_clean == 0 || clean), "null work list");
     TNL_ARG_CHECK(n >= 16 && n % 16 == 0 && n <= 16384, "work-list mode: n must be a multiple of 16 in [16, 16384]");
     TNL_ARG_CHECK(C >= 8 && C % 8 == 0, "C must be a multiple of 8");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (C % 24 == 0) return launch_bwd_sparse<IdwtCfg<24, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, active, clean, counts, max_active, max_clean, parts, s);
-    if (C % 16 == 0) return launch_bwd_sparse<IdwtCfg<16, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, active, clean, counts, max_active, max_clean, parts, s);
-    return launch_bwd_sparse<IdwtCfg<8, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, active, clean, counts, max_active, max_clean, parts, s);
+    if (C % 24 == 0) return launch_bwd_sparse<IdwtCfg<24, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, active, clean, counts, max_active, max_clean, parts, abs_sum, s);
+    if (C % 16 == 0) return launch_bwd_sparse<IdwtCfg<16, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, active, clean, counts, max_active, max_clean, parts, abs_sum, s);
+    return launch_bwd_sparse<IdwtCfg<8, 32>>(g_out, g_x, g_yh, n, C, yh, reg_grad, reg_coef, active, clean, counts, max_active, max_clean, parts, abs_sum, s);
 }
 
 }  // extern "C"

@@ -92,6 +92,23 @@ k_tiles_copy(float* __restrict__ planes, void* __restrict__ compact, const int32
     }
 }
 
+// zero the listed tiles of planes [3][R][R][C]; the list length is read on the device (grid sized by its capacity)
+__global__ void __launch_bounds__(256)
+k_tiles_zero(float* __restrict__ planes, const int32_t* __restrict__ tile_ids, const int32_t* __restrict__ count, int R, int C, int T) {
+    const int tile = blockIdx.x;
+    if (tile >= __ldg(count)) return;
+    const int id = __ldg(tile_ids + tile);
+    const int nt = R / T;
+    const int p = id / (nt * nt), ty = (id / nt) % nt, tx = id % nt;
+    const int n4 = T * C / 4;
+    const int rows_per_cta = (T + gridDim.y - 1) / gridDim.y;
+    const int row_end = min(T, (int)(blockIdx.y + 1) * rows_per_cta);
+    for (int row = blockIdx.y * rows_per_cta; row < row_end; ++row) {
+        float4* dst = reinterpret_cast<float4*>(planes + (((size_t)p * R + (size_t)ty * T + row) * R + (size_t)tx * T) * C);
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
 }  // namespace tnl
 
 using namespace tnl;
@@ -108,6 +125,15 @@ int tnl_mark_dirty_tiles(const uint8_t* bitfield, uint32_t cascade, uint32_t H, 
     const uint32_t n = cascade * H * H * H;
     k_mark_dirty_tiles<<<ceil_div(n, 256u), 256, 0, s>>>(bitfield, cascade, H, bound, (int)R, (int)T, (int)margin, flags);
     return finish_launch("mark_dirty_tiles");
+}
+
+int tnl_tiles_zero(float* planes, const int32_t* tile_ids, const int32_t* count, uint32_t capacity, uint32_t R, uint32_t C, uint32_t T,
+                   tnl_stream_t stream) {
+    if (capacity == 0) return 0;
+    TNL_ARG_CHECK(planes && tile_ids && count, "null pointer");
+    TNL_ARG_CHECK(R % T == 0 && (T * C) % 4 == 0, "bad tile geometry");
+    k_tiles_zero<<<dim3(capacity, 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(planes, tile_ids, count, (int)R, (int)C, (int)T);
+    return finish_launch("tiles_zero");
 }
 
 int tnl_tiles_pack(const float* planes, const int32_t* tile_ids, uint32_t n_tiles, uint32_t R, uint32_t C, uint32_t T,

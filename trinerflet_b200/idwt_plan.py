@@ -86,7 +86,13 @@ class IdwtPlan:
         self.version = 0          # bumped whenever a list buffer is reallocated (captured CUDA graphs must be rebuilt)
         self.fwd = [None] * levels   # per level: dict(active, clean, counts, cap_active, cap_clean)
         self.bwd = [None] * levels
+        self.gap = [None] * levels
         self.stats = {}
+        # set by the training step when it drives the backward itself (SplitIdwtBackward): the forward then skips the
+        # |yh| pass over the clean blocks and the backward's clean part, which reads those coefficients anyway, adds it
+        self.defer_clean_abs = False
+        self.on_planes_ready = None   # called once, right after the last active forward level has been issued
+        self.zero = None              # tiles of the plane-gradient buffer the backward reads: dict(ids, count, cap)
 
     def _store(self, slot_list, l, active, clean):
         slot = slot_list[l]
@@ -115,10 +121,29 @@ class IdwtPlan:
             mf, mb = fwd_maps[l].cpu().numpy(), bwd_maps[l].cpu().numpy()
             self._store(self.fwd, l, _items(mf, True, MAX_ACTIVE_RUN), _items(mf, False, MAX_CLEAN_RUN))
             self._store(self.bwd, l, _items(mb, True, MAX_ACTIVE_RUN), _items(mb, False, MAX_CLEAN_RUN))
+            # blocks the backward treats as active but the forward does not reconstruct: with defer_clean_abs their |yh| is
+            # counted neither by the forward's active blocks nor by the backward's clean part -> a (small) list of their own
+            self._store(self.gap, l, np.zeros((0, 4), dtype=np.int32), _items(mb & ~mf, True, MAX_CLEAN_RUN))
             frac_f.append(float(mf.mean()))
             frac_b.append(float(mb.mean()))
-        self.stats = dict(active_fraction_forward=frac_f, active_fraction_backward=frac_b, tile_fraction=float(f.float().mean()))
+        # the backward's active top-level blocks read the incoming gradient on their 8-pixel halo: tiles k-1 .. k+1
+        z = F.max_pool2d(bwd_maps[-1][None].float(), kernel_size=3, stride=1, padding=1)[0] > 0
+        ids = torch.nonzero(z.reshape(-1)).squeeze(-1).int()
+        if self.zero is None or ids.numel() > self.zero["cap"]:
+            cap = max(64, 2 * ids.numel())
+            self.zero = dict(ids=torch.zeros(cap, dtype=torch.int32, device=self.device),
+                             count=torch.zeros(1, dtype=torch.int32, device=self.device), cap=cap)
+            self.version += 1
+        self.zero["ids"][:ids.numel()].copy_(ids)
+        self.zero["count"].fill_(int(ids.numel()))
+        self.stats = dict(active_fraction_forward=frac_f, active_fraction_backward=frac_b, tile_fraction=float(f.float().mean()),
+                          zero_fill_fraction=float(z.float().mean()))
         return self
+
+    def zero_gradient_tiles(self, g_planes_dense):
+        """Zero the tiles of a (channels-last, dense-storage) plane-gradient buffer that the work-list backward reads."""
+        call("tnl_tiles_zero", ptr(g_planes_dense), ptr(self.zero["ids"]), ptr(self.zero["count"]), self.zero["cap"], self.R, self.C,
+             TILE, stream())
 
     @staticmethod
     def from_model(model, margin=2, plan=None):
@@ -136,14 +161,23 @@ class IdwtPlan:
         return plan.update(flags)
 
     # ---- per-level launches ------------------------------------------------------------------------------------------
-    def forward_level(self, l, x, yh, out, n, abs_sum):
+    def forward_level(self, l, x, yh, out, n, abs_sum, parts=3):
+        """parts: 1 = reconstruct the active blocks, 2 = |yh| sum of the clean blocks, 3 = both."""
         s = self.fwd[l]
         call("tnl_idwt_level_forward_sparse", ptr(x), ptr(yh), ptr(out), n, self.C, ptr(abs_sum), ptr(s["active"]), ptr(s["clean"]),
-             ptr(s["counts"]), s["cap_active"], s["cap_clean"], stream())
+             ptr(s["counts"]), s["cap_active"], s["cap_clean"], int(parts), stream())
 
-    def backward_level(self, l, g, g_x, g_yh, n, yh, reg_grad, reg_coef, parts=3):
-        """parts: 1 = active blocks only, 2 = clean blocks only (independent of g), 3 = both."""
+    def forward_gap_abs(self, l, yh, n, abs_sum):
+        """abs_sum += sum |yh| over the blocks that are active in the backward but not reconstructed by the forward."""
+        s = self.gap[l]
+        call("tnl_idwt_level_forward_sparse", ptr(yh), ptr(yh), ptr(yh), n, self.C, ptr(abs_sum), ptr(s["active"]), ptr(s["clean"]),
+             ptr(s["counts"]), 0, s["cap_clean"], 2, stream())
+
+    def backward_level(self, l, g, g_x, g_yh, n, yh, reg_grad, reg_coef, parts=3, abs_sum=None):
+        """parts: 1 = active blocks only, 2 = clean blocks only (independent of g), 3 = both.
+        abs_sum: the clean part adds sum |yh| of its blocks (see defer_clean_abs)."""
         s = self.bwd[l]
         call("tnl_idwt_level_backward_sparse", ptr(g) if g is not None else None, ptr(g_x), ptr(g_yh), n, self.C,
              ptr(yh) if yh is not None else None, ptr(reg_grad) if reg_grad is not None else None, float(reg_coef), ptr(s["active"]),
-             ptr(s["clean"]), ptr(s["counts"]), s["cap_active"], s["cap_clean"], int(parts), stream())
+             ptr(s["clean"]), ptr(s["counts"]), s["cap_active"], s["cap_clean"], int(parts),
+             ptr(abs_sum) if abs_sum is not None else None, stream())

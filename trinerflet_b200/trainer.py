@@ -86,18 +86,25 @@ class TrainStep:
                 self.refresh_plan()
             enc.idwt_plan = self._plan
         prefetch = self.prefetch_planes and not do_update and rays_o.is_cuda
+        # work-list steps drive the IDWT backward themselves (two parts, see SplitIdwtBackward); its gradient-independent
+        # part goes to the prefetch stream right away and overlaps the render
+        will_split = use_plan and not self.pipelined_tail and all(p.grad is None for p in enc.parameters())
+        # (debug mode of the exchange sums the whole gradient buffer, so it needs all of it defined)
+        partial_zero = will_split and not (self.reducer is not None and self.reducer.check)
+        if use_plan:
+            self._plan.defer_clean_abs = will_split
         if prefetch:
             if self._side is None:
                 self._side = torch.cuda.Stream()
-            planes = enc.prefetch_planes(self._side)
+            planes = enc.prefetch_planes(self._side, partial_zero=partial_zero)
         else:
             planes = enc.get_planes()
         enc.idwt_plan = None   # the cached planes of this step are built; anything reconstructed later is dense again
-        # work-list steps drive the IDWT backward themselves (two parts, see SplitIdwtBackward); its gradient-independent
-        # part goes to the prefetch stream right away and overlaps the render
+        abs_sums = enc._last_abs_sums
         self._split = None
-        if use_plan and all(p.grad is None for p in enc.parameters()):
+        if will_split:
             self._split = self._make_split(enc, opt)
+            self._split.abs_sums = abs_sums          # completed by the clean part (the forward skipped those blocks)
             if prefetch and self._split.reg_ready:
                 with torch.cuda.stream(self._side):
                     self._split.run_clean()
@@ -125,22 +132,34 @@ class TrainStep:
             # cut the graph at the planes: render backward -> plane gradient; (N > 1: exchange its dirty tiles;) IDWT backward
             leaf = planes.detach().requires_grad_(True)
             enc.last_used_planes = leaf
+            lam = opt.wavelet_regularization
+            have_reg = lam > 0 and len(enc.get_wavelet_features()) > 0
             with torch.autocast("cuda", dtype=torch.float16, enabled=opt.fp16):
                 loss = self._render_loss(rays_o, rays_d, images)
                 enc._join_prefetch()
-                reg = wavelet_regulariser(enc, opt.wavelet_regularization, True)
+                # the autograd fall-back needs the regulariser as a graph node now; the split backward applies its gradient
+                # itself and completes the |yh| sums in its clean part, so there the value is formed at the end
+                reg = wavelet_regulariser(enc, lam, True) if (self._split is None and have_reg) else None
                 enc.reset_cahce()
                 self.scaler.scale(loss).backward()                    # -> leaf.grad and the MLP gradients of this shard
             self._cut = (planes, leaf, reg)
             if self.reducer is None:
+                split = self._split
                 self._idwt_backward()
+                if split is not None and have_reg:
+                    reg = enc.wavelet_l1(lam, abs_sums)
                 self._cut = None
                 self._split = None
                 if self.world_size > 1 and not capturing:
                     parallel.allreduce_gradients(model, self.world_size)
             else:
+                if self._split is not None and not self._split.clean_done:   # first step of a run (no loss scale yet)
+                    self._split.reg_scale = self.scaler._scale if self.scaler.is_enabled() else self._split.reg_scale
+                    self._split.run_clean()
                 if prefetch:   # the early part of the IDWT backward belongs to this segment of the step (graph A)
                     torch.cuda.current_stream().wait_stream(self._side)
+                if self._split is not None and have_reg:
+                    reg = enc.wavelet_l1(lam, abs_sums)
                 if not capturing:
                     self._exchange_and_finish()
             loss = loss.detach() + (reg.detach() if reg is not None else 0.0)

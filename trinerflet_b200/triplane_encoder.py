@@ -115,8 +115,19 @@ class _BuildPlanes(Function):
             if plan is None:
                 call("tnl_idwt_level_forward", ptr(x), ptr(yh), ptr(out), n, C, ptr(abs_sums[l:l + 1]), stream())
             else:
-                plan.forward_level(l, x, yh, out, n, abs_sums[l:l + 1])
+                plan.forward_level(l, x, yh, out, n, abs_sums[l:l + 1], parts=1)
             x, n = out, 2 * n
+        if plan is not None:
+            if plan.on_planes_ready is not None and plan.defer_clean_abs:
+                plan.on_planes_ready()               # the planes are complete and nothing else of this call is awaited
+            plan.on_planes_ready = None
+            n = ctx.n0
+            for l, yh in enumerate(saved):           # |yh| of the blocks that were not reconstructed (regulariser value)
+                if plan.defer_clean_abs:             # ... except those the backward's clean part will read anyway
+                    plan.forward_gap_abs(l, yh, n, abs_sums[l:l + 1])
+                else:
+                    plan.forward_level(l, saved[l], yh, saved[l], n, abs_sums[l:l + 1], parts=2)   # x / out are not touched
+                n *= 2
         ctx.save_for_backward(*saved)
         return x, abs_sums
 
@@ -193,6 +204,7 @@ class SplitIdwtBackward:
         self.C, self.levels = encoder.number_of_features, len(encoder.planes_features_wavelet_coefs)
         self.n0 = encoder.planes_features.shape[2]
         self.reg_scale, self.reg_coef = reg_scale, float(reg_coef)
+        self.abs_sums = None   # [L] tensor the clean part completes with sum |yh| of its blocks (plan.defer_clean_abs)
         dev = encoder.planes_features.device
         self.g_x = [cl_empty_planes(self.C, self.n0 * 2 ** l, device=dev) for l in range(self.levels)]
         self.g_yh = [cl_empty_coefs(self.C, self.n0 * 2 ** l, device=dev) for l in range(self.levels)]
@@ -200,8 +212,9 @@ class SplitIdwtBackward:
     def _level(self, l, g, parts):
         use_reg = self.reg_scale is not None and self.reg_coef != 0.0
         yh = self.enc.planes_features_wavelet_coefs[l].detach()
+        abs_sum = self.abs_sums[l:l + 1] if (self.abs_sums is not None and (parts & 2)) else None
         self.plan.backward_level(l, g, self.g_x[l], self.g_yh[l], self.n0 * 2 ** l, yh if use_reg else None,
-                                 self.reg_scale if use_reg else None, self.reg_coef, parts)
+                                 self.reg_scale if use_reg else None, self.reg_coef, parts, abs_sum)
 
     def run_clean(self):
         for l in range(self.levels):
@@ -406,20 +419,30 @@ class TriPlaneVolume(nn.Module):
 
     reset_cache = reset_cahce
 
-    def prefetch_planes(self, side):
+    def prefetch_planes(self, side, partial_zero=False):
         """Reconstruct the planes on stream `side` while the caller's stream goes on with work that does not need them
         (ray marching, the cell sort); the first sampling call waits for them.  Also zero-fills the plane-gradient buffer
         of this step's sampling backward there.  Same result as get_planes(); the autograd node of the reconstruction
         runs its backward on `side` too (torch's stream-aware engine orders it after the sampling backward)."""
         main = torch.cuda.current_stream()
         side.wait_stream(main)
+        plan = self.idwt_plan
         with torch.cuda.stream(side):
-            planes = self.get_planes()
             ready = torch.cuda.Event()
-            ready.record(side)
+            fired = []
+            if plan is not None:
+                plan.on_planes_ready = lambda: (ready.record(side), fired.append(1))
+            planes = self.get_planes()
+            if not fired:
+                ready.record(side)
             gbuf = None
             if torch.is_grad_enabled() and planes.requires_grad:
-                gbuf = cl_empty_planes(self.number_of_features, self.plane_resolution, device=planes.device, zero=True)
+                if plan is not None and partial_zero:
+                    # the work-list backward only reads the tiles around the occupied ones: zero those, leave the rest undefined
+                    gbuf = cl_empty_planes(self.number_of_features, self.plane_resolution, device=planes.device)
+                    plan.zero_gradient_tiles(gbuf.permute(0, 2, 3, 1))
+                else:
+                    gbuf = cl_empty_planes(self.number_of_features, self.plane_resolution, device=planes.device, zero=True)
                 gready = torch.cuda.Event()
                 gready.record(side)
                 gbuf = (gbuf, gready)
@@ -454,18 +477,21 @@ class TriPlaneVolume(nn.Module):
         self.last_used_planes = planes
         return planes
 
-    def wavelet_l1(self, lam):
-        self._join_prefetch()
+    def wavelet_l1(self, lam, abs_sums=None):
         """lam * (sum_l mean|yh_l| * numel_l / numel_all) / L -- the regulariser of nerf/utils.py:640-655 (unweighted
         branch), taken from the |yh| sums the plane reconstruction produced; its gradient is applied inside the IDWT
-        backward kernels (no extra pass over the coefficients).  Call after get_planes() of the same step."""
+        backward kernels (no extra pass over the coefficients).  Call after get_planes() of the same step, or pass the
+        |yh| sums of that reconstruction."""
+        self._join_prefetch()
         feats = self.get_wavelet_features()
         if len(feats) == 0:
             return None
-        if self.last_used_planes is None or getattr(self, "_last_abs_sums", None) is None:
-            self.get_planes()
+        if abs_sums is None:
+            if self.last_used_planes is None or getattr(self, "_last_abs_sums", None) is None:
+                self.get_planes()
+            abs_sums = self._last_abs_sums
         total = sum(v.numel() for v in feats)
-        return lam * self._last_abs_sums.sum() / (total * len(feats))
+        return lam * abs_sums.sum() / (total * len(feats))
 
     def sample_from_planes(self, coordinates, plane_features=None, lbound=None, n_valid=None):
         if plane_features is None:
