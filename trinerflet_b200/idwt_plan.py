@@ -111,6 +111,17 @@ class IdwtPlan:
         slot["counts"].copy_(torch.tensor([active.shape[0], clean.shape[0]], dtype=torch.int32))
         slot["n_active"], slot["n_clean"] = int(active.shape[0]), int(clean.shape[0])
 
+    def _active_items(self, block_map, target_ctas=4 * 148):
+        """Runs of active blocks, as long as possible (halo overhead 8 rows per item) but short enough that the coarse
+        levels, which have few blocks, still spread over the machine (a CTA streams its rows sequentially)."""
+        chunks = max(1, self.C // 16)
+        run = MAX_ACTIVE_RUN
+        items = _items(block_map, True, run)
+        while run > 1 and items.shape[0] * chunks < target_ctas:
+            run -= 1
+            items = _items(block_map, True, run)
+        return items
+
     def update(self, flags):
         """flags: uint8/bool [3 * T * T] or [3, T, T] device tensor from tnl_mark_dirty_tiles (T = R / 32)."""
         T = self.R // TILE
@@ -119,8 +130,8 @@ class IdwtPlan:
         frac_f, frac_b = [], []
         for l in range(self.levels):
             mf, mb = fwd_maps[l].cpu().numpy(), bwd_maps[l].cpu().numpy()
-            self._store(self.fwd, l, _items(mf, True, MAX_ACTIVE_RUN), _items(mf, False, MAX_CLEAN_RUN))
-            self._store(self.bwd, l, _items(mb, True, MAX_ACTIVE_RUN), _items(mb, False, MAX_CLEAN_RUN))
+            self._store(self.fwd, l, self._active_items(mf), _items(mf, False, MAX_CLEAN_RUN))
+            self._store(self.bwd, l, self._active_items(mb), _items(mb, False, MAX_CLEAN_RUN))
             # blocks the backward treats as active but the forward does not reconstruct: with defer_clean_abs their |yh| is
             # counted neither by the forward's active blocks nor by the backward's clean part -> a (small) list of their own
             self._store(self.gap, l, np.zeros((0, 4), dtype=np.int32), _items(mb & ~mf, True, MAX_CLEAN_RUN))
