@@ -143,20 +143,23 @@ def algorithmic_bytes(name, meta, C, m_valid, plan=None):
         n, c = meta[0], meta[1]
         lvl = int(round(math.log2(n / plan.n0)))
         px = 3 * c * n * n * 4
-        if name.endswith("forward_sparse"):
-            a = plan.stats["active_fraction_forward"][lvl]
-            return px * (a * (4 + 4) + (1 - a) * 3)
+        a = plan.stats["active_fraction_forward"][lvl]
         b = plan.stats["active_fraction_backward"][lvl]
         parts = int(meta[-1])            # bit 0: active blocks, bit 1: clean blocks (they may be separate calls)
+        if name.endswith("forward_sparse"):
+            # the |yh| pass covers all non-reconstructed blocks, or (regulariser value completed by the backward's clean
+            # part, plan.defer_clean_abs) only those the backward treats as active
+            clean = (b - a) if plan.defer_clean_abs else (1 - a)
+            return px * (((parts & 1) and a * (4 + 4)) + ((parts & 2) and clean * 3))
         return px * (((parts & 1) and b * (4 + 3 + 4)) + ((parts & 2) and (1 - b) * (3 + 4)))
     if name == "tnl_sample_planes_forward":
         return m_valid * (12 + g)
     if name == "tnl_sample_planes_backward":
         return m_valid * 2 * g
     if name == "tnl_mlp_forward":
-        return m_valid * 28
+        return m_valid * (2 * 3 * C + 28)            # fp16 feature row + dirs in, sigma + rgb out
     if name == "tnl_mlp_backward":
-        return m_valid * 16
+        return m_valid * (2 * 2 * 3 * C + 28)        # feature row in, feature-gradient row out (fp16), dirs, g_sigma, g_rgb
     if name == "tnl_composite_rays_train_forward":
         return m_valid * 24 + meta[1] * 32
     if name == "tnl_composite_rays_train_backward":
@@ -371,8 +374,19 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         dom = max((k for k in kernels if kernels[k]["achieved_GBps"]), key=lambda k: kernels[k]["ms_per_step"])
+        # DRAM bytes of the dominant kernel measured by ncu (dram__bytes_read.sum + dram__bytes_write.sum, one --set full
+        # capture of a base-light step, summarised under profiles/), per launch like `achieved`
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+            if tr and args.config == tr.get("config"):
+                traffic = round(tr["dram_bytes_per_step"] / kernels[dom]["calls_per_step"] / 1e9, 4)
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_GBps"], "peak": peak, "unit": "GB/s",
-                    "frac": round(kernels[dom]["achieved_GBps"] / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "frac": round(kernels[dom]["achieved_GBps"] / peak, 4), "traffic": traffic, "traffic_unit": "GB/launch",
+                    "algorithmic_GB_per_launch": round(kernels[dom]["algorithmic_GB_per_step"] / kernels[dom]["calls_per_step"], 4),
+                    "peak_source": peak_src,
                     "launch_ms": round(kernels[dom]["ms_per_step"] / kernels[dom]["calls_per_step"], 4)}
         # B_step: what the reference's (dense) data flow has to move per step; the work-list IDWT moves less
         # plane data than that, so this fraction is "dense-equivalent" throughput, not DRAM utilisation
