@@ -108,7 +108,9 @@ def check(rc, what):
 
 
 # number of kernels each ABI call launches (for the launch counter the benchmark reports)
-KERNELS_PER_CALL = {"tnl_march_rays_train": 5, "tnl_compact_alive": 3, "tnl_cell_sort": 5}
+KERNELS_PER_CALL = {"tnl_march_rays_train": 5, "tnl_compact_alive": 3, "tnl_cell_sort": 5, "tnl_mlp_pack_weights": 2}
+# work-list IDWT calls launch one kernel per requested part (position of the `parts` argument from the end)
+_PARTS_ARG = {"tnl_idwt_level_forward_sparse": -2, "tnl_idwt_level_backward_sparse": -3}
 launch_count = 0
 _profile = None  # when enabled: name -> list of (start_event, end_event, scalar_args)
 
@@ -133,7 +135,10 @@ def profile_stop():
 def call(name, *args):
     global launch_count
     fn = getattr(load(), name)
-    launch_count += KERNELS_PER_CALL.get(name, 1)
+    if name in _PARTS_ARG:
+        launch_count += bin(int(args[_PARTS_ARG[name]]) & 3).count("1")
+    else:
+        launch_count += KERNELS_PER_CALL.get(name, 1)
     if _profile is None:
         check(fn(*args), name)
         return
