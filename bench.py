@@ -408,6 +408,18 @@ def main():
             torch.cuda.synchronize()
             extras["ms_per_step_with_optimizer"] = round((time.perf_counter() - t0) / 3 * 1e3, 3)
             del optim, ts2
+            torch.cuda.empty_cache()
+            # the same with the fused epilogue (trinerflet_b200/optim.py: unscale + check + Adam + scale update, 2 kernels)
+            optim = trainer.make_optimizer(net, 1e-2, fused=True)
+            ts2 = trainer.TrainStep(net, opt, optimizer=optim, world_size=1)
+            ts2.step(*devb[0], update_grid=False)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(3):
+                ts2.step(*devb[i], update_grid=False)
+            torch.cuda.synchronize()
+            extras["ms_per_step_with_fused_optimizer"] = round((time.perf_counter() - t0) / 3 * 1e3, 3)
+            del optim, ts2
         except Exception as ex:  # pragma: no cover
             extras["ms_per_step_with_optimizer"] = f"failed: {ex}"
         cpu = None

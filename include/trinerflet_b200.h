@@ -210,6 +210,20 @@ int tnl_umma_bench2(uint32_t a_lbo, uint32_t a_sbo, uint32_t a_step, uint32_t a_
  * [20..39] issuer wait (stage*2+wg), [40..59] issuer issue); NULL switches it off (default). */
 int tnl_mlp_tc_profile(unsigned long long* counters64);
 
+/* ------------------------------------------------------------------ optimizer epilogue -------- */
+/* `scaler.step(optimizer); scaler.update()` of the reference loop (reconstruction/nerf/utils.py:1170-1173) with
+ * torch.optim.Adam(betas, eps) (reconstruction/main_nerf.py:119), over flat fp32 arrays (any memory order, the same for
+ * p / g / m / v).  All scalars that depend on earlier kernels stay on the device, so the epilogue needs no host sync.
+ *   tnl_grad_nonfinite : *found_inf = 1 if any element of g is inf / NaN (caller zero-fills found_inf once per step)
+ *   tnl_adam_prepare   : state3 = {step, 1 - beta1^step, sqrt(1 - beta2^step)}; step += 1 unless *found_inf != 0
+ *   tnl_adam_step      : unless *found_inf != 0:  g' = g * (*inv_scale) (+ weight_decay * p);  m += (g' - m)(1 - beta1);
+ *                        v = beta2 v + (1 - beta2) g'^2;  p -= lr / state3[1] * m / (sqrt(v) / state3[2] + eps)
+ * inv_scale / found_inf may be NULL (no loss scaling). */
+int tnl_grad_nonfinite(const float* g, uint64_t n, float* found_inf, tnl_stream_t stream);
+int tnl_adam_prepare(float* state3, const float* found_inf, float beta1, float beta2, tnl_stream_t stream);
+int tnl_adam_step(float* p, const float* g, float* m, float* v, uint64_t n, const float* inv_scale, const float* found_inf,
+                  const float* state3, float lr, float beta1, float beta2, float eps, float weight_decay, tnl_stream_t stream);
+
 /* ------------------------------------------------------------------ density grid ------------- */
 /* Fused pieces of NeRFRenderer.update_extra_state (reconstruction/nerf/renderer.py:448-542). */
 /* cell-centre sample positions for a list of Morton cells of one cascade (renderer.py:474-483):

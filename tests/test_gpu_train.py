@@ -156,3 +156,38 @@ def test_worklist_idwt_training_step_equals_dense():
     assert abs(out[0][0] - out[1][0]) <= 1e-6 * abs(out[0][0])
     for a, b in zip(out[0][1], out[1][1]):
         assert rel_l2(a, b) <= 1e-6       # the scatter's float atomics are the only run-to-run freedom
+
+
+def test_fused_adam_matches_gradscaler_plus_torch_adam():
+    """trinerflet_b200.optim.FusedAdam (unscale + non-finite check + Adam + loss-scale update in two streaming kernels) vs
+    the reference's scaler.step(torch.optim.Adam) / scaler.update() (nerf/utils.py:1170-1173, main_nerf.py:119)."""
+    from trinerflet_b200 import scene, trainer
+    sc = scene.make_scene()
+    g = torch.Generator().manual_seed(7)
+    batches = [tuple(t.cuda() for t in scene.sample_batch(sc, 2048, g)) for _ in range(4)]
+    runs = []
+    for fused in (False, True):
+        net = _model("tiny")
+        ts = trainer.TrainStep(net, trainer.default_opt(), trainer.make_optimizer(net, 1e-2, fused=fused), world_size=1)
+        for i, b in enumerate(batches):
+            torch.manual_seed(i)
+            ts.step(*b, update_grid=False)
+        runs.append((net, ts))
+    (net_a, ts_a), (net_b, ts_b) = runs
+    for (na, pa), (nb, pb) in zip(net_a.named_parameters(), net_b.named_parameters()):
+        # (float atomics in the gradient scatter reorder sums from run to run, and with eps = 1e-15 the first Adam steps are
+        # ~lr * sign(g): a single near-zero gradient of either sign already costs 1e-4 here; an arithmetic error costs > 1e-2)
+        assert rel_l2(pb, pa) <= 1e-3, (na, rel_l2(pb, pa))
+    assert float(ts_a.scaler.get_scale()) == float(ts_b.scaler._scale)
+    # a non-finite gradient: parameters untouched, loss scale halved, step count not advanced
+    before = [p.detach().clone() for p in net_b.parameters()]
+    scale0 = float(ts_b.scaler._scale)
+    step0 = float(ts_b.optimizer.param_groups[0]["_tnl_state"][0])
+    net_b.zero_grad(set_to_none=True)
+    ts_b.forward_backward(*batches[0], update_grid=False)
+    net_b.sigma_net[0].weight.grad[0, 0] = float("inf")
+    ts_b.optimizer_step()
+    for p, q in zip(net_b.parameters(), before):
+        assert torch.equal(p, q)
+    assert float(ts_b.scaler._scale) == 0.5 * scale0
+    assert float(ts_b.optimizer.param_groups[0]["_tnl_state"][0]) == step0

@@ -103,3 +103,30 @@ def test_gradient_allreduce_and_gather_world2():
     out = mgr.dict()
     mp.spawn(_ddp_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+def test_fused_adam_arithmetic_matches_torch_adam():
+    """The update rule of csrc/optim.cu (k_adam_prepare + adam1), restated with torch ops, against torch.optim.Adam with
+    the reference's hyper-parameters (main_nerf.py:119) and GradScaler-style unscaling -- pins the formula without a GPU."""
+    import math
+    torch.manual_seed(0)
+    p_ref = torch.nn.Parameter(0.1 * torch.randn(257))
+    opt = torch.optim.Adam([p_ref], lr=1e-2, betas=(0.9, 0.99), eps=1e-15)
+    p = p_ref.detach().clone()
+    m, v, step = torch.zeros_like(p), torch.zeros_like(p), 0.0
+    b1, b2, lr, eps, scale = 0.9, 0.99, 1e-2, 1e-15, 65536.0
+    for it in range(5):
+        g_scaled = torch.randn(257) * scale * (0.0 if it == 2 else 1.0)      # one all-zero gradient step on the way
+        p_ref.grad = g_scaled / scale
+        opt.step()
+        step += 1.0                                                            # k_adam_prepare
+        bc1 = 1.0 - b1 ** step
+        bc2s = math.sqrt(1.0 - b2 ** step)
+        g = g_scaled * torch.tensor(1.0 / scale)                               # adam1
+        m = m + (g - m) * (1.0 - b1)
+        v = v * b2 + (1.0 - b2) * g * g
+        p = p - (lr / bc1) * (m / (v.sqrt() / bc2s + eps))
+        assert torch.allclose(p, p_ref.detach(), rtol=1e-5, atol=1e-8)
+    from trinerflet_b200.optim import _dense_storage
+    t = torch.zeros(3, 4, 4, 2).permute(0, 3, 1, 2)
+    assert _dense_storage(t) and not _dense_storage(t[:, :1]) and not _dense_storage(torch.zeros(4, 4)[:, ::2])

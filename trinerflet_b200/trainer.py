@@ -329,8 +329,12 @@ class TrainStep:
     def optimizer_step(self):
         if self.optimizer is None:
             return
-        self.scaler.step(self.optimizer)
-        self.scaler.update()
+        from .optim import FusedAdam
+        if isinstance(self.optimizer, FusedAdam):
+            self.optimizer.step(scaler=self.scaler)        # unscale + non-finite check + Adam + loss-scale update, fused
+        else:
+            self.scaler.step(self.optimizer)
+            self.scaler.update()
         self.optimizer.zero_grad(set_to_none=True)
 
     def step(self, rays_o, rays_d, images, update_grid=None):
@@ -340,6 +344,10 @@ class TrainStep:
         return loss
 
 
-def make_optimizer(model, lr=1e-2):
-    """main_nerf.py:119: Adam(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15)."""
+def make_optimizer(model, lr=1e-2, fused=False):
+    """main_nerf.py:119: Adam(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15).  fused=True: the same update as two
+    streaming kernels that also absorb GradScaler.step/update (trinerflet_b200/optim.py)."""
+    if fused:
+        from .optim import FusedAdam
+        return FusedAdam(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15)
     return torch.optim.Adam(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15)
