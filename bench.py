@@ -434,9 +434,10 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"{args.config}: C={C} R={R} wavelet_levels={S} ({int(round(__import__('math').log2(S)))} IDWT levels), "
                                    f"{n_rays} rays/GPU/step, synthetic 800x800 Blender-shaped scene, ball occupancy r=0.75, random-init",
-                       "rays_per_gpu": n_rays, "global_rays": n_rays * world, "parallelism": f"ray-sharded dp{world}, replicated coefficients, NCCL grad all-reduce",
-                       "timed_region": "get_planes (IDWT) + render + loss + backward (+ grad all-reduce); optimizer and density-grid refresh excluded (metric definition), see extras",
-                       "launch": "one CUDA-graph replay per step" if use_graph else "eager Python launches",
+                       "rays_per_gpu": n_rays, "global_rays": n_rays * world, "parallelism": (f"ray-sharded dp{world}, replicated coefficients; plane gradient exchanged as bf16 dirty tiles (NCCL all-reduce) "
+                                                       "between the render backward and the IDWT backward" if world > 1 else "single GPU"),
+                       "timed_region": "get_planes (work-list IDWT over the occupied tiles) + render + loss + backward (+ gradient exchange); optimizer and density-grid refresh excluded (metric definition), see extras",
+                       "launch": ("one CUDA-graph replay per step" if world == 1 else "two CUDA-graph replays per step around the NCCL exchange") if use_graph else "eager Python launches",
                        "l2": "inputs (1.6 GB of coefficients/planes per pass) exceed the 126 MB L2; a different ray batch every step"},
             "clocks": clk, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
