@@ -7,6 +7,11 @@
  *   pytorch_wavelets DWTInverse      (reconstruction/triplaneencoder/triplane_encoder.py:394)
  *   F.grid_sample                    (triplane_encoder.py:329)
  *   nn.Linear x5 / trunc_exp / sigmoid (reconstruction/nerf/network.py:118-147)
+ *   GradScaler.step/update + Adam    (reconstruction/nerf/utils.py:1170-1173, reconstruction/main_nerf.py:119)
+ * and a few entry points without a reference counterpart that the B200 design adds on the same path: the sample
+ * visit order (tnl_cell_sort), the tile set a training step can touch and its exchange between GPUs
+ * (tnl_mark_dirty_tiles, tnl_tiles_*), the work-list variants of the IDWT (tnl_idwt_level_*_sparse), and diagnostics
+ * that pin the tcgen05 conventions on hardware (tnl_umma_*).
  *
  * Conventions (all entry points):
  *   - plain device pointers + explicit element counts, no torch types; every output buffer is
