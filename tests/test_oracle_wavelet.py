@@ -62,3 +62,31 @@ def test_closed_form_and_adjoint():
     lhs = (y.detach() * gy).sum()
     rhs = (pf.detach() * pf.grad).sum() + (c0.detach() * c0.grad).sum() + (c1.detach() * c1.grad).sum()
     assert abs(lhs - rhs) < 1e-10 * abs(lhs)
+
+
+def test_bior68_taps_are_the_6_8_biorthogonal_pair():
+    """Known-answer anchor for the embedded filter constants (no PyWavelets here to compare against): 'bior6.8' means the
+    reconstruction low-pass has 6 zeros at z = -1 and the decomposition low-pass 8, i.e. the dual high-pass filters have
+    exactly 6 resp. 8 vanishing moments.  Together with perfect reconstruction (tested above) the product filter
+    rec_lo * dec_lo is then the unique order-14 max-flat half-band filter of length 27 -- a typo in any tap breaks this."""
+    import numpy as np
+    from oracle import wavelet as ow
+    k = np.arange(18, dtype=np.float64) - 8.5
+    rec_hi, dec_hi = np.array(ow.BIOR68_REC_HI, dtype=np.float64), np.array(ow.BIOR68_DEC_HI, dtype=np.float64)
+    rec_lo, dec_lo = np.array(ow.BIOR68_REC_LO, dtype=np.float64), np.array(ow.BIOR68_DEC_LO, dtype=np.float64)
+    for f, order in ((rec_hi, 8), (dec_hi, 6)):
+        scale = np.abs(f).sum()
+        for p in range(order):
+            assert abs((k ** p * f).sum()) <= 1e-8 * scale * 8.5 ** p
+        assert abs((k ** order * f).sum()) > 1.0            # ... and no more than that
+    # half-band property of the product filter: every second tap vanishes except the centre one (= 1)
+    prod = np.convolve(rec_lo, dec_lo)
+    centre = int(np.argmax(np.abs(prod)))
+    assert abs(prod[centre] - 1.0) <= 1e-12
+    others = prod[(np.arange(prod.size) - centre) % 2 == 0]
+    assert np.abs(others).sum() - abs(prod[centre]) <= 1e-12
+    assert np.count_nonzero(np.abs(prod) > 1e-15) <= 27
+    # symmetric filters (linear phase)
+    nz = lambda f: f[np.flatnonzero(f)[0]: np.flatnonzero(f)[-1] + 1]
+    assert np.allclose(nz(rec_lo), nz(rec_lo)[::-1]) and np.allclose(nz(dec_lo), nz(dec_lo)[::-1])
+    assert nz(rec_lo).size == 11 and nz(dec_lo).size == 17
