@@ -191,3 +191,42 @@ def test_fused_adam_matches_gradscaler_plus_torch_adam():
         assert torch.equal(p, q)
     assert float(ts_b.scaler._scale) == 0.5 * scale0
     assert float(ts_b.optimizer.param_groups[0]["_tnl_state"][0]) == step0
+
+
+def test_cuda_graph_replay_equals_eager_step():
+    """TrainStep.capture()/replay() (what bench.py times) against the same step launched eagerly: same loss, same
+    gradients; gradients stay attached across optimizer_step() + replay()."""
+    from trinerflet_b200 import scene, trainer
+    sc = scene.make_scene()
+    g = torch.Generator().manual_seed(11)
+    b = [tuple(t.cuda() for t in scene.sample_batch(sc, 4096, g)) for _ in range(3)]
+    out = []
+    for graph in (False, True):
+        net = _model("tiny")
+        ts = trainer.TrainStep(net, trainer.default_opt(), None, world_size=1)
+        torch.manual_seed(0)
+        ts.forward_backward(*b[0], update_grid=False)
+        net.mean_count = int(net.step_counter[0, 0].item())       # steady state: fixed sample-buffer size, no D2H sync
+        net.local_step = 0
+        net.zero_grad(set_to_none=True)
+        if graph:
+            ts.capture(*b[1], warmup=1)
+            torch.manual_seed(5)                                  # the captured torch.rand of the ray jitter restarts here
+            loss = ts.replay(*b[2])
+        else:
+            for _ in range(2):
+                net.zero_grad(set_to_none=True)
+                ts.forward_backward(*b[1], update_grid=False)
+            net.zero_grad(set_to_none=True)
+            torch.manual_seed(5)
+            loss = ts.forward_backward(*b[2], update_grid=False)
+        out.append((float(loss), [p.grad.detach().clone() for p in net.parameters()], net, ts))
+    assert abs(out[0][0] - out[1][0]) <= 1e-5 * abs(out[0][0])
+    for a, c in zip(out[0][1], out[1][1]):
+        assert rel_l2(c, a) <= 1e-5
+    net, ts = out[1][2], out[1][3]
+    ts.optimizer = trainer.make_optimizer(net, 1e-2, fused=True)
+    ts.optimizer_step()
+    assert all(p.grad is None for p in net.parameters())
+    ts.replay(*b[2])
+    assert all(p.grad is not None for p in net.parameters())

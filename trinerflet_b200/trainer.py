@@ -308,6 +308,9 @@ class TrainStep:
                 self._idwt_backward()
         self._graphs = (gA, gB)
         self._graph_plan_version = self._plan.version if self._plan is not None else None
+        # the gradient tensors the captured kernels write into; replay() re-attaches them, so zero_grad(set_to_none=True)
+        # between replays (optimizer_step does it) is harmless
+        self._graph_grads = [(p, p.grad) for p in self.model.parameters() if p.grad is not None]
         return self
 
     def replay(self, rays_o, rays_d, images):
@@ -323,6 +326,8 @@ class TrainStep:
             gB.replay()
         elif self.world_size > 1:
             parallel.allreduce_gradients(self.model, self.world_size)
+        for p, g in self._graph_grads:
+            p.grad = g
         self.global_step += 1
         return self._static_loss
 
