@@ -130,3 +130,21 @@ def test_fused_adam_arithmetic_matches_torch_adam():
     from trinerflet_b200.optim import _dense_storage
     t = torch.zeros(3, 4, 4, 2).permute(0, 3, 1, 2)
     assert _dense_storage(t) and not _dense_storage(t[:, :1]) and not _dense_storage(torch.zeros(4, 4)[:, ::2])
+
+
+def test_trunc_exp_matches_the_oracle_including_the_truncated_range():
+    from oracle import field as of
+    from trinerflet_b200.activation import trunc_exp
+    x = torch.tensor([-40.0, -15.0001, -15.0, -3.25, 0.0, 0.5, 14.999, 15.0, 15.5, 30.0])
+    g = torch.tensor([1.0, -2.0, 0.5, 3.0, 1.0, -1.0, 2.0, 1.0, 1.0, 0.25])
+    a = x.clone().requires_grad_(True)
+    b = x.clone().requires_grad_(True)
+    ya, yb = trunc_exp(a), of.trunc_exp(b)
+    ya.backward(g)
+    yb.backward(g)
+    assert torch.equal(ya, yb) and torch.equal(a.grad, b.grad)
+    h = x.half().clone().requires_grad_(True)          # fp16 logits (autocast): fp32 value, gradient back in fp16
+    y = trunc_exp(h)
+    assert y.dtype == torch.float32
+    y.backward(g)
+    assert h.grad.dtype == torch.float16
