@@ -240,6 +240,18 @@ int tnl_grid_cell_positions(const int32_t* indices, uint32_t n, uint32_t H, floa
  * full sweep (indices == NULL => idx = i) or scattered cells; see DESIGN.md for the tmp_grid semantics. */
 int tnl_grid_ema_update(float* grid, const float* tmp_grid, uint32_t n, float decay, tnl_stream_t stream);
 
+/* ------------------------------------------------------------------ step feeder -- */
+/* replaces, for one step's batch, get_rays (reconstruction/nerf/utils.py:64-149), the index into the shuffled ray table
+ * of shuffle_data / select_batch (utils.py:228-243) and the target gather of collate (nerf/provider.py:708-711).
+ * poses [B][4][4] cam2world (row-major, 16-byte aligned); pixel centre + 0.5, dir = normalise((i-cx)/fx, (j-cy)/fy, 1),
+ * rays_d = dir @ R^T, rays_o = t.  A ray id addresses the flattened [B*H*W] table: id = image * H*W + row * W + col.
+ * ray_ids [n] int64 device pointer, or NULL for the contiguous range first_id .. first_id+n-1 (full frames, N = -1).
+ * images [B][H*W][image_channels] fp32 (optional, channels 3 or 4) -> targets [n][image_channels]; both NULL to skip.
+ * Ids outside [0, B*H*W) are clamped (the reference raises on the host). */
+int tnl_rays_from_ids(const float* poses, uint32_t B, float fx, float fy, float cx, float cy, uint32_t H, uint32_t W,
+                      const int64_t* ray_ids, int64_t first_id, uint32_t n, const float* images, uint32_t image_channels,
+                      float* rays_o, float* rays_d, float* targets, tnl_stream_t stream);
+
 /* ------------------------------------------------------------------ multi-GPU gradient exchange ---- */
 /* flags [3][R/T][R/T] (uint8): 1 where a tile of T x T texels can receive plane gradient, i.e. lies under the projection
  * of an occupied density-grid cell (+ margin texels).  Deterministic function of the bitfield: identical on all ranks. */

@@ -43,3 +43,19 @@ def random_bitfield(seed=0, cascade=2, H=128, radius=0.8, bound=1.5):
     grid = np.where(flip, 1.0 - grid, grid).astype(np.float32)
     bits = np.packbits(grid.reshape(-1) > 0.5, bitorder='little')
     return torch.from_numpy(grid), torch.from_numpy(bits)
+
+
+def build_emu(name, deps=(), flags=()):
+    """Compile tests/emu/<name>.cpp (the host emulator of a kernel's per-thread code) into tests/emu/_build/lib<name>.so
+    if it is older than its sources, and load it with ctypes.  TEST-ONLY code, never part of the product library."""
+    import ctypes
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "tests", "emu", name + ".cpp")
+    so = os.path.join(root, "tests", "emu", "_build", "lib" + name + ".so")
+    newest = max(os.path.getmtime(p) for p in [src] + [os.path.join(root, d) for d in deps])
+    if not os.path.exists(so) or os.path.getmtime(so) < newest:
+        os.makedirs(os.path.dirname(so), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", *flags, "-o", so, src])
+    return ctypes.CDLL(so)

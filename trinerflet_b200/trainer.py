@@ -331,6 +331,16 @@ class TrainStep:
         self.global_step += 1
         return self._static_loss
 
+    def replay_from_feeder(self, feeder, batch_idx, batch_size):
+        """One captured fwd+bwd whose rays and targets are generated on the device (rays.RayFeeder): the
+        feeder kernel writes straight into the graph's static input buffers -- no host batch, no H2D copy."""
+        ids = feeder.batch_ids(batch_idx, batch_size)
+        if ids.numel() != self._static[0].shape[0]:
+            raise RuntimeError("replay_from_feeder: the batch does not have the captured number of rays (ragged last batch: "
+                               "run it through step()/forward_backward instead)")
+        feeder.select_batch(batch_idx, batch_size, out=self._static)
+        return self.replay(*self._static)
+
     def optimizer_step(self):
         if self.optimizer is None:
             return
