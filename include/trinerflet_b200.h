@@ -96,6 +96,29 @@ size_t tnl_compact_alive_workspace(uint32_t n);
 int tnl_compact_alive(const int32_t* alive, uint32_t n, int32_t* out, int32_t* n_out_dev, void* workspace,
                       size_t workspace_bytes, tnl_stream_t stream);
 
+/* Device-driven inference loop: the loop state of NeRFRenderer.run_cuda's eval branch
+ * (reconstruction/nerf/renderer.py:342-368: n_alive, n_step = max(min(N // n_alive, 8), 1), step += n_step, the
+ * boolean-index compaction) lives in `ctrl` (device int32[8]) so that the host can issue several iterations back to back
+ * and read the state only now and then (the reference synchronises once per iteration).
+ *   ctrl[0] n_alive   ctrl[1] n_step (0 = loop finished)   ctrl[2] samples per ray marched so far
+ *   ctrl[3] n_alive*n_step = valid rows of this iteration (pass ctrl+3 as `n_valid` to the sampling / MLP calls)
+ *   ctrl[4] iterations that did work   ctrl[6] survivors left by the last compaction
+ * Start state: all zero except ctrl[6] = N.  One iteration = tnl_infer_plan; tnl_march_rays_dev; field; tnl_composite_rays_dev;
+ * tnl_compact_alive_dev (alive -> out, swap the two lists).  `cap` >= n_alive sizes the grids (any upper bound: N, or the
+ * last n_alive the host has seen); buffers hold min(N, 8*cap) rows (+ alignment).  Rows a ray does not reach are zeroed by the
+ * marcher (the host-driven calls rely on freshly zeroed buffers instead).  noises may be NULL (no perturbation).
+ * Iterations issued after the loop has finished do nothing.  Results are identical to the host-driven calls. */
+int tnl_infer_plan(int32_t* ctrl, uint32_t N, uint32_t max_steps, tnl_stream_t stream);
+int tnl_march_rays_dev(const int32_t* ctrl, uint32_t cap, const int32_t* rays_alive, const float* rays_t,
+                       const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C,
+                       uint32_t H, const uint8_t* grid, const float* fars, float* xyzs, float* dirs, float* deltas,
+                       const float* noises, tnl_stream_t stream);
+int tnl_composite_rays_dev(const int32_t* ctrl, uint32_t cap, float T_thresh, int32_t* rays_alive, float* rays_t,
+                           const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum, float* depth,
+                           float* image, tnl_stream_t stream);
+int tnl_compact_alive_dev(int32_t* ctrl, uint32_t cap, const int32_t* alive, int32_t* out, void* workspace,
+                          size_t workspace_bytes, tnl_stream_t stream);
+
 /* ------------------------------------------------------------------ SH direction encoder ----- */
 /* replaces sh_encode_forward (shencoder.h:9, shencoder.cu:387-398) for degree <= 4, dy_dx = NULL */
 int tnl_sh_encode_forward(const float* inputs, float* outputs, uint32_t B, uint32_t degree, tnl_stream_t stream);

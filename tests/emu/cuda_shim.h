@@ -79,14 +79,51 @@ struct Block {
     std::vector<Warp> warps;
 };
 
+#if defined(__x86_64__)
+#define TNL_EMU_ASM_SWITCH 1
+// minimal cooperative context switch (callee-saved registers + stack pointer); swapcontext() costs a sigprocmask system
+// call per switch, which dominates kernels that rendezvous often (block scans with 1024 threads)
+extern "C" void tnl_emu_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.weak tnl_emu_switch
+.type tnl_emu_switch,@function
+tnl_emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size tnl_emu_switch,.-tnl_emu_switch
+)");
+#endif
+
 struct Fiber {
+#ifdef TNL_EMU_ASM_SWITCH
+    void* sp = nullptr;
+#else
     ucontext_t ctx;
+#endif
     bool done = true;
     unsigned tid = 0;
 };
 
 struct Runtime {
+#ifdef TNL_EMU_ASM_SWITCH
+    void* main_sp = nullptr;
+#else
     ucontext_t main_ctx;
+#endif
     std::vector<Fiber> fibers;
     char* stacks = nullptr;
     size_t stacks_for = 0;
@@ -117,11 +154,24 @@ inline void set_thread(unsigned tid) {
     threadIdx.z = tid / (blockDim.x * blockDim.y);
 }
 
-inline void yield() {
+inline void to_main(Fiber* f) {
     Runtime& r = rt();
-    Fiber* f = r.cur;
+#ifdef TNL_EMU_ASM_SWITCH
+    tnl_emu_switch(&f->sp, r.main_sp);
+#else
     swapcontext(&f->ctx, &r.main_ctx);
+#endif
 }
+inline void to_fiber(Fiber* f) {
+    Runtime& r = rt();
+#ifdef TNL_EMU_ASM_SWITCH
+    tnl_emu_switch(&r.main_sp, f->sp);
+#else
+    swapcontext(&r.main_ctx, &f->ctx);
+#endif
+}
+
+inline void yield() { to_main(rt().cur); }
 
 inline void release_block_if_complete(Block& b) {
     if (b.alive > 0 && b.arrived == b.alive) {
@@ -151,7 +201,8 @@ inline void trampoline() {
     w.alive &= ~(1u << (f->tid % 32));
     release_block_if_complete(b);
     release_warp_if_complete(w);
-    swapcontext(&f->ctx, &r.main_ctx);
+    to_main(f);
+    abort();   // a finished fiber is never resumed
 }
 
 inline void run_block(unsigned nthreads, const std::function<void()>& body) {
@@ -172,11 +223,22 @@ inline void run_block(unsigned nthreads, const std::function<void()>& body) {
         Fiber& f = r.fibers[t];
         f.done = false;
         f.tid = t;
+#ifdef TNL_EMU_ASM_SWITCH
+        // initial frame: six zeroed callee-saved registers, then the entry point as the return address of the first switch;
+        // after that `ret` the stack pointer is 8 (mod 16), as after a call
+        uintptr_t top = reinterpret_cast<uintptr_t>(r.stacks + (size_t)(t + 1) * r.stack_bytes) & ~uintptr_t(15);
+        void** sp = reinterpret_cast<void**>(top - 64);
+        for (int k = 0; k < 6; ++k) sp[k] = nullptr;
+        sp[6] = reinterpret_cast<void*>(&trampoline);
+        sp[7] = nullptr;
+        f.sp = sp;
+#else
         getcontext(&f.ctx);
         f.ctx.uc_stack.ss_sp = r.stacks + (size_t)t * r.stack_bytes;
         f.ctx.uc_stack.ss_size = r.stack_bytes;
         f.ctx.uc_link = nullptr;
         makecontext(&f.ctx, (void (*)())trampoline, 0);
+#endif
         b.warps[t / 32].alive |= 1u << (t % 32);
     }
     unsigned remaining = nthreads;
@@ -188,7 +250,7 @@ inline void run_block(unsigned nthreads, const std::function<void()>& body) {
             if (f.done) continue;
             r.cur = &f;
             set_thread(t);
-            swapcontext(&r.main_ctx, &f.ctx);
+            to_fiber(&f);
             if (f.done) --remaining;
         }
         // every fiber was resumed once; if none of them reached a new rendezvous or returned, the state cannot change

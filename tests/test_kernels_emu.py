@@ -475,3 +475,79 @@ def test_worklist_idwt_entry_points_equal_dense(C, n0, levels, density):
     assert np.array_equal(gx_s.view(np.uint32), gx_d.view(np.uint32))
     for a, b in zip(gy_s, gy_d):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+# ------------------------------------------------------------------------------------------------ device-driven inference loop
+def _host_driven_loop(o, d, bits, nears, fars, field, max_steps, T_thresh=1e-4):
+    """renderer.py:342-368 with the host-driven entry points (fresh zeroed buffers and a host read of the count per iteration)"""
+    N = len(o)
+    ws, dp, im = np.zeros(N, np.float32), np.zeros(N, np.float32), np.zeros((N, 3), np.float32)
+    alive, rt = np.arange(N, dtype=np.int32), nears.copy()
+    work = np.zeros(max(kemu.lib().tnl_compact_alive_workspace(N), 16), np.uint8)
+    n_alive, step, iters = N, 0, 0
+    while step < max_steps and n_alive > 0:
+        n_step = max(min(N // n_alive, 8), 1)
+        M = n_alive * n_step
+        M += 128 - M % 128
+        x, dd, dl = np.zeros((M, 3), np.float32), np.zeros((M, 3), np.float32), np.zeros((M, 2), np.float32)
+        kemu.call("tnl_march_rays", n_alive, n_step, alive, rt, o, d, BOUND, 0.0, max_steps, CAS, H, bits, nears, fars, x, dd, dl,
+                  np.zeros(n_alive, np.float32), None)
+        sig, rgb = field(x, dd)
+        kemu.call("tnl_composite_rays", n_alive, n_step, T_thresh, alive, rt, sig, rgb, dl, ws, dp, im, None)
+        out, cnt = np.zeros(n_alive, np.int32), np.zeros(1, np.int32)
+        kemu.call("tnl_compact_alive", alive, n_alive, out, cnt, work, work.size, None)
+        n_alive = int(cnt[0])
+        alive = out[:n_alive].copy()
+        step += n_step
+        iters += 1
+    return ws, dp, im, rt, iters
+
+
+def _device_driven_loop(o, d, bits, nears, fars, field, max_steps, chunk, T_thresh=1e-4):
+    """the same loop with the state in `ctrl`: `chunk` iterations are issued between two reads of the state"""
+    N = len(o)
+    ws, dp, im = np.zeros(N, np.float32), np.zeros(N, np.float32), np.zeros((N, 3), np.float32)
+    lists = [np.arange(N, dtype=np.int32), np.full(N, -9, np.int32)]
+    rt = nears.copy()
+    rows = N + 128 - N % 128
+    # persistent buffers, deliberately dirty: the marcher must clear every row it owns
+    x, dd, dl = (np.full((rows, k), 7.0, np.float32) for k in (3, 3, 2))
+    ctrl = np.zeros(8, np.int32)
+    ctrl[6] = N
+    work = np.zeros(max(kemu.lib().tnl_compact_alive_workspace(N), 16), np.uint8)
+    cap, issued, reads = N, 0, 0
+    while True:
+        for _ in range(chunk):
+            kemu.call("tnl_infer_plan", ctrl, N, max_steps, None)
+            kemu.call("tnl_march_rays_dev", ctrl, cap, lists[0], rt, o, d, BOUND, 0.0, max_steps, CAS, H, bits, fars, x, dd, dl, None, None)
+            n_rows = int(ctrl[3])                  # (the field kernels read this through their n_valid pointer)
+            sig, rgb = field(x[:max(n_rows, 1)], dd[:max(n_rows, 1)])
+            kemu.call("tnl_composite_rays_dev", ctrl, cap, T_thresh, lists[0], rt, sig, rgb, dl, ws, dp, im, None)
+            kemu.call("tnl_compact_alive_dev", ctrl, cap, lists[0], lists[1], work, work.size, None)
+            lists.reverse()
+            issued += 1
+        reads += 1                                  # the host looks at the state once per chunk
+        assert ctrl[6] <= cap
+        cap = int(ctrl[6])
+        if cap == 0 or ctrl[2] >= max_steps:
+            break
+    return ws, dp, im, rt, int(ctrl[4]), issued, reads
+
+
+@pytest.mark.parametrize("max_steps,chunk", [(1024, 8), (48, 5)])
+def test_device_driven_inference_loop_equals_host_driven(scene, max_steps, chunk):
+    o, d, bits, nears, fars = scene
+    N = 500
+    o, d, nears, fars = o[:N].copy(), d[:N].copy(), nears[:N].copy(), fars[:N].copy()
+
+    def field(x, dd):      # a deterministic stand-in for the sigma / colour heads (a function of the sample only)
+        s = (np.abs(np.sin(37.0 * x[:, 0] + 11.0 * x[:, 1])) * 12.0).astype(np.float32)
+        c = np.abs(np.cos(x * 5.0 + dd)).astype(np.float32)
+        return s, np.ascontiguousarray(c)
+
+    ws_h, dp_h, im_h, rt_h, it_h = _host_driven_loop(o, d, bits, nears, fars, field, max_steps)
+    ws_d, dp_d, im_d, rt_d, it_d, issued, reads = _device_driven_loop(o, d, bits, nears, fars, field, max_steps, chunk)
+    assert it_d == it_h and issued >= it_h and reads == -(-issued // chunk) and reads < it_h
+    assert _bits_equal(ws_d, ws_h) and _bits_equal(dp_d, dp_h) and _bits_equal(im_d, im_h) and _bits_equal(rt_d, rt_h)
+    if max_steps == 48:
+        assert it_h < 48     # the step budget, not the alive count, ended this one

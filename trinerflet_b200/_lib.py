@@ -40,6 +40,10 @@ SIGNATURES = {
     "tnl_composite_rays": (_int, [_u32, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tnl_compact_alive_workspace": (_sz, [_u32]),
     "tnl_compact_alive": (_int, [_vp, _u32, _vp, _vp, _vp, _sz, _vp]),
+    "tnl_infer_plan": (_int, [_vp, _u32, _u32, _vp]),
+    "tnl_march_rays_dev": (_int, [_vp, _u32, _vp, _vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tnl_composite_rays_dev": (_int, [_vp, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tnl_compact_alive_dev": (_int, [_vp, _u32, _vp, _vp, _vp, _sz, _vp]),
     "tnl_sh_encode_forward": (_int, [_vp, _vp, _u32, _u32, _vp]),
     "tnl_idwt_level_forward": (_int, [_vp, _vp, _vp, _u32, _u32, _vp, _vp]),
     "tnl_idwt_level_backward": (_int, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _f32, _u32, _u32, _vp]),
@@ -113,7 +117,8 @@ def check(rc, what):
 
 
 # number of kernels each ABI call launches (for the launch counter the benchmark reports)
-KERNELS_PER_CALL = {"tnl_march_rays_train": 5, "tnl_compact_alive": 3, "tnl_cell_sort": 5, "tnl_mlp_pack_weights": 2}
+KERNELS_PER_CALL = {"tnl_march_rays_train": 5, "tnl_compact_alive": 3, "tnl_compact_alive_dev": 3, "tnl_cell_sort": 5,
+                    "tnl_mlp_pack_weights": 2}
 # work-list IDWT calls launch one kernel per requested part (position of the `parts` argument from the end)
 _PARTS_ARG = {"tnl_idwt_level_forward_sparse": -2, "tnl_idwt_level_backward_sparse": -3}
 launch_count = 0

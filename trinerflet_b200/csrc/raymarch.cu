@@ -499,20 +499,20 @@ k_composite_train_bwd(const float* __restrict__ grad_ws, const float* __restrict
 // ------------------------------------------------------------------------------------------------
 // inference marching / compositing (reference :700-905)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays_alive,
-                             const float* __restrict__ rays_t, const float* __restrict__ rays_o,
-                             const float* __restrict__ rays_d, float bound, float dt_gamma, uint32_t max_steps,
-                             uint32_t C, uint32_t H, const uint8_t* __restrict__ grid, const float* __restrict__ fars,
-                             float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
-                             const float* __restrict__ noises) {
-    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= n_alive) return;
+// one alive ray: up to n_step samples into rows [n*n_step, (n+1)*n_step) of xyzs / dirs / deltas.  zero_tail: clear the rows
+// the ray does not reach (the host-driven loop passes freshly zeroed buffers instead, as the reference does).
+__device__ __forceinline__ void march_rays_one(uint32_t n, uint32_t n_step, const int32_t* __restrict__ rays_alive,
+                                               const float* __restrict__ rays_t, const float* __restrict__ rays_o,
+                                               const float* __restrict__ rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                                               uint32_t C, uint32_t H, const uint8_t* __restrict__ grid,
+                                               const float* __restrict__ fars, float* __restrict__ xyzs, float* __restrict__ dirs,
+                                               float* __restrict__ deltas, const float* __restrict__ noises, bool zero_tail) {
     const int32_t index = rays_alive[n];
     const MarchParams p = make_params(bound, dt_gamma, max_steps, C, H, grid);
     const MarchRay r = load_ray(rays_o + 3 * (size_t)index, rays_d + 3 * (size_t)index);
     const float far = fars[index];
     float t = rays_t[index];
-    t = __fmaf_rn(clampf(__fmul_rn(t, dt_gamma), p.dt_min, p.dt_max), noises[n], t);
+    if (noises != nullptr) t = __fmaf_rn(clampf(__fmul_rn(t, dt_gamma), p.dt_min, p.dt_max), noises[n], t);
     float last_t = t;
     float* px = xyzs + 3 * (size_t)n * n_step;
     float* pd = dirs + 3 * (size_t)n * n_step;
@@ -531,14 +531,32 @@ __global__ void k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* _
             ++step;
         }
     }
+    if (zero_tail)
+        for (; step < n_step; ++step) {
+            px[0] = 0.f; px[1] = 0.f; px[2] = 0.f;
+            pd[0] = 0.f; pd[1] = 0.f; pd[2] = 0.f;
+            pl[0] = 0.f; pl[1] = 0.f;
+            px += 3; pd += 3; pl += 2;
+        }
 }
 
-__global__ void k_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* __restrict__ rays_alive,
-                                 float* __restrict__ rays_t, const float* __restrict__ sigmas,
-                                 const float* __restrict__ rgbs, const float* __restrict__ deltas,
-                                 float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image) {
+__global__ void k_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t* __restrict__ rays_alive,
+                             const float* __restrict__ rays_t, const float* __restrict__ rays_o,
+                             const float* __restrict__ rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                             uint32_t C, uint32_t H, const uint8_t* __restrict__ grid, const float* __restrict__ fars,
+                             float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
+                             const float* __restrict__ noises) {
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= n_alive) return;
+    march_rays_one(n, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, fars, xyzs, dirs, deltas,
+                   noises, false);
+}
+
+__device__ __forceinline__ void composite_rays_one(uint32_t n, uint32_t n_step, float T_thresh, int32_t* __restrict__ rays_alive,
+                                                   float* __restrict__ rays_t, const float* __restrict__ sigmas,
+                                                   const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                                                   float* __restrict__ weights_sum, float* __restrict__ depth,
+                                                   float* __restrict__ image) {
     const int32_t index = rays_alive[n];
     const float* s = sigmas + (size_t)n * n_step;
     const float* c = rgbs + 3 * (size_t)n * n_step;
@@ -566,6 +584,103 @@ __global__ void k_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thre
     image[3 * (size_t)index] = r;
     image[3 * (size_t)index + 1] = g;
     image[3 * (size_t)index + 2] = b;
+}
+
+__global__ void k_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t* __restrict__ rays_alive,
+                                 float* __restrict__ rays_t, const float* __restrict__ sigmas,
+                                 const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                                 float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_alive) return;
+    composite_rays_one(n, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image);
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-driven inference loop: the loop state of renderer.py:342-368 lives in `ctrl` on the device, so the
+// host can issue several iterations without reading anything back.
+//   ctrl[0] n_alive   rays in the current alive list            ctrl[1] n_step   samples per ray this iteration (0 = finished)
+//   ctrl[2] step      samples per ray marched so far            ctrl[3] n_rows   n_alive * n_step = valid rows of this iteration
+//   ctrl[4] iterations that did work                            ctrl[6] n_next   survivors left by the last compaction
+// k_infer_plan is the only writer of ctrl[0..4]; the compaction writes ctrl[6].
+// ------------------------------------------------------------------------------------------------
+enum { kCtlAlive = 0, kCtlStep = 1, kCtlMarched = 2, kCtlRows = 3, kCtlIters = 4, kCtlNext = 6 };
+
+__global__ void k_infer_plan(int32_t* __restrict__ ctrl, uint32_t N, uint32_t max_steps) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int32_t n_alive = ctrl[kCtlNext];
+    const int32_t marched = ctrl[kCtlMarched];
+    int32_t n_step = 0;
+    if (n_alive > 0 && (uint32_t)marched < max_steps) {      // renderer.py:342-352
+        n_step = (int32_t)(N / (uint32_t)n_alive);
+        n_step = n_step > 8 ? 8 : (n_step < 1 ? 1 : n_step);
+    }
+    ctrl[kCtlAlive] = n_alive;
+    ctrl[kCtlStep] = n_step;
+    ctrl[kCtlRows] = n_alive * n_step;
+    if (n_step > 0) {
+        ctrl[kCtlMarched] = marched + n_step;                   // renderer.py:368
+        ctrl[kCtlIters] += 1;
+    }
+}
+
+__global__ void k_march_rays_dev(const int32_t* __restrict__ ctrl, const int32_t* __restrict__ rays_alive,
+                                 const float* __restrict__ rays_t, const float* __restrict__ rays_o,
+                                 const float* __restrict__ rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C,
+                                 uint32_t H, const uint8_t* __restrict__ grid, const float* __restrict__ fars,
+                                 float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas,
+                                 const float* __restrict__ noises) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_alive = (uint32_t)ctrl[kCtlAlive], n_step = (uint32_t)ctrl[kCtlStep];
+    if (n_step == 0 || n >= n_alive) return;
+    march_rays_one(n, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, fars, xyzs, dirs, deltas,
+                   noises, true);
+}
+
+__global__ void k_composite_rays_dev(const int32_t* __restrict__ ctrl, float T_thresh, int32_t* __restrict__ rays_alive,
+                                     float* __restrict__ rays_t, const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                     const float* __restrict__ deltas, float* __restrict__ weights_sum, float* __restrict__ depth,
+                                     float* __restrict__ image) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_alive = (uint32_t)ctrl[kCtlAlive], n_step = (uint32_t)ctrl[kCtlStep];
+    if (n_step == 0 || n >= n_alive) return;
+    composite_rays_one(n, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image);
+}
+
+// compaction with the element count read from ctrl; grids are sized by the caller's upper bound `cap`.  A finished
+// iteration (n_step == 0) leaves the list and ctrl[6] untouched.
+__global__ void k_compact_sums_dev(const int32_t* __restrict__ ctrl, const int32_t* __restrict__ alive,
+                                   uint32_t* __restrict__ block_sums) {
+    __shared__ uint32_t sm[33];
+    const uint32_t n = ctrl[kCtlStep] > 0 ? (uint32_t)ctrl[kCtlAlive] : 0u;
+    const uint32_t i = blockIdx.x * kScanThreads + threadIdx.x;
+    uint32_t total;
+    block_exclusive_scan(scan_value<1>(alive, i, n, 1), &total, sm);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void k_compact_scan_dev(int32_t* __restrict__ ctrl, uint32_t* __restrict__ block_sums, uint32_t nblocks) {
+    __shared__ uint32_t sm[33];
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < nblocks; base += kScanThreads) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < nblocks ? block_sums[i] : 0u;
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan(v, &total, sm);
+        if (i < nblocks) block_sums[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0 && ctrl[kCtlStep] > 0) ctrl[kCtlNext] = (int32_t)carry;
+}
+
+__global__ void k_compact_scatter_dev(const int32_t* __restrict__ ctrl, const int32_t* __restrict__ alive,
+                                      const uint32_t* __restrict__ block_sums, int32_t* __restrict__ out) {
+    __shared__ uint32_t sm[33];
+    const uint32_t n = ctrl[kCtlStep] > 0 ? (uint32_t)ctrl[kCtlAlive] : 0u;
+    const uint32_t i = blockIdx.x * kScanThreads + threadIdx.x;
+    const uint32_t f = scan_value<1>(alive, i, n, 1);
+    uint32_t total;
+    const uint32_t ex = block_exclusive_scan(f, &total, sm);
+    if (f) out[block_sums[blockIdx.x] + ex] = alive[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -723,6 +838,51 @@ int tnl_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_
     k_composite_rays<<<ceil_div(n_alive, kT), kT, 0, S(stream)>>>(n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas,
                                                                    rgbs, deltas, weights_sum, depth, image);
     return finish_launch("composite_rays");
+}
+
+int tnl_infer_plan(int32_t* ctrl, uint32_t N, uint32_t max_steps, tnl_stream_t stream) {
+    TNL_ARG_CHECK(ctrl, "null pointer");
+    TNL_ARG_CHECK(N >= 1 && max_steps >= 1, "N and max_steps must be positive");
+    k_infer_plan<<<1, 32, 0, S(stream)>>>(ctrl, N, max_steps);
+    return finish_launch("infer_plan");
+}
+
+int tnl_march_rays_dev(const int32_t* ctrl, uint32_t cap, const int32_t* rays_alive, const float* rays_t, const float* rays_o,
+                       const float* rays_d, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+                       const uint8_t* grid, const float* fars, float* xyzs, float* dirs, float* deltas, const float* noises,
+                       tnl_stream_t stream) {
+    if (cap == 0) return 0;
+    TNL_ARG_CHECK(ctrl && rays_alive && rays_t && rays_o && rays_d && grid && fars && xyzs && dirs && deltas, "null pointer");
+    TNL_ARG_CHECK(C >= 1 && C <= 8 && H >= 2 && H <= 1024 && max_steps >= 1, "unsupported cascade / grid size");
+    k_march_rays_dev<<<ceil_div(cap, kT), kT, 0, S(stream)>>>(ctrl, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C,
+                                                              H, grid, fars, xyzs, dirs, deltas, noises);
+    return finish_launch("march_rays_dev");
+}
+
+int tnl_composite_rays_dev(const int32_t* ctrl, uint32_t cap, float T_thresh, int32_t* rays_alive, float* rays_t,
+                           const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum, float* depth,
+                           float* image, tnl_stream_t stream) {
+    if (cap == 0) return 0;
+    TNL_ARG_CHECK(ctrl && rays_alive && rays_t && sigmas && rgbs && deltas && weights_sum && depth && image, "null pointer");
+    k_composite_rays_dev<<<ceil_div(cap, kT), kT, 0, S(stream)>>>(ctrl, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas,
+                                                                  weights_sum, depth, image);
+    return finish_launch("composite_rays_dev");
+}
+
+int tnl_compact_alive_dev(int32_t* ctrl, uint32_t cap, const int32_t* alive, int32_t* out, void* workspace,
+                          size_t workspace_bytes, tnl_stream_t stream) {
+    if (cap == 0) return 0;
+    TNL_ARG_CHECK(ctrl && alive && out, "null pointer");
+    if (workspace == nullptr || workspace_bytes < tnl_compact_alive_workspace(cap)) {
+        set_error("compact_alive_dev: workspace too small");
+        return TNL_ERR_WORKSPACE;
+    }
+    uint32_t* block_sums = static_cast<uint32_t*>(workspace);
+    const uint32_t nb = ceil_div(cap, (uint32_t)kScanThreads);
+    k_compact_sums_dev<<<nb, kScanThreads, 0, S(stream)>>>(ctrl, alive, block_sums);
+    k_compact_scan_dev<<<1, kScanThreads, 0, S(stream)>>>(ctrl, block_sums, nb);
+    k_compact_scatter_dev<<<nb, kScanThreads, 0, S(stream)>>>(ctrl, alive, block_sums, out);
+    return finish_launch("compact_alive_dev");
 }
 
 size_t tnl_compact_alive_workspace(uint32_t n) { return sizeof(uint32_t) * (ceil_div(n, (uint32_t)kScanThreads) + 1); }

@@ -264,3 +264,82 @@ def compact_rays_alive(rays_alive, n_alive=None):
     ws = _workspace(lib.tnl_compact_alive_workspace(n), rays_alive.device)
     call("tnl_compact_alive", ptr(rays_alive), n, ptr(out), ptr(cnt), ptr(ws), ws.numel(), stream())
     return out, cnt
+
+
+class DeviceRayLoop:
+    """Device-driven form of the inference loop of NeRFRenderer.run_cuda (reconstruction/nerf/renderer.py:342-368; SURVEY.md
+    8f-3).  n_alive, n_step = max(min(N // n_alive, 8), 1), the step budget and the alive-list compaction live in `ctrl` on
+    the device (tnl_infer_plan / tnl_march_rays_dev / tnl_composite_rays_dev / tnl_compact_alive_dev), the sample buffers are
+    allocated once per frame, and the host reads the state back only when `poll()` is called -- the reference (and the
+    host-driven calls above) synchronise once per iteration.  Per-ray results are identical to the host-driven loop.
+
+        loop = DeviceRayLoop(rays_o, rays_d, nears, fars, bound, bitfield, cascade, H, dt_gamma, max_steps, perturb)
+        while True:
+            for _ in range(chunk):
+                xyzs, dirs = loop.begin_iteration()
+                sigmas, rgbs = field(xyzs, dirs, n_valid=loop.n_valid)
+                loop.end_iteration(sigmas, rgbs, weights_sum, depth, image, T_thresh)
+            if loop.poll():
+                break
+    """
+
+    def __init__(self, rays_o, rays_d, nears, fars, bound, density_bitfield, C, H, dt_gamma=0, max_steps=1024, perturb=False):
+        self.rays_o = _cuda_f32(rays_o).view(-1, 3)
+        self.rays_d = _cuda_f32(rays_d).view(-1, 3)
+        dev = self.rays_o.device
+        self.N = N = self.rays_o.shape[0]
+        self.nears, self.fars = _cuda_f32(nears), _cuda_f32(fars)
+        self.bound, self.C, self.H = float(bound), int(C), int(H)
+        self.dt_gamma, self.max_steps = float(dt_gamma), int(max_steps)
+        self.bitfield = density_bitfield.contiguous()
+        self.ctrl = torch.tensor([0, 0, 0, 0, 0, 0, N, 0], dtype=torch.int32, device=dev)
+        self.n_valid = self.ctrl[3:4]                      # n_alive * n_step of the running iteration, on the device
+        self.lists = [torch.arange(N, dtype=torch.int32, device=dev), torch.empty(N, dtype=torch.int32, device=dev)]
+        self.rays_t = self.nears.clone()
+        rows = N + 128 - N % 128                           # n_alive * n_step <= N always; same padding rule as march_rays
+        self.xyzs = torch.zeros(rows, 3, dtype=torch.float32, device=dev)
+        self.dirs = torch.zeros(rows, 3, dtype=torch.float32, device=dev)
+        self.deltas = torch.zeros(rows, 2, dtype=torch.float32, device=dev)
+        self.noises = torch.rand(N, dtype=torch.float32, device=dev) if perturb else None   # first iteration only (renderer.py:354)
+        self.ws = _workspace(_lib.load().tnl_compact_alive_workspace(N), dev)
+        self.cap = N                                       # the host's upper bound of n_alive (sizes the grids)
+        self.iterations_issued = 0
+        self.reads = 0
+
+    def _rows_cap(self):
+        m = min(self.N, 8 * self.cap)
+        return min(m + 128 - m % 128, self.xyzs.shape[0])
+
+    def begin_iteration(self):
+        """plan + march -> views of the sample buffers the field has to evaluate (rows >= *n_valid are stale: skip them)"""
+        if self.cap <= 0:
+            raise RuntimeError("DeviceRayLoop: the loop has finished")
+        call("tnl_infer_plan", ptr(self.ctrl), self.N, self.max_steps, stream())
+        noises = self.noises if self.iterations_issued == 0 else None
+        call("tnl_march_rays_dev", ptr(self.ctrl), self.cap, ptr(self.lists[0]), ptr(self.rays_t), ptr(self.rays_o), ptr(self.rays_d),
+             self.bound, self.dt_gamma, self.max_steps, self.C, self.H, ptr(self.bitfield), ptr(self.fars), ptr(self.xyzs),
+             ptr(self.dirs), ptr(self.deltas), ptr(noises), stream())
+        r = self._rows_cap()
+        return self.xyzs[:r], self.dirs[:r]
+
+    def end_iteration(self, sigmas, rgbs, weights_sum, depth, image, T_thresh=1e-2):
+        """composite into weights_sum / depth / image (in place) and compact the alive list"""
+        sigmas = sigmas.detach().float().contiguous()
+        rgbs = rgbs.detach().float().contiguous()
+        r = self._rows_cap()
+        if sigmas.shape[0] < r or rgbs.shape[0] < r:
+            raise RuntimeError("DeviceRayLoop: sigmas / rgbs must cover the rows returned by begin_iteration()")
+        call("tnl_composite_rays_dev", ptr(self.ctrl), self.cap, float(T_thresh), ptr(self.lists[0]), ptr(self.rays_t), ptr(sigmas),
+             ptr(rgbs), ptr(self.deltas), ptr(weights_sum), ptr(depth), ptr(image), stream())
+        call("tnl_compact_alive_dev", ptr(self.ctrl), self.cap, ptr(self.lists[0]), ptr(self.lists[1]), ptr(self.ws), self.ws.numel(),
+             stream())
+        self.lists.reverse()
+        self.iterations_issued += 1
+
+    def poll(self):
+        """read the loop state (one D2H copy + sync); tightens the grid bound; True when the loop has finished"""
+        c = self.ctrl.cpu()
+        self.reads += 1
+        self.cap = int(c[6])
+        self.iterations_done = int(c[4])
+        return self.cap <= 0 or int(c[2]) >= self.max_steps

@@ -100,7 +100,24 @@ class NeRFRenderer(nn.Module):
             weights_sum = torch.zeros(N, dtype=torch.float32, device=device)
             depth = torch.zeros(N, dtype=torch.float32, device=device)
             image = torch.zeros(N, 3, dtype=torch.float32, device=device)
-            n_alive = N
+            chunk = int(getattr(self, "infer_chunk", 0))
+            if chunk > 0 and N > 0:
+                # device-driven loop: `chunk` iterations are issued per read of the loop state; sample
+                # buffers live for the whole frame; identical per-ray results (opt-in: model.infer_chunk = 8)
+                loop = raymarching.DeviceRayLoop(rays_o, rays_d, nears, fars, self.bound, self.density_bitfield, self.cascade,
+                                                 self.grid_size, dt_gamma, max_steps, perturb)
+                while True:
+                    for _ in range(chunk):
+                        xyzs, dirs = loop.begin_iteration()
+                        sigmas, rgbs = self(xyzs, dirs, n_valid=loop.n_valid)
+                        sigmas = self.density_scale * sigmas
+                        loop.end_iteration(sigmas, rgbs, weights_sum, depth, image, T_thresh)
+                    if loop.poll():
+                        break
+                self.last_infer_loop = loop
+                n_alive = 0
+            else:
+                n_alive = N
             rays_alive = torch.arange(n_alive, dtype=torch.int32, device=device)
             rays_t = nears.clone()
             step = 0
