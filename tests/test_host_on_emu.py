@@ -1,0 +1,262 @@
+"""CPU: the package's HOST code (autograd Functions, NeRFRenderer.run_cuda / update_extra_state, IdwtPlan, RayFeeder,
+DeviceRayLoop, PlaneGradReducer) running end to end on CPU tensors over the host build of the product kernels
+(tests/emu_backend.py points the ctypes binding at tests/emu/_build/libkemu.so for the duration of a test), in fp32,
+against the oracle pipeline.  The product has no CPU path; this is the test-suite executing the same Python + the same
+kernel sources without a GPU.  The fused MLP kernels are not emulated: outside autocast NeRFNetwork runs the reference's
+fp32 op sequence with torch, which is what these tests exercise."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from tests import emu_backend
+from tests.util import rel_l2
+
+BOUND = 1.5
+
+
+@pytest.fixture
+def emu(monkeypatch):
+    return emu_backend.install(monkeypatch)
+
+
+def _model(seed=0, radius=0.75):
+    from trinerflet_b200 import scene
+    from trinerflet_b200.network import NeRFNetwork
+    c = scene.CONFIGS["tiny"]
+    net = NeRFNetwork(bound=BOUND, cuda_ray=True, density_thresh=10, min_near=0.2, triplane_channels=c["C"],
+                      triplane_resolution=c["R"], triplane_wavelet_levels=c["S"], hidden_dim=c["hidden"], hidden_dim_color=c["hidden"])
+    scene.init_model_(net, seed=seed)
+    scene.install_ball_occupancy(net, radius)
+    return net
+
+
+def test_training_step_matches_oracle_pipeline_fp32(emu):
+    """render (march -> sample -> fp32 heads -> composite) + MSE + wavelet regulariser, forward and backward, through
+    NeRFNetwork.render and TrainStep.forward_backward vs oracle/pipeline.py::train_step on identical rays and jitter"""
+    from oracle import pipeline
+    from trinerflet_b200 import scene, trainer
+    net = _model()
+    net.train()
+    sc = scene.make_scene()
+    N = 384
+    ro, rd, tgt = scene.sample_batch(sc, N, torch.Generator().manual_seed(0))
+    opt = trainer.default_opt(fp16=False)
+    ts = trainer.TrainStep(net, opt, None)
+    torch.manual_seed(5)
+    loss = ts.forward_backward(ro, rd, tgt, update_grid=False)
+    M = int(net.step_counter[0, 0])
+    assert M > 2000
+    # oracle on the same parameters / rays / noises (the wrapper draws torch.rand(N) from the global generator)
+    torch.manual_seed(5)
+    noises = torch.rand(N).numpy()
+    pf = net.encoder.planes_features.detach().clone().contiguous().requires_grad_(True)
+    coefs = [p.detach().clone().contiguous().requires_grad_(True) for p in net.encoder.planes_features_wavelet_coefs]
+    W = [w.detach().clone().requires_grad_(True) for w in net._weights()]
+    loss_o, M_o = pipeline.train_step(pf, coefs, W, ro, rd, tgt, net.density_bitfield.numpy(), noises, lam=opt.wavelet_regularization)
+    assert M_o == M
+    assert abs(float(loss) - loss_o) <= 1e-5 * abs(loss_o)
+    assert rel_l2(net.encoder.planes_features.grad, pf.grad) <= 1e-4
+    for p, c in zip(net.encoder.planes_features_wavelet_coefs, coefs):
+        assert rel_l2(p.grad, c.grad) <= 1e-4
+    for w, wo in zip(net._weights(), W):
+        assert rel_l2(w.grad, wo.grad) <= 1e-4
+    # steady state (mean_count > 0: fixed buffer, no count read-back) gives the same loss
+    net.mean_count = M
+    net.zero_grad(set_to_none=True)
+    torch.manual_seed(5)
+    loss2 = ts.forward_backward(ro, rd, tgt, update_grid=False)
+    assert abs(float(loss2) - float(loss)) <= 1e-6 * abs(float(loss))
+
+
+def test_inference_render_host_loop_and_device_loop(emu):
+    from trinerflet_b200 import parallel, scene
+    net = _model()
+    net.eval()
+    sc = scene.make_scene()
+    ro, rd = scene.full_frame(sc, 3)
+    pick = torch.arange(0, ro.shape[0], 613)[:900]
+    ro, rd = ro[pick].contiguous(), rd[pick].contiguous()
+    outs = []
+    for chunk in (0, 6):
+        net.infer_chunk = chunk
+        with torch.no_grad():
+            outs.append(net.render(ro.unsqueeze(0), rd.unsqueeze(0), staged=True, bg_color=1, perturb=False, max_steps=256))
+    loop = net.last_infer_loop
+    assert loop.reads < loop.iterations_done and loop.iterations_issued >= loop.iterations_done
+    a, b = outs
+    assert float(a["weights_sum"].sum()) > 5.0
+    assert torch.equal(a["image"], b["image"]) and torch.equal(a["weights_sum"], b["weights_sum"])
+    m = torch.isfinite(a["depth"])
+    assert torch.equal(a["depth"][m], b["depth"][m])
+    # ray tiles are independent: shards rendered separately reproduce the frame (rendering partition)
+    with torch.no_grad():
+        parts = [net.render(ro[lo:hi].unsqueeze(0), rd[lo:hi].unsqueeze(0), staged=True, bg_color=1, perturb=False,
+                            max_steps=256)["image"].view(-1, 3) for lo, hi in (parallel.shard_range(900, r, 3) for r in range(3))]
+    assert (torch.cat(parts) - a["image"].view(-1, 3)).abs().max().item() <= 1e-4
+
+
+def test_update_extra_state_and_plan_refresh(emu):
+    from trinerflet_b200 import raymarching as rm
+    from trinerflet_b200.idwt_plan import IdwtPlan
+    net = _model()
+    net.density_grid.zero_()
+    net.iter_density = 0
+    net.mean_density = 0
+    net.update_extra_state()
+    assert net.iter_density == 1 and float(net.density_grid.min()) >= 0 and net.mean_density > 0
+    thresh = min(net.mean_density, net.density_thresh)
+    assert torch.equal(net.density_bitfield, rm.packbits(net.density_grid, thresh))
+    assert np.array_equal(net.density_bitfield.numpy(), np.packbits(net.density_grid.numpy().reshape(-1) > thresh, bitorder='little'))
+    net.iter_density = 16
+    before = net.density_grid.clone()
+    net.update_extra_state()
+    assert net.iter_density == 17 and bool((net.density_grid >= before * 0.95 - 1e-6).all())
+    from trinerflet_b200 import scene
+    scene.install_ball_occupancy(net, 0.4)
+    plan = IdwtPlan.from_model(net)
+    assert 0.0 < plan.stats["tile_fraction"] < 0.6
+    assert plan.stats["zero_fill_fraction"] >= plan.stats["tile_fraction"]
+
+
+def test_worklist_build_planes_autograd_equals_dense(emu):
+    """triplane_encoder.build_planes_with_abs with an IdwtPlan (the autograd Function the training step uses) vs dense"""
+    from tests.util import cl_coefs, cl_planes
+    from trinerflet_b200.idwt_plan import IdwtPlan
+    from trinerflet_b200.triplane_encoder import build_planes_with_abs
+    C, n0, levels = 16, 16, 2
+    R, T = n0 * 2 ** levels, n0 * 2 ** levels // 32
+    g = torch.Generator().manual_seed(5)
+    flags = torch.zeros(3, T, T, dtype=torch.bool)
+    flags[:, 0, 1] = True
+    flags[1, 1, 0] = True
+    plan = IdwtPlan(R, n0, levels, C, "cpu").update(flags)
+    pf = torch.randn(3, C, n0, n0, generator=g)
+    coefs = [0.1 * torch.randn(3, C, 3, n0 * 2 ** l, n0 * 2 ** l, generator=g) for l in range(levels)]
+    mask = flags.repeat_interleave(32, 1).repeat_interleave(32, 2)[:, None]
+    gout = torch.randn(3, C, R, R, generator=g) * mask
+    w_abs = torch.rand(levels, generator=g)
+    res = []
+    for p in (None, plan):
+        pf_g = cl_planes(pf).requires_grad_(True)
+        coefs_g = [cl_coefs(c).requires_grad_(True) for c in coefs]
+        out, abs_sums = build_planes_with_abs(pf_g, coefs_g, p)
+        ((out * gout).sum() + (abs_sums * w_abs).sum()).backward()
+        res.append((out.detach(), abs_sums.detach(), pf_g.grad, [c.grad for c in coefs_g]))
+    (o_d, a_d, gp_d, gc_d), (o_s, a_s, gp_s, gc_s) = res
+    assert torch.equal(torch.where(mask, o_s, 0.0), torch.where(mask, o_d, 0.0))
+    assert rel_l2(a_s, a_d) <= 1e-5
+    assert torch.equal(gp_s, gp_d)
+    for a, b in zip(gc_s, gc_d):
+        assert torch.equal(a, b)
+
+
+def test_ray_feeder_and_get_rays_host_code(emu, golden_dir):
+    from oracle import rays as R
+    from trinerflet_b200 import rays
+    gold = np.load(os.path.join(golden_dir, "rays_ref.npz"))
+    H, W, bs = 37, 53, int(gold["C_bs"])
+    poses = torch.from_numpy(gold["B_poses"])
+    images = torch.from_numpy(gold["C_images"]).view(4, H, W, 4)
+    feeder = rays.RayFeeder(poses, gold["B_intr"], H, W, images)
+    assert feeder.steps_per_epoch(bs) == 8
+    feeder.shuffle(perm=torch.from_numpy(gold["C_perm"]))
+    for b in (0, 3, 7):
+        data = feeder.select_batch(b, bs)
+        assert np.array_equal(data["rays_o"][0].numpy(), gold[f"C_b{b}_rays_o"])
+        assert np.array_equal(data["rays_d"][0].numpy(), gold[f"C_b{b}_rays_d"])
+        assert np.array_equal(data["images"][0].numpy(), gold[f"C_b{b}_images"])
+    f0 = rays.RayFeeder(poses, gold["B_intr"], H, W, images, seed=3).shuffle()
+    assert torch.equal(torch.sort(f0.perm).values, torch.arange(4 * H * W))
+    whole = f0.select_batch(2, 1001)
+    parts = [rays.RayFeeder(poses, gold["B_intr"], H, W, images, seed=3, rank=r, world_size=2).shuffle().select_batch(2, 1001)
+             for r in range(2)]
+    assert parts[0]["rays_d"].shape[1] == 501 and parts[1]["rays_d"].shape[1] == 500
+    for k in ("rays_o", "rays_d", "images"):
+        assert torch.equal(torch.cat([parts[0][k], parts[1][k]], 1), whole[k])
+    bufs = tuple(torch.full((1001, w), float("nan")) for w in (3, 3, 4))
+    f0.select_batch(2, 1001, out=bufs)
+    assert torch.equal(bufs[1], whole["rays_d"][0]) and torch.equal(bufs[2], whole["images"][0])
+    with pytest.raises(RuntimeError):
+        f0.select_batch(2, 1001, out=tuple(torch.zeros(10, w) for w in (3, 3, 4)))
+
+    # get_rays: the reference's signature, result dict and index-selection branches
+    def check(res, n):
+        assert res["rays_o"].shape == (4, n, 3) and res["rays_d"].shape == (4, n, 3) and res["inds"].shape == (4, n)
+        inds = res["inds"].numpy()
+        assert inds.min() >= 0 and inds.max() < H * W
+        o, d, _ = R.get_rays_np(gold["B_poses"], gold["B_intr"], H, W, inds)
+        assert np.array_equal(res["rays_o"].numpy(), o) and np.array_equal(res["rays_d"].numpy(), d)
+
+    res = rays.get_rays(poses, gold["B_intr"], H, W, -1)
+    check(res, H * W)
+    assert np.array_equal(res["rays_d"].numpy(), gold["B_full_d"])
+    torch.manual_seed(11)
+    res = rays.get_rays(poses, gold["B_intr"], H, W, 257)                # the draw make_rays_golden.py recorded (utils.py:115)
+    check(res, 257)
+    assert np.array_equal(res["inds"].numpy(), gold["B_inds"]) and np.array_equal(res["rays_d"].numpy(), gold["B_rays_d"])
+    check(rays.get_rays(poses, gold["B_intr"], H, W, 10 ** 9), H * W)
+    res = rays.get_rays(poses, gold["B_intr"], H, W, 160, patch_size=4)
+    check(res, 160)
+    p = res["inds"][0].view(10, 16)
+    assert torch.equal(p - p[:, :1], (torch.arange(4).view(4, 1) * W + torch.arange(4)).view(1, 16).expand(10, 16))
+    res = rays.get_rays(poses, gold["B_intr"], H, W, 64, error_map=torch.rand(4, 128 * 128, generator=torch.Generator().manual_seed(1)))
+    check(res, 64)
+    assert res["inds_coarse"].shape == (4, 64)
+
+
+# ------------------------------------------------------------------------------------------------ world_size 2 (gloo)
+def _exchange_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from _pytest.monkeypatch import MonkeyPatch
+    mpatch = MonkeyPatch()
+    try:
+        emu_backend.install(mpatch)
+        os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from tests.util import cl_planes
+        from trinerflet_b200 import parallel
+        net = _model(radius=0.5)
+        R, C = net.encoder.plane_resolution, net.encoder.number_of_features
+        ok = True
+        for transport, tol in ((torch.float32, 0.0), (torch.bfloat16, 8e-3)):
+            red = parallel.PlaneGradReducer(net, world, check=True, transport=transport).refresh()
+            nt = R // red.tile
+            flags = torch.zeros(3 * nt * nt, dtype=torch.bool)
+            flags[red.tile_ids.long()] = True
+            mask = flags.view(3, nt, nt).repeat_interleave(red.tile, 1).repeat_interleave(red.tile, 2)[:, None]
+            gens = [torch.Generator().manual_seed(100 + r) for r in range(world)]
+            grads = [torch.randn(3, C, R, R, generator=g) * mask for g in gens]          # what each rank's scatter produced
+            mine = cl_planes(grads[rank].clone())
+            red.reduce_(mine)
+            want = sum(grads) / world
+            err = ((mine - want).norm() / want.norm()).item()
+            ok = ok and (torch.equal(mine, want) if tol == 0.0 else err <= tol) and 0 < red.fraction < 0.7
+            # a gradient outside the dirty tiles must trip the debug check
+            bad = cl_planes(torch.ones(3, C, R, R))
+            try:
+                red.reduce_(bad)
+                ok = ok and bool(mask.all())
+            except RuntimeError:
+                pass
+        out[rank] = bool(ok)
+        dist.destroy_process_group()
+    finally:
+        mpatch.undo()
+
+
+def test_sparse_plane_gradient_exchange_world2_gloo():
+    """PlaneGradReducer (mark tiles -> pack -> all-reduce -> unpack/average) between two ranks over gloo, with the pack /
+    unpack / mark kernels running on the host build: fp32 transport reproduces the dense average exactly, bf16 transport
+    stays inside its stated rounding."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_exchange_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] and out[1]

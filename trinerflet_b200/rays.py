@@ -115,9 +115,8 @@ class RayFeeder:
     into contiguous slices for the ray-sharded multi-GPU step (every rank draws the same permutation from `seed`)."""
 
     def __init__(self, poses, intrinsics, H, W, images=None, seed=None, rank=0, world_size=1):
-        if not poses.is_cuda:
-            raise RuntimeError("RayFeeder: poses must be a CUDA tensor (no CPU path)")
         self.poses = poses.contiguous().float()
+        _lib.ptr(self.poses)                               # raises unless the poses live on a CUDA device: there is no CPU path
         self.intrinsics = _intr(intrinsics)
         self.H, self.W = int(H), int(W)
         self.B = self.poses.shape[0]
