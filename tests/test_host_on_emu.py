@@ -260,3 +260,79 @@ def test_sparse_plane_gradient_exchange_world2_gloo():
     out = mgr.dict()
     mp.spawn(_exchange_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+def _train_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from _pytest.monkeypatch import MonkeyPatch
+    mpatch = MonkeyPatch()
+    try:
+        emu_backend.install(mpatch)
+        os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from trinerflet_b200 import parallel, scene, trainer
+        N = 256
+        sc = scene.make_scene()
+        ro, rd, tgt = scene.sample_batch(sc, N, torch.Generator().manual_seed(0))
+        opt = trainer.default_opt(fp16=False)
+        # reference: the whole batch on one rank (no exchange)
+        ref = _model()
+        ref.train()
+        torch.manual_seed(5)
+        loss_ref = trainer.TrainStep(ref, opt, None).forward_backward(ro, rd, tgt, update_grid=False)
+        # this rank's shard through the ray-sharded step (dirty-tile exchange of the plane gradient, fp32 transport)
+        net = _model()
+        net.train()
+        lo, hi = parallel.shard_range(N, rank, world)
+        ts = trainer.TrainStep(net, opt, None, world_size=world, check_sparse=True, transport=torch.float32)
+        torch.manual_seed(5)
+        torch.rand(lo)                                   # skip the jitter values of the rays before this shard
+        loss = ts.forward_backward(ro[lo:hi], rd[lo:hi], tgt[lo:hi], update_grid=False)
+        # shards have equal size: the average of the per-rank mean losses / gradients is the full-batch mean
+        lt = loss.clone()
+        dist.all_reduce(lt)
+        ok = abs(float(lt) / world - float(loss_ref)) <= 1e-5 * abs(float(loss_ref))
+        for (n, p), q in zip(net.named_parameters(), ref.parameters()):
+            ok = ok and p.grad is not None and rel_l2(p.grad, q.grad) <= 2e-5
+        out[rank] = bool(ok)
+        dist.destroy_process_group()
+    finally:
+        mpatch.undo()
+
+
+def test_ray_sharded_training_step_world2_equals_single_rank():
+    """two ranks, half of the rays each, replicated parameters; render backward -> dirty-tile exchange of the
+    plane gradient (gloo here, NCCL on the box) -> IDWT backward; MLP gradients in one bucket.  Loss and every parameter
+    gradient equal the single-rank step on the whole batch."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_train_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] and out[1]
+
+
+def test_worklist_training_step_equals_dense_step(emu):
+    """the optimised steady-state step (work-list IDWT forward, SplitIdwtBackward: clean part + active part, |yh| sums
+    completed by the backward, gap lists) against the dense step on the same rays: same loss, same gradients"""
+    from trinerflet_b200 import scene, trainer
+    sc = scene.make_scene()
+    N = 300
+    ro, rd, tgt = scene.sample_batch(sc, N, torch.Generator().manual_seed(2))
+    res = []
+    for sparse in (False, True):
+        net = _model(radius=0.45)
+        net.train()
+        ts = trainer.TrainStep(net, trainer.default_opt(fp16=False), None)
+        ts.sparse_idwt = sparse
+        ts.plan_on_any_device = True
+        torch.manual_seed(9)
+        loss = ts.forward_backward(ro, rd, tgt, update_grid=False)
+        res.append((float(loss), [p.grad.clone() for p in net.parameters()], ts))
+    (l_d, g_d, _), (l_s, g_s, ts) = res
+    assert ts._plan is not None and 0 < ts._plan.stats["tile_fraction"] < 1
+    assert abs(l_s - l_d) <= 1e-6 * abs(l_d)
+    for a, b in zip(g_s, g_d):
+        assert rel_l2(a, b) <= 1e-6

@@ -60,6 +60,7 @@ class TrainStep:
         # (idwt_plan.py); steps that refresh the density grid query the field everywhere and stay dense
         self.sparse_idwt = True
         self._plan = None
+        self.plan_on_any_device = False   # test hook: the CPU suite runs the work-list step over the host build of the kernels
         self._graphs = None
 
     # ---- the three segments of a step ---------------------------------------------------------------------------------
@@ -80,7 +81,8 @@ class TrainStep:
         enc.reset_cahce()
         do_update = (self.global_step % opt.update_extra_interval == 0) if update_grid is None else update_grid
         enc.idwt_plan = None
-        use_plan = self.sparse_idwt and not do_update and rays_o.is_cuda and model.cuda_ray and self._plan_supported()
+        use_plan = (self.sparse_idwt and not do_update and (rays_o.is_cuda or self.plan_on_any_device) and model.cuda_ray
+                    and self._plan_supported())
         if use_plan:
             if self._plan is None:
                 self.refresh_plan()
