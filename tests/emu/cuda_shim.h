@@ -18,7 +18,9 @@
 #include <string.h>
 #include <ucontext.h>
 
+#include <algorithm>
 #include <functional>
+#include <utility>
 #include <vector>
 
 #define TNL_KERNEL_EMU 1
@@ -133,6 +135,7 @@ struct Runtime {
     size_t stack_bytes = 64 * 1024;
     unsigned long long progress = 0;   // bumped by every arrival at a rendezvous and every thread exit
     std::vector<uint64_t> dyn_smem;    // dynamic shared memory of the running launch (16-byte aligned, see dyn_smem())
+    std::vector<unsigned> order;       // resume order of the fibers of a block (TNL_EMU_SCHED)
 };
 
 inline Runtime& rt() {
@@ -243,9 +246,24 @@ inline void run_block(unsigned nthreads, const std::function<void()>& body) {
     }
     unsigned remaining = nthreads;
     unsigned idle_rounds = 0;
+    // race check: TNL_EMU_SCHED=reverse | random[:seed] changes the order in which runnable threads are resumed.  A kernel
+    // whose result depends on it (beyond the order of float atomics) is missing a barrier.
+    static const int sched = [] {
+        const char* e = getenv("TNL_EMU_SCHED");
+        if (e == nullptr) return 0;
+        if (strncmp(e, "reverse", 7) == 0) return 1;
+        if (strncmp(e, "random", 6) == 0) { srand(e[6] == ':' ? (unsigned)atoi(e + 7) : 1u); return 2; }
+        return 0;
+    }();
+    std::vector<unsigned>& order = r.order;
+    order.resize(nthreads);
+    for (unsigned t = 0; t < nthreads; ++t) order[t] = sched == 1 ? nthreads - 1 - t : t;
     while (remaining > 0) {
         const unsigned long long before = r.progress;
-        for (unsigned t = 0; t < nthreads; ++t) {
+        if (sched == 2)
+            for (unsigned t = nthreads; t > 1; --t) std::swap(order[t - 1], order[(unsigned)rand() % t]);
+        for (unsigned k = 0; k < nthreads; ++k) {
+            const unsigned t = order[k];
             Fiber& f = r.fibers[t];
             if (f.done) continue;
             r.cur = &f;
