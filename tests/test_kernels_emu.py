@@ -551,3 +551,98 @@ def test_device_driven_inference_loop_equals_host_driven(scene, max_steps, chunk
     assert _bits_equal(ws_d, ws_h) and _bits_equal(dp_d, dp_h) and _bits_equal(im_d, im_h) and _bits_equal(rt_d, rt_h)
     if max_steps == 48:
         assert it_h < 48     # the step budget, not the alive count, ended this one
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+def test_edge_cases_empty_single_and_degenerate_inputs(scene):
+    """empty and one-element inputs, rays that miss the box, zero / out-of-range n_valid, dead and full alive lists, tails
+    of the vectorised kernels -- the cases where index arithmetic usually breaks (run under tests/emu/run_asan.sh too)"""
+    o, d, bits, nears, fars = scene
+    z = None
+    # N = 0 everywhere: nothing is launched, nothing is touched
+    e3, e1 = np.zeros((0, 3), np.float32), np.zeros(0, np.float32)
+    kemu.call("tnl_near_far_from_aabb", e3, e3, AABB, 0, 0.2, e1, e1, z)
+    kemu.call("tnl_packbits", e1, 0, 0.5, np.zeros(0, np.uint8), z)
+    kemu.call("tnl_sample_planes_forward", np.zeros((3, 4, 4, 8), np.float32), e3, 0, 4, 8, 1.0, 0, z, z, np.zeros((0, 24), np.float32), 0, z)
+    kemu.call("tnl_tiles_pack", np.zeros((3, 32, 32, 8), np.float32), np.zeros(0, np.int32), 0, 32, 8, 32, np.zeros(0, np.float32), 0, z)
+    # one ray; a ray that points away from the box (far < near -> no samples, count 0)
+    o1 = np.array([[0.0, 0.0, 4.0], [0.0, 0.0, 4.0]], np.float32)
+    d1 = np.array([[0.0, 0.0, -1.0], [0.0, 0.0, 1.0]], np.float32)
+    n1, f1 = np.empty(2, np.float32), np.empty(2, np.float32)
+    kemu.call("tnl_near_far_from_aabb", o1, d1, AABB, 2, 0.2, n1, f1, z)
+    n_o, f_o = orc.near_far_from_aabb(o1, d1, AABB, 0.2)
+    assert _bits_equal(n1, n_o) and _bits_equal(f1, f_o) and n1[0] == 2.5 and f1[0] == 5.5 and f1[1] < n1[1]   # box behind the ray
+    full = np.full_like(bits, 255)
+    for n in (1, 2):
+        x, _, dl, rays, cnt = _march_train(o1[:n], d1[:n], full, n1[:n], f1[:n], np.zeros(n, np.float32), 2048)
+        r_o = orc.march_rays_train(o1[:n], d1[:n], BOUND, full, CAS, H, n1[:n], f1[:n], np.zeros(n, np.float32), 2048)[3]
+        assert np.array_equal(rays, r_o) and rays[0, 2] > 100 and cnt[1] == n
+        if n == 2:
+            assert rays[1, 2] == 0
+    # max_steps = 1: exactly one sample per hitting ray
+    *_, rays, cnt = _march_train(o1, d1, full, n1, f1, np.zeros(2, np.float32), 128, 0.0, 1)
+    assert rays[0, 2] == 1 and rays[1, 2] == 0 and cnt[0] == 1
+    # compositing: a ray without samples, zero density, and a wall that saturates at the first sample
+    rays3 = np.array([[0, 0, 0], [1, 0, 4], [2, 4, 4]], np.int32)
+    deltas = np.full((8, 2), 0.01, np.float32)
+    sig = np.concatenate([np.zeros(4), np.full(4, 1e6)]).astype(np.float32)
+    rgb = np.full((8, 3), 0.5, np.float32)
+    ws, dp, im = np.full(3, -1, np.float32), np.full(3, -1, np.float32), np.full((3, 3), -1, np.float32)
+    kemu.call("tnl_composite_rays_train_forward", sig, rgb, deltas, rays3, 8, 3, 1e-4, ws, dp, im, z)
+    ws_o, dp_o, im_o = orc.composite_rays_train_forward(sig, rgb, deltas, rays3, 1e-4)
+    assert np.allclose(ws, ws_o, atol=1e-6) and np.allclose(im, im_o, atol=1e-6) and np.allclose(dp, dp_o, atol=1e-6)
+    assert ws[0] == 0 and ws[1] == 0 and abs(ws[2] - 1) < 1e-6
+    gs, gc = np.full(8, 9, np.float32), np.full((8, 3), 9, np.float32)
+    kemu.call("tnl_composite_rays_train_backward", np.ones(3, np.float32), np.ones((3, 3), np.float32), sig, rgb, deltas, rays3, ws, im,
+              8, 3, 1e-4, gs, gc, z)
+    gs_o, gc_o = orc.composite_rays_train_backward(np.ones(3, np.float32), np.ones((3, 3), np.float32), sig, rgb, deltas, rays3, ws_o,
+                                                   im_o, 1e-4)
+    assert np.allclose(gs[:5], gs_o[:5], atol=1e-5) and np.allclose(gc[:5], gc_o[:5], atol=1e-6)
+    # alive-list compaction: all dead, all alive, a single element
+    work = np.zeros(64, np.uint8)
+    for alive in (np.full(37, -1, np.int32), np.arange(37, dtype=np.int32), np.array([5], np.int32), np.array([-1], np.int32)):
+        out, cnt = np.full(len(alive), -7, np.int32), np.full(1, -7, np.int32)
+        kemu.call("tnl_compact_alive", alive, len(alive), out, cnt, work, work.size, z)
+        keep = alive[alive >= 0]
+        assert cnt[0] == len(keep) and np.array_equal(out[:len(keep)], keep) and (out[len(keep):] == -7).all()
+    # sampling: n_valid = 0, n_valid beyond M, negative n_valid; points outside the box clamp to the border texels
+    g = torch.Generator().manual_seed(3)
+    planes = torch.randn(3, 8, 16, 16, generator=g)
+    xyz = torch.tensor([[9.0, -9.0, 0.3], [-1.5, 1.5, 1.5], [0.1, 0.2, 0.3]])
+    ref = of.sample_planes(planes, xyz, BOUND).numpy()
+    inv_bound = float(np.float32(1.0) / np.float32(BOUND))
+    for nv, rows in ((0, 0), (-4, 0), (2, 2), (99, 3)):
+        feat = np.full((3, 24), np.nan, np.float32)
+        kemu.call("tnl_sample_planes_forward", _cl(planes), xyz.numpy(), 3, 16, 8, inv_bound, 0, np.array([nv], np.int32), z, feat, 0, z)
+        assert np.allclose(feat[:rows], ref[:rows], atol=1e-6) and (feat[rows:] == 0).all()
+        gp = np.zeros((3, 16, 16, 8), np.float32)
+        kemu.call("tnl_sample_planes_backward", np.ones((3, 24), np.float32), 0, xyz.numpy(), 3, 16, 8, inv_bound, 0,
+                  np.array([nv], np.int32), z, gp, z)
+        assert abs(gp.sum() - rows * 24) <= 1e-4                       # bilinear weights of a point sum to one per channel
+    # cell sort: one point; many points in one cell
+    for pts in (np.zeros((1, 3), np.float32), np.full((300, 3), 0.01, np.float32)):
+        perm = np.full(len(pts), -1, np.int32)
+        wsz = kemu.lib().tnl_cell_sort_workspace(len(pts), 64)
+        wk = np.zeros(max(wsz, 16), np.uint8)
+        kemu.call("tnl_cell_sort", pts, len(pts), z, inv_bound, 64, perm, wk, wk.size, z)
+        assert np.array_equal(np.sort(perm), np.arange(len(pts)))
+    # optimizer: lengths below / off the 4-wide vector path
+    for n in (1, 3, 5, 1023):
+        p, m, v = np.ones(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+        gr = np.full(n, 0.5, np.float32)
+        state = np.zeros(4, np.float32)
+        kemu.call("tnl_adam_prepare", state, z, 0.9, 0.99, z)
+        kemu.call("tnl_adam_step", p, gr, m, v, u64(n), z, z, state, 1e-2, 0.9, 0.99, 1e-15, 0.0, z)
+        assert np.allclose(p, 1 - 1e-2, atol=1e-6) and np.allclose(m, 0.05, atol=1e-7)   # first Adam step moves by lr * sign(g)
+        found = np.zeros(1, np.float32)
+        gr[n - 1] = np.nan
+        kemu.call("tnl_grad_nonfinite", gr, u64(n), found, z)
+        assert found[0] == 1.0
+    # IDWT: smallest supported level; unsupported geometry is an argument error, not a launch
+    lib = kemu.lib()
+    x, yh, out = np.zeros((3, 8, 8, 8), np.float32), np.zeros((3, 3, 8, 8, 8), np.float32), np.full((3, 16, 16, 8), np.nan, np.float32)
+    x[:] = 1.0
+    kemu.call("tnl_idwt_level_forward", x, yh, out, 8, 8, z, z)
+    assert abs(out[:, 8, 8, :].mean() - 1.0) < 1e-5                    # DC gain 1 in the interior (IDWT(2*c, 0) = c)
+    assert lib.tnl_idwt_level_forward(kemu.p(x), kemu.p(yh), kemu.p(out), 12, 8, None, None) == -1
+    assert lib.tnl_idwt_level_forward(kemu.p(x), kemu.p(yh), kemu.p(out), 8, 12, None, None) == -1
