@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=0, help="rays per GPU per step (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-next-rows", action="store_true", help="skip the extras.next_rows measurements (feeder, render loops)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU work for the cpu_baseline leg")
     return ap.parse_args()
@@ -226,6 +227,66 @@ def run_reference(args, cfg, n_rays):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def next_rows(args, net, ts, sc, n_rays, dev, use_graph):
+    """Step feeder (rays + targets generated on the device into the captured step's inputs) and full-frame inference with
+    the host-driven / device-driven loop.  Reported under extras only."""
+    import torch
+    from trinerflet_b200 import rays, scene
+    out = {}
+    try:
+        if use_graph:
+            H, W = scene.H_IMG, scene.W_IMG
+            images = torch.rand(sc.poses.shape[0], H * W, 3, device=dev)          # resident targets (768 MB fp32)
+            feeder = rays.RayFeeder(sc.poses.to(dev), sc.intrinsics, H, W, images, seed=0).shuffle()
+            for b in range(3):
+                ts.replay_from_feeder(feeder, b, n_rays).item()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for b in range(args.steps):
+                ts.replay_from_feeder(feeder, 3 + b, n_rays).item()
+            e1.record()
+            torch.cuda.synchronize()
+            out["e2e_device_feeder_rays_per_s"] = n_rays / (e0.elapsed_time(e1) / args.steps * 1e-3)
+            out["e2e_device_feeder_note"] = "rays_o / rays_d / targets generated by tnl_rays_from_ids into the graph's static inputs, loss read back every step; 0 H2D bytes per step"
+            del feeder, images
+    except Exception as ex:  # pragma: no cover
+        out["e2e_device_feeder_rays_per_s"] = f"failed: {ex}"
+    try:
+        net.eval()
+        ro, rd = scene.full_frame(sc, 0)
+        ro, rd = ro.to(dev), rd.to(dev)
+        ref = None
+        for chunk in (0, 8):
+            net.infer_chunk = chunk
+
+            def frame():
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+                    return net.render(ro.unsqueeze(0), rd.unsqueeze(0), staged=True, bg_color=1, perturb=False, max_steps=1024)
+
+            img = frame()["image"]
+            ref = img if ref is None else ref
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(2):
+                frame()
+            e1.record()
+            torch.cuda.synchronize()
+            key = "host_loop" if chunk == 0 else f"device_loop_chunk{chunk}"
+            out[f"render_800x800_ms_{key}"] = round(e0.elapsed_time(e1) / 2, 3)
+            if chunk:
+                out["render_max_abs_diff_between_loops"] = float((img - ref).abs().max())
+                out["render_iterations"] = net.last_infer_loop.iterations_done
+                out["render_state_reads"] = net.last_infer_loop.reads
+    except Exception as ex:  # pragma: no cover
+        out["render"] = f"failed: {ex}"
+    finally:
+        net.infer_chunk = 0
+        net.train()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -442,6 +503,10 @@ def main():
             "clocks": clk, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
         }
+        # ---- the two "next" rows, outside the metric; N = 1 only.  Everything the contract line needs
+        # has been computed above: a failure in here can only turn into a "failed: ..." string inside extras ----
+        if world == 1 and not args.no_next_rows:
+            extras["next_rows"] = next_rows(args, net, ts, sc, n_rays, dev, use_graph)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

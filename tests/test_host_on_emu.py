@@ -336,3 +336,38 @@ def test_worklist_training_step_equals_dense_step(emu):
     assert abs(l_s - l_d) <= 1e-6 * abs(l_d)
     for a, b in zip(g_s, g_d):
         assert rel_l2(a, b) <= 1e-6
+
+
+def test_bench_next_rows_render_section_runs(emu, monkeypatch):
+    """bench.py's extras.next_rows (render part) executed on the host build with a small frame and fake CUDA events: the
+    keys the bench reports exist and both loops agree.  (The feeder part needs a captured CUDA graph: GPU only.)"""
+    import types
+    import bench
+    from trinerflet_b200 import scene
+
+    class FakeEvent:
+        def __init__(self, enable_timing=False):
+            pass
+
+        def record(self):
+            pass
+
+        def elapsed_time(self, other):
+            return 2.0
+
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    full = scene.full_frame
+
+    def small_frame(sc, idx=0):
+        ro, rd = full(sc, idx)
+        pick = torch.arange(0, ro.shape[0], 1601)
+        return ro[pick].contiguous(), rd[pick].contiguous()
+
+    monkeypatch.setattr(scene, "full_frame", small_frame)
+    net = _model()
+    net.train()
+    out = bench.next_rows(types.SimpleNamespace(steps=2), net, None, scene.make_scene(), 64, torch.device("cpu"), use_graph=False)
+    assert out["render_800x800_ms_host_loop"] == 1.0 and out["render_800x800_ms_device_loop_chunk8"] == 1.0, out
+    assert out["render_max_abs_diff_between_loops"] == 0.0 and out["render_state_reads"] < out["render_iterations"]
+    assert net.training and net.infer_chunk == 0

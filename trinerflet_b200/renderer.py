@@ -106,7 +106,8 @@ class NeRFRenderer(nn.Module):
                 # buffers live for the whole frame; identical per-ray results (opt-in: model.infer_chunk = 8)
                 loop = raymarching.DeviceRayLoop(rays_o, rays_d, nears, fars, self.bound, self.density_bitfield, self.cascade,
                                                  self.grid_size, dt_gamma, max_steps, perturb)
-                while True:
+                # every live iteration marches >= 1 sample per ray, so the loop needs at most max_steps iterations
+                for _ in range(-(-int(max_steps) // chunk) + 1):
                     for _ in range(chunk):
                         xyzs, dirs = loop.begin_iteration()
                         sigmas, rgbs = self(xyzs, dirs, n_valid=loop.n_valid)
@@ -114,6 +115,8 @@ class NeRFRenderer(nn.Module):
                         loop.end_iteration(sigmas, rgbs, weights_sum, depth, image, T_thresh)
                     if loop.poll():
                         break
+                else:
+                    raise RuntimeError("device-driven inference loop did not terminate")
                 self.last_infer_loop = loop
                 n_alive = 0
             else:
