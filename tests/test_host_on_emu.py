@@ -371,3 +371,40 @@ def test_bench_next_rows_render_section_runs(emu, monkeypatch):
     assert out["render_800x800_ms_host_loop"] == 1.0 and out["render_800x800_ms_device_loop_chunk8"] == 1.0, out
     assert out["render_max_abs_diff_between_loops"] == 0.0 and out["render_state_reads"] < out["render_iterations"]
     assert net.training and net.infer_chunk == 0
+
+
+def test_mark_untrained_grid_matches_brute_force(emu):
+    """NeRFRenderer.mark_untrained_grid (renderer.py:383-446) against a direct evaluation of the visibility rule over all
+    128^3 x cascade cells (Morton order from the oracle)"""
+    from oracle import raymarch as orc
+    from trinerflet_b200 import scene
+    net = _model()
+    sc = scene.make_scene()
+    poses = sc.poses[:3]
+    net.density_grid.fill_(0.5)
+    net.mark_untrained_grid(poses, sc.intrinsics)
+    fx, fy, cx, cy = sc.intrinsics
+    H = net.grid_size
+    a = np.arange(H, dtype=np.int32)
+    xx, yy, zz = np.meshgrid(a, a, a, indexing="ij")
+    coords = np.stack([xx.reshape(-1), yy.reshape(-1), zz.reshape(-1)], -1)
+    idx = orc.morton3D(coords).astype(np.int64)
+    world = torch.from_numpy(2 * coords.astype(np.float32) / (H - 1) - 1)
+    unseen_total = 0
+    for cas in range(net.cascade):
+        bound = min(2 ** cas, net.bound)
+        hgs = bound / H
+        pts = world * (bound - hgs)
+        seen = torch.zeros(H ** 3, dtype=torch.bool)
+        for b in range(poses.shape[0]):
+            cam = (pts - poses[b, :3, 3]) @ poses[b, :3, :3]
+            seen |= (cam[:, 2] > 0) & (cam[:, 0].abs() < cx / fx * cam[:, 2] + hgs * 2) & (cam[:, 1].abs() < cy / fy * cam[:, 2] + hgs * 2)
+        want = np.full(H ** 3, 0.5, np.float32)
+        want[idx[~seen.numpy()]] = -1.0
+        assert np.array_equal(net.density_grid[cas].numpy(), want)
+        unseen_total += int((~seen).sum())
+    assert 0 < unseen_total < net.cascade * H ** 3
+    # cells marked -1 stay out of the occupancy bitfield and are skipped by the EMA update (renderer.py:526-527)
+    net.iter_density = 16
+    net.update_extra_state()
+    assert bool((net.density_grid[net.density_grid < 0] == -1).all()) and int((net.density_grid < 0).sum()) == unseen_total
