@@ -74,6 +74,7 @@ struct Warp {
     unsigned mask = 0;        // member mask of the current rendezvous (taken from its first arriver)
     unsigned gen = 0;
     uint64_t slot[32];
+    uint32_t wide[32][8];     // per-lane operand registers of the emulated warp-wide PTX instructions (mma / ldmatrix)
 };
 
 struct Block {
@@ -371,6 +372,58 @@ inline unsigned warp_vote(unsigned mask, bool pred) {
     return bits;
 }
 
+// ---- warp-wide PTX instructions of the mma.sync kernels (csrc/mlp.cu); substituted for the asm by gen_kemu.py ----
+inline float half_bits_to_float(uint32_t v, int hi) {
+    const uint16_t b = hi ? (uint16_t)(v >> 16) : (uint16_t)(v & 0xffffu);
+    _Float16 h;
+    memcpy(&h, &b, 2);
+    return (float)h;
+}
+
+// mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32: D = A(16x16, row) * B(16x8, col) + D.  Fragment layout (g = lane / 4,
+// t = lane % 4): a0 (g, 2t..2t+1)  a1 (g+8, 2t..)  a2 (g, 2t+8..)  a3 (g+8, 2t+8..);  b0 (k 2t..2t+1, n g)  b1 (k 2t+8.., n g);
+// d0 (g, 2t)  d1 (g, 2t+1)  d2 (g+8, 2t)  d3 (g+8, 2t+1).  Products of fp16 values are exact in fp32; the sum is formed in
+// fp64 and rounded once (the tensor core's internal accumulation order is not specified; tests carry fp16 tolerances).
+inline void mma_m16n8k16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    unsigned lane;
+    Warp& w = my_warp(lane);
+    for (int i = 0; i < 4; ++i) w.wide[lane][i] = a[i];
+    w.wide[lane][4] = b0;
+    w.wide[lane][5] = b1;
+    warp_barrier(w, lane, 0xffffffffu);
+    const int g = (int)lane >> 2, t = (int)lane & 3;
+    float out[4];
+    for (int i = 0; i < 4; ++i) {
+        const int m = g + 8 * (i >> 1), n = 2 * t + (i & 1);
+        double acc = (double)d[i];
+        for (int k = 0; k < 16; ++k) {
+            const float av = half_bits_to_float(w.wide[(m & 7) * 4 + ((k & 7) >> 1)][(m >> 3) + 2 * (k >> 3)], k & 1);
+            const float bv = half_bits_to_float(w.wide[n * 4 + ((k & 7) >> 1)][4 + (k >> 3)], k & 1);
+            acc += (double)av * (double)bv;
+        }
+        out[i] = (float)acc;
+    }
+    warp_barrier(w, lane, 0xffffffffu);
+    for (int i = 0; i < 4; ++i) d[i] = out[i];
+}
+
+// ldmatrix.sync.aligned.m8n8.xN.trans.shared.b16: lane 8j+i supplies the address of row i of matrix j (8 halves);
+// with .trans thread (g, t) receives r[j] = { M_j[2t][g], M_j[2t+1][g] }
+template <int NMAT>
+inline void ldmatrix_trans(uint32_t (&r)[NMAT], const void* row_ptr) {
+    unsigned lane;
+    Warp& w = my_warp(lane);
+    w.slot[lane] = (uint64_t)reinterpret_cast<uintptr_t>(row_ptr);
+    warp_barrier(w, lane, 0xffffffffu);
+    const int g = (int)lane >> 2, t = (int)lane & 3;
+    for (int j = 0; j < NMAT; ++j) {
+        const uint16_t* r0 = reinterpret_cast<const uint16_t*>((uintptr_t)w.slot[8 * j + 2 * t]);
+        const uint16_t* r1 = reinterpret_cast<const uint16_t*>((uintptr_t)w.slot[8 * j + 2 * t + 1]);
+        r[j] = (uint32_t)r0[g] | ((uint32_t)r1[g] << 16);
+    }
+    warp_barrier(w, lane, 0xffffffffu);
+}
+
 inline unsigned lane_id() {
     unsigned lane;
     my_warp(lane);
@@ -480,6 +533,15 @@ static inline __half __float2half(float f) { return __float2half_rn(f); }
 static inline float __half2float(__half h) { return (float)h.v; }
 static inline __half2 __floats2half2_rn(float a, float b) { __half2 r; r.x = __float2half_rn(a); r.y = __float2half_rn(b); return r; }
 static inline float2 __half22float2(__half2 h) { return float2{__half2float(h.x), __half2float(h.y)}; }
+
+static inline __half2 __float2half2_rn(float a) { return __floats2half2_rn(a, a); }
+static inline __half2 __hmax2(__half2 a, __half2 b) {
+    __half2 r;
+    r.x.v = a.x.v > b.x.v ? a.x.v : b.x.v;
+    r.y.v = a.y.v > b.y.v ? a.y.v : b.y.v;
+    return r;
+}
+static inline size_t __cvta_generic_to_shared(const void* p) { return reinterpret_cast<size_t>(p); }
 
 struct __nv_bfloat16 {
     uint16_t bits;

@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "trinerflet_b200", "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
-SOURCES = ["api.cu", "raymarch.cu", "sample.cu", "sort.cu", "tiles.cu", "optim.cu", "grid.cu", "rays.cu", "idwt.cu"]
+SOURCES = ["api.cu", "raymarch.cu", "sample.cu", "sort.cu", "tiles.cu", "optim.cu", "grid.cu", "rays.cu", "idwt.cu", "mlp.cu"]
 # TNL_KEMU_ASAN=1: AddressSanitizer build (run the tests with LD_PRELOAD=$(gcc -print-file-name=libasan.so)
 # ASAN_OPTIONS=detect_leaks=0): out-of-bounds reads / writes of the kernels on the callers' heap buffers become hard errors
 ASAN = os.environ.get("TNL_KEMU_ASAN") == "1"
@@ -94,17 +94,44 @@ _RED = re.compile(r'asm volatile\("red\.global\.add\.v4\.f32[^;]*?;\\n"\s*::\s*"
                   r'\s*"f"\((?P<c>[^"]+?)\),\s*"f"\((?P<d>[^"]+?)\)\s*:\s*"memory"\);', re.S)
 
 
+# the three warp-wide instructions of the mma.sync MLP kernels (csrc/mlp.cu); the helper functions that wrap them name their
+# operands d / a / b and r / p
+_MMA = re.compile(r'asm volatile\(\s*"mma\.sync\.aligned\.m16n8k16\.row\.col\.f32\.f16\.f16\.f32[^;]*?;\\n"[^;]*?\);', re.S)
+_LDSM = re.compile(r'asm volatile\("ldmatrix\.sync\.aligned\.m8n8\.x(?P<n>[24])\.trans\.shared\.b16[^;]*?;\\n"[^;]*?\);', re.S)
+
+
 def rewrite_ptx(src):
     def sub(m):
         g = m.groupdict()
         return (f"{{ float* a_ = {g['addr']}; a_[0] += {g['a']}; a_[1] += {g['b']}; a_[2] += {g['c']}; a_[3] += {g['d']}; }}")
     src, n = _RED.subn(sub, src)
+    src, k = _MMA.subn("tnl_emu::mma_m16n8k16(d, a, b.x, b.y);", src)
+    n += k
+    src, k = _LDSM.subn(lambda m: f"tnl_emu::ldmatrix_trans<{m.group('n')}>(r, p);", src)
+    n += k
     if "asm" in re.sub(r"//.*", "", src):
         raise RuntimeError("inline PTX the emulator does not know")
     return src, n
 
 
 _DYN_SMEM = re.compile(r'extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];')
+
+
+# the tcgen05 implementation (csrc/mlp_tc.cu) cannot be emulated: the host build reports it as unsupported, so the C ABI
+# dispatches every call to the mma.sync kernels of csrc/mlp.cu
+MLP_TC_STUB = '''// GENERATED by tests/emu/gen_kemu.py -- test-only
+#include "cuda_shim.h"
+#include "mlp_tc.cuh"
+#include <stdlib.h>
+namespace tnl {
+bool mlp_tc_supported(uint32_t, uint32_t, uint32_t) { return false; }
+size_t mlp_tc_packed_bytes(uint32_t) { return 0; }
+void mlp_tc_pack(uint32_t, const float*, const float*, const float*, const float*, const float*, void*, cudaStream_t) { abort(); }
+void mlp_tc_forward(uint32_t, const void*, const void*, const float*, uint32_t, const int32_t*, float*, float*, float*, cudaStream_t) { abort(); }
+void mlp_tc_backward(uint32_t, const void*, const void*, const float*, uint32_t, const int32_t*, const float*, const float*, void*,
+                     float*, float*, float*, float*, float*, cudaStream_t) { abort(); }
+}  // namespace tnl
+'''
 
 
 def generate(name):
@@ -122,7 +149,7 @@ def generate(name):
 
 def build(force=False):
     os.makedirs(OUT_DIR, exist_ok=True)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, h) for h in ("common.cuh", "rays_core.cuh", "idwt_core.cuh")]
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, h) for h in ("common.cuh", "rays_core.cuh", "idwt_core.cuh", "mlp_math.cuh", "mlp_tc.cuh")]
     deps += [os.path.join(HERE, "cuda_shim.h"), os.path.abspath(__file__), os.path.join(ROOT, "include", "trinerflet_b200.h")]
     if not force and os.path.exists(SO) and os.path.getmtime(SO) >= max(os.path.getmtime(d) for d in deps):
         return SO
@@ -135,6 +162,12 @@ def build(force=False):
         san = ["-fsanitize=address", "-fno-omit-frame-pointer"] if ASAN else []
         procs.append(subprocess.Popen(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-w", *san, "-I", HERE,
                                        "-I", os.path.join(HERE, "shim_include"), "-I", CSRC, "-c", cpp, "-o", obj]))
+    stub = os.path.join(OUT_DIR, ("kemu_asan_" if ASAN else "kemu_") + "mlp_tc_stub.cpp")
+    with open(stub, "w") as f:
+        f.write(MLP_TC_STUB)
+    objs.append(stub.replace(".cpp", ".o"))
+    procs.append(subprocess.Popen(["g++", "-O1", "-std=c++17", "-fPIC", "-w", *(["-fsanitize=address"] if ASAN else []), "-I", HERE,
+                                   "-I", os.path.join(HERE, "shim_include"), "-I", CSRC, "-c", stub, "-o", objs[-1]]))
     for p in procs:
         if p.wait() != 0:
             raise RuntimeError("kernel emulator: compilation failed")

@@ -4,9 +4,10 @@ collectives are real rendezvous; tests/emu/gen_kemu.py rewrites only the <<<...>
 checked against the oracle exactly as the GPU tests check the device build -- at sizes the emulator finishes in seconds.
 
 What this covers without a GPU: index arithmetic, scans, compaction, tap weights, rounding order (the fp32 intrinsics map
-to correctly rounded host operations).  What it cannot cover: the tensor-core MLP kernels and the cp.async/FFMA2 IDWT
-kernels (the latter have their own emulator, tests/test_idwt_emu.py), `__expf` (libm here, ex2.approx on the device), and
-anything about performance.  The GPU tests (-m gpu) remain the parity tests proper."""
+to correctly rounded host operations), the IDWT kernels through their real entry points (cp.async / FFMA2 have host
+equivalents in idwt_core.cuh) and the mma.sync MLP kernels (the shim emulates mma.m16n8k16 and ldmatrix as warp
+collectives).  What it cannot cover: the tcgen05 MLP kernels (csrc/mlp_tc.cu), `__expf` (libm here, ex2.approx on the
+device), the tensor core's internal summation order, and anything about performance.  The GPU tests (-m gpu) remain the parity tests proper."""
 import ctypes
 import os
 
@@ -646,3 +647,82 @@ def test_edge_cases_empty_single_and_degenerate_inputs(scene):
     assert abs(out[:, 8, 8, :].mean() - 1.0) < 1e-5                    # DC gain 1 in the interior (IDWT(2*c, 0) = c)
     assert lib.tnl_idwt_level_forward(kemu.p(x), kemu.p(yh), kemu.p(out), 12, 8, None, None) == -1
     assert lib.tnl_idwt_level_forward(kemu.p(x), kemu.p(yh), kemu.p(out), 8, 12, None, None) == -1
+
+
+# ------------------------------------------------------------------------------------------------ MLP heads (mma.sync kernels)
+def _mlp_pack_emu(C, hidden, W):
+    from trinerflet_b200._lib import MlpDims
+    dims = MlpDims(3 * C, hidden, hidden)
+    nbytes = kemu.lib().tnl_mlp_packed_bytes(ctypes.byref(dims))
+    assert nbytes > 0
+    packed = np.zeros(nbytes, np.uint8)
+    kemu.call("tnl_mlp_pack_weights", ctypes.byref(dims), *[kemu.f32(w.numpy()) for w in W], packed, None)
+    return dims, packed
+
+
+@pytest.mark.parametrize("C,hidden,M", [(16, 64, 333), (32, 64, 130), (48, 128, 70)])
+def test_mlp_forward_mma_kernels_match_fp16_oracle(C, hidden, M):
+    """csrc/mlp.cu (mma.sync.m16n8k16 + fragment-ordered weights; the host build emulates the warp-wide instructions)
+    against the oracle's fp16-autocast emulation: same tolerances as tests/test_gpu_field.py"""
+    g = torch.Generator().manual_seed(C + hidden)
+    W = of.init_mlp_weights(C, hidden, hidden, gen=g)
+    feat = 0.5 * torch.randn(M, 3 * C, generator=g)
+    d = torch.randn(M, 3, generator=g)
+    d = d / d.norm(dim=-1, keepdim=True)
+    s_o, rgb_o, geo_o = of.mlp_forward(feat, d, W, fp16=True)
+    dims, packed = _mlp_pack_emu(C, hidden, W)
+    sigma, rgb, geo = np.full(M, np.nan, np.float32), np.full((M, 3), np.nan, np.float32), np.full((M, 15), np.nan, np.float32)
+    kemu.call("tnl_mlp_forward", ctypes.byref(dims), packed, feat.numpy(), 0, d.numpy(), M, None, sigma, rgb, geo, None)
+    assert np.abs(rgb - rgb_o.numpy()).max() <= 2e-3
+    assert (np.abs(sigma - s_o.numpy()) / np.maximum(np.abs(s_o.numpy()), 1e-3)).max() <= 4e-3
+    assert np.abs(geo - geo_o.numpy()).max() <= 2e-3 * max(1.0, geo_o.abs().max().item())
+    # fp16 feature stream: the same rounding point, identical outputs; n_valid: skipped rows are zeros
+    sigma_h, rgb_h = np.zeros(M, np.float32), np.zeros((M, 3), np.float32)
+    kemu.call("tnl_mlp_forward", ctypes.byref(dims), packed, feat.numpy().astype(np.float16), 1, d.numpy(), M, None, sigma_h, rgb_h,
+              None, None)
+    assert np.array_equal(sigma_h, sigma) and np.array_equal(rgb_h, rgb)
+    nv = np.array([M // 3], np.int32)
+    sigma_v, rgb_v = np.full(M, np.nan, np.float32), np.full((M, 3), np.nan, np.float32)
+    kemu.call("tnl_mlp_forward", ctypes.byref(dims), packed, feat.numpy(), 0, d.numpy(), M, nv, sigma_v, rgb_v, None, None)
+    assert np.array_equal(sigma_v[:M // 3], sigma[:M // 3]) and (sigma_v[M // 3:] == 0).all() and (rgb_v[M // 3:] == 0).all()
+    # density only (dirs = NULL)
+    sigma_d, geo_d = np.zeros(M, np.float32), np.zeros((M, 15), np.float32)
+    kemu.call("tnl_mlp_forward", ctypes.byref(dims), packed, feat.numpy(), 0, None, M, None, sigma_d, None, geo_d, None)
+    assert np.array_equal(sigma_d, sigma) and np.array_equal(geo_d, geo)
+
+
+@pytest.mark.parametrize("C,M", [(16, 300), (32, 150), (48, 77)])
+def test_mlp_backward_mma_kernels_match_fp16_oracle(C, M):
+    g = torch.Generator().manual_seed(3 + C)
+    W = of.init_mlp_weights(C, 64, 64, gen=g)
+    feat = 0.5 * torch.randn(M, 3 * C, generator=g)
+    d = torch.randn(M, 3, generator=g)
+    d = d / d.norm(dim=-1, keepdim=True)
+    gs = torch.randn(M, generator=g) * 64.0            # loss-scaled gradients, as GradScaler produces
+    grgb = torch.randn(M, 3, generator=g) * 64.0
+    W_o = [w.clone().requires_grad_(True) for w in W]
+    f_o = feat.clone().requires_grad_(True)
+    s_o, rgb_o, _ = of.mlp_forward(f_o, d, W_o, fp16=True)
+    ((s_o * gs).sum() + (rgb_o * grgb).sum()).backward()
+    dims, packed = _mlp_pack_emu(C, 64, W)
+    g_feat = np.full((M, 3 * C), np.nan, np.float32)
+    gW = [np.zeros(tuple(w.shape), np.float32) for w in W]
+    kemu.call("tnl_mlp_backward", ctypes.byref(dims), packed, feat.numpy(), 0, d.numpy(), M, None, gs.numpy(), grgb.numpy(), g_feat,
+              *gW, None)
+    assert np.linalg.norm(g_feat - f_o.grad.numpy()) / np.linalg.norm(f_o.grad.numpy()) <= 1e-2
+    for a, b in zip(gW, W_o):
+        assert np.linalg.norm(a - b.grad.numpy()) / np.linalg.norm(b.grad.numpy()) <= 1e-2, a.shape
+    # fp16 feature stream in / out: identical rounding points
+    g_feat_h = np.zeros((M, 3 * C), np.float16)
+    gW_h = [np.zeros(tuple(w.shape), np.float32) for w in W]
+    kemu.call("tnl_mlp_backward", ctypes.byref(dims), packed, feat.numpy().astype(np.float16), 1, d.numpy(), M, None, gs.numpy(),
+              grgb.numpy(), g_feat_h, *gW_h, None)
+    assert np.array_equal(g_feat_h.astype(np.float32), g_feat)
+    for a, b in zip(gW_h, gW):
+        assert np.allclose(a, b, rtol=1e-5, atol=1e-5 * np.abs(b).max())
+    # the 128-wide heads have no fused backward in this round: the ABI says so instead of launching
+    from trinerflet_b200._lib import MlpDims
+    big = MlpDims(3 * C, 128, 128)
+    rc = kemu.lib().tnl_mlp_backward(ctypes.byref(big), kemu.p(packed), kemu.p(feat.numpy()), 0, kemu.p(d.numpy()), M, None,
+                                     kemu.p(gs.numpy()), kemu.p(grgb.numpy()), kemu.p(g_feat), *[kemu.p(x) for x in gW], None)
+    assert rc == -2
