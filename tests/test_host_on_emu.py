@@ -408,3 +408,33 @@ def test_mark_untrained_grid_matches_brute_force(emu):
     net.iter_density = 16
     net.update_extra_state()
     assert bool((net.density_grid[net.density_grid < 0] == -1).all()) and int((net.density_grid < 0).sum()) == unseen_total
+
+
+def test_stage_growth_checkpoint_adds_a_zero_level(emu):
+    """main_nerf.py:172-205 stages: (R, S) = (64, 2) -> (128, 4) keeps the base plane resolution, loads the coarser levels from the
+    previous stage's checkpoint (strict=False, nerf/utils.py:1482) and adds one finer, zero-initialised level (SURVEY.md
+    App. A-3).  The planes of the grown model equal the oracle's reconstruction from (old coefficients + a zero level)."""
+    from oracle import wavelet as ow
+    from trinerflet_b200.network import NeRFNetwork
+
+    def make(R, S):
+        return NeRFNetwork(bound=BOUND, cuda_ray=True, density_thresh=10, min_near=0.2, triplane_channels=8, triplane_resolution=R,
+                           triplane_wavelet_levels=S)
+
+    g = torch.Generator().manual_seed(0)
+    s1 = make(64, 2)
+    assert s1.encoder.planes_features.shape == (3, 8, 32, 32) and len(s1.encoder.planes_features_wavelet_coefs) == 1
+    with torch.no_grad():
+        s1.encoder.planes_features.copy_(torch.randn(3, 8, 32, 32, generator=g))
+        s1.encoder.planes_features_wavelet_coefs[0].copy_(0.1 * torch.randn(3, 8, 3, 32, 32, generator=g))
+    ckpt = {k: v.clone().contiguous() for k, v in s1.state_dict().items()}
+    s2 = make(128, 4)
+    assert s2.encoder.planes_features.shape == (3, 8, 32, 32) and len(s2.encoder.planes_features_wavelet_coefs) == 2
+    missing, unexpected = s2.load_state_dict(ckpt, strict=False)
+    assert missing == ["encoder.planes_features_wavelet_coefs.1"] and not unexpected
+    assert float(s2.encoder.planes_features_wavelet_coefs[1].abs().sum()) == 0.0
+    s2.encoder.reset_cahce()
+    planes = s2.encoder.get_planes().detach()
+    assert planes.shape == (3, 8, 128, 128)
+    want = ow.build_planes(ckpt["encoder.planes_features"], [ckpt["encoder.planes_features_wavelet_coefs.0"], torch.zeros(3, 8, 3, 64, 64)])
+    assert (planes - want).abs().max().item() <= 1e-5 * want.abs().max().item()
