@@ -17,12 +17,8 @@ from trinerflet_b200 import _lib
 
 
 def _ptr(t):
-    if t is None:
-        return None
-    if not t.is_contiguous() and t.numel() > 0:
-        # same contract as on the device: the caller hands dense storage in the layout the ABI expects
-        pass
-    return ctypes.c_void_p(t.data_ptr())
+    """host pointer of a CPU tensor (same contract as on the device: dense storage in the layout the ABI expects)"""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
 def _stream():
