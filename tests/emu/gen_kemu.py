@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "trinerflet_b200", "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
-SOURCES = ["api.cu", "raymarch.cu", "sample.cu", "sort.cu", "tiles.cu", "optim.cu", "grid.cu", "rays.cu", "idwt.cu", "mlp.cu"]
+SOURCES = ["api.cu", "raymarch.cu", "sample.cu", "sort.cu", "tiles.cu", "optim.cu", "grid.cu", "rays.cu", "idwt.cu", "mlp.cu", "tsample.cu"]
 # TNL_KEMU_ASAN=1: AddressSanitizer build (run the tests with LD_PRELOAD=$(gcc -print-file-name=libasan.so)
 # ASAN_OPTIONS=detect_leaks=0): out-of-bounds reads / writes of the kernels on the callers' heap buffers become hard errors
 ASAN = os.environ.get("TNL_KEMU_ASAN") == "1"
@@ -149,7 +149,7 @@ def generate(name):
 
 def build(force=False):
     os.makedirs(OUT_DIR, exist_ok=True)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, h) for h in ("common.cuh", "rays_core.cuh", "idwt_core.cuh", "mlp_math.cuh", "mlp_tc.cuh")]
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, h) for h in ("common.cuh", "rays_core.cuh", "idwt_core.cuh", "mlp_math.cuh", "mlp_tc.cuh", "sample_coords.cuh")]
     deps += [os.path.join(HERE, "cuda_shim.h"), os.path.abspath(__file__), os.path.join(ROOT, "include", "trinerflet_b200.h")]
     if not force and os.path.exists(SO) and os.path.getmtime(SO) >= max(os.path.getmtime(d) for d in deps):
         return SO

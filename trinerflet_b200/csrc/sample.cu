@@ -16,56 +16,9 @@
 // lerp in registers, one 128-bit store into the contiguous feature row.  Backward: one 128-bit
 // load of the feature gradient and four vector atomic adds (red.global.add.v4.f32).
 #include "common.cuh"
+#include "sample_coords.cuh"
 
 namespace tnl {
-
-struct Tap {
-    int x0, y0;       // north-west texel
-    float nw, ne, sw, se;
-    bool x1ok, y1ok;  // south / east neighbours inside the plane
-};
-
-__device__ __forceinline__ float to_pixel(float g, int R) {
-    float v = ((g + 1.0f) * 0.5f) * (float)(R - 1);
-    return fminf((float)(R - 1), fmaxf(v, 0.0f));
-}
-
-__device__ __forceinline__ Tap make_tap(float gx, float gy, int R) {
-    const float ix = to_pixel(gx, R), iy = to_pixel(gy, R);
-    const float fx = floorf(ix), fy = floorf(iy);
-    Tap t;
-    t.x0 = (int)fx;
-    t.y0 = (int)fy;
-    const float ex = fx + 1.0f, ey = fy + 1.0f;  // south-east corner coordinates
-    t.nw = (ex - ix) * (ey - iy);
-    t.ne = (ix - fx) * (ey - iy);
-    t.sw = (ex - ix) * (iy - fy);
-    t.se = (ix - fx) * (iy - fy);
-    t.x1ok = t.x0 + 1 <= R - 1;
-    t.y1ok = t.y0 + 1 <= R - 1;
-    return t;
-}
-
-__device__ __forceinline__ void plane_coords(const float* __restrict__ xyz, uint32_t m, int p, float inv_bound,
-                                             int fp16_coords, float& gx, float& gy) {
-    const int a = (p == 2) ? 1 : 0;
-    const int b = (p == 1) ? 1 : 2;
-    gx = __fmul_rn(__ldg(xyz + 3 * (size_t)m + a), inv_bound);
-    gy = __fmul_rn(__ldg(xyz + 3 * (size_t)m + b), inv_bound);
-    if (fp16_coords) {  // autocast rounds the projected coordinates to fp16 (triplane_encoder.py:299)
-        gx = __half2float(__float2half_rn(gx));
-        gy = __half2float(__float2half_rn(gy));
-    }
-}
-
-__device__ __forceinline__ uint2 pack4h(float4 v) {
-    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
-    return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
-}
-__device__ __forceinline__ float4 unpack4h(uint2 u) {
-    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-    return make_float4(a.x, a.y, b.x, b.y);
-}
 
 // HALF: features are written as fp16 -- the rounding the first nn.Linear applies under autocast anyway (network.py:127),
 // moved into the producer so that the feature stream costs half the bytes.
