@@ -229,12 +229,39 @@ def run_reference(args, cfg, n_rays):
     print(json.dumps(line), flush=True)
 
 
-def next_rows(args, net, ts, sc, n_rays, dev, use_graph):
-    """Step feeder (rays + targets generated on the device into the captured step's inputs) and full-frame inference with
-    the host-driven / device-driven loop.  Reported under extras only."""
+def next_rows(args, net, ts, sc, n_rays, dev, use_graph, devb=None):
+    """Step feeder (rays + targets generated on the device into the captured step's inputs), full-frame inference with the
+    host-driven / device-driven loop, and the A/B of the opt-in tile-binned sampling kernels.  Reported under extras only."""
     import torch
-    from trinerflet_b200 import rays, scene
+    from trinerflet_b200 import rays, scene, trainer
     out = {}
+    try:
+        # A/B: the same captured step with encoder.tiled_sampling (csrc/tsample.cu) instead of the point-ordered kernels
+        if use_graph and devb is not None:
+            enc = net.encoder
+            enc.tiled_sampling = True
+            try:
+                ts3 = trainer.TrainStep(net, ts.opt, optimizer=None, world_size=1)
+                net.zero_grad(set_to_none=True)
+                ts3.forward_backward(*devb[-1], update_grid=False)
+                ts3.capture(*devb[-2], warmup=1)
+                for i in range(3):
+                    ts3.replay(*devb[i])
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(args.steps):
+                    ts3.replay(*devb[args.warmup + i])
+                e1.record()
+                torch.cuda.synchronize()
+                out["tiled_sampling_ms_per_step"] = round(e0.elapsed_time(e1) / args.steps, 4)
+                out["tiled_sampling_note"] = "same captured fwd+bwd step with the opt-in tile-binned sampling kernels; compare with ms_per_step"
+                del ts3
+            finally:
+                enc.tiled_sampling = False
+                enc.sampling_tiles = None
+    except Exception as ex:  # pragma: no cover
+        out["tiled_sampling_ms_per_step"] = f"failed: {ex}"
     try:
         if use_graph:
             H, W = scene.H_IMG, scene.W_IMG
@@ -506,7 +533,7 @@ def main():
         # ---- the two "next" rows, outside the metric; N = 1 only.  Everything the contract line needs
         # has been computed above: a failure in here can only turn into a "failed: ..." string inside extras ----
         if world == 1 and not args.no_next_rows:
-            extras["next_rows"] = next_rows(args, net, ts, sc, n_rays, dev, use_graph)
+            extras["next_rows"] = next_rows(args, net, ts, sc, n_rays, dev, use_graph, devb)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -438,3 +438,29 @@ def test_stage_growth_checkpoint_adds_a_zero_level(emu):
     assert planes.shape == (3, 8, 128, 128)
     want = ow.build_planes(ckpt["encoder.planes_features"], [ckpt["encoder.planes_features_wavelet_coefs.0"], torch.zeros(3, 8, 3, 64, 64)])
     assert (planes - want).abs().max().item() <= 1e-5 * want.abs().max().item()
+
+
+@pytest.mark.parametrize("sparse", [False, True])
+def test_tile_binned_sampling_training_step_equals_default(emu, sparse):
+    """encoder.tiled_sampling = True (tap sort + csrc/tsample.cu through _SamplePlanesTiled, restricted to the plan's zero list
+    on work-list steps, unzeroed gradient buffer) against the default point-ordered kernels: same loss, same gradients"""
+    from trinerflet_b200 import scene, trainer
+    sc = scene.make_scene()
+    N = 300
+    ro, rd, tgt = scene.sample_batch(sc, N, torch.Generator().manual_seed(4))
+    res = []
+    for tiled in (False, True):
+        net = _model(radius=0.45)
+        net.train()
+        net.encoder.tiled_sampling = tiled
+        ts = trainer.TrainStep(net, trainer.default_opt(fp16=False), None)
+        ts.sparse_idwt = sparse
+        ts.plan_on_any_device = True
+        torch.manual_seed(9)
+        loss = ts.forward_backward(ro, rd, tgt, update_grid=False)
+        res.append((float(loss), [p.grad.clone() for p in net.parameters()], net, ts))
+    (l_a, g_a, _, _), (l_b, g_b, net, ts) = res
+    assert (net.encoder.sampling_tiles is not None) == sparse
+    assert abs(l_a - l_b) <= 1e-6 * abs(l_a)
+    for a, b in zip(g_a, g_b):
+        assert rel_l2(b, a) <= 2e-6

@@ -31,8 +31,10 @@ template <int C4>
 struct TCfg {
     static constexpr int C = 4 * C4;
     static constexpr int PITCH = C + 4;                 // floats per texel in shared memory (+4: spreads texels over the banks)
-    static constexpr int SLOTS = 32;                    // points in flight per iteration
-    static constexpr int NT = SLOTS * C4;               // thread <-> (point slot, 4-channel group)
+    // points in flight per iteration.  The tile fills most of an SM's shared memory (one CTA per SM), so the CTA itself has
+    // to bring the warps that hide the latency of the perm / coordinate / feature-row accesses: 24-32 warps
+    static constexpr int SLOTS = C4 <= 4 ? 256 : (C4 <= 8 ? 128 : 64);
+    static constexpr int NT = SLOTS * C4;               // thread <-> (point slot, 4-channel group); 1024 / 1024 / 768
     static constexpr size_t SMEM_F = sizeof(float) * kTW * kTW * PITCH;
     static constexpr size_t SMEM_B = sizeof(float) * kTS * kTS * PITCH;
 };
