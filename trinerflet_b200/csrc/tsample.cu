@@ -35,8 +35,10 @@ struct TCfg {
     // to bring the warps that hide the latency of the perm / coordinate / feature-row accesses: 24-32 warps
     static constexpr int SLOTS = C4 <= 4 ? 256 : (C4 <= 8 ? 128 : 64);
     static constexpr int NT = SLOTS * C4;               // thread <-> (point slot, 4-channel group); 1024 / 1024 / 768
-    static constexpr size_t SMEM_F = sizeof(float) * kTW * kTW * PITCH;
-    static constexpr size_t SMEM_B = sizeof(float) * kTS * kTS * PITCH;
+    static constexpr size_t TILE_F = sizeof(float) * kTW * kTW * PITCH;   // forward: tile + halo
+    static constexpr size_t TILE_B = sizeof(float) * kTS * kTS * PITCH;   // backward: own texels only
+    static size_t smem_fwd(uint32_t G) { return TILE_F + 2 * sizeof(uint32_t) * G; }        // + bin table (G entries)
+    static size_t smem_bwd(uint32_t G) { return TILE_B + 2 * sizeof(uint32_t) * 4 * G; }    // + bin table (4G entries)
 };
 
 struct TileGeom {
@@ -72,6 +74,54 @@ __device__ __forceinline__ void bin_range(const uint32_t* __restrict__ bin_end, 
     end = __ldg(bin_end + bin);
 }
 
+// The points of a tile are spread over G (forward) or 4G (backward) bins.  Walking the bins one after the other would
+// serialise three dependent global loads (bin range -> perm -> coordinates) per bin; instead the bin table is built once in
+// shared memory -- pref[k] = number of points in bins 0..k, gend[k] = end offset of bin k in perm -- and the CTA iterates
+// over the flat point index j: bin = first k with pref[k] > j, perm index = gend[k] - (pref[k] - j).
+struct BinTable {
+    uint32_t* pref;   // [n] inclusive prefix of the bin sizes
+    uint32_t* gend;   // [n] end offset of the bin in perm
+    int n;
+    uint32_t total;
+};
+
+// n <= 1024 entries; every thread of the CTA calls it (two barriers)
+template <typename F>
+__device__ __forceinline__ BinTable build_bin_table(uint32_t* smem_words, int n, F range_of) {
+    BinTable bt;
+    bt.pref = smem_words;
+    bt.gend = smem_words + n;
+    bt.n = n;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        uint32_t start, end;
+        range_of(k, start, end);
+        bt.pref[k] = end - start;
+        bt.gend[k] = end;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {   // n is at most a few hundred: a serial scan costs less than a barrier-based one
+        uint32_t run = 0;
+        for (int k = 0; k < n; ++k) {
+            run += bt.pref[k];
+            bt.pref[k] = run;
+        }
+    }
+    __syncthreads();
+    bt.total = n > 0 ? bt.pref[n - 1] : 0u;
+    return bt;
+}
+
+__device__ __forceinline__ uint32_t bin_lookup(const BinTable& bt, uint32_t j) {
+    int lo = 0, hi = bt.n - 1;          // j < total, so the answer exists
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (bt.pref[mid] > j) hi = mid; else lo = mid + 1;
+    }
+    return bt.gend[lo] - (bt.pref[lo] - j);
+}
+
+constexpr int kUnroll = 4;   // independent points per thread in flight (perm -> coordinates -> feature row are dependent loads)
+
 template <int C4, bool HALF>
 __global__ void __launch_bounds__(TCfg<C4>::NT, 1)
 k_tsample_fwd(const float* __restrict__ planes, const float* __restrict__ xyz, int R, int G, float inv_bound, int fp16_coords,
@@ -92,15 +142,25 @@ k_tsample_fwd(const float* __restrict__ planes, const float* __restrict__ xyz, i
         const float4 v = __ldg(reinterpret_cast<const float4*>(planes + (((size_t)t.p * R + (y_base + ly)) * R + (x_base + lx)) * C) + q);
         *reinterpret_cast<float4*>(tile + (ly * kTW + lx) * Cfg::PITCH + 4 * q) = v;
     }
-    __syncthreads();
-    for (int k = 0; k < G; ++k) {
-        uint32_t start, end;
+    uint32_t* words = reinterpret_cast<uint32_t*>(tile + kTW * kTW * Cfg::PITCH);
+    const BinTable bt = build_bin_table(words, G, [&](int k, uint32_t& start, uint32_t& end) {
         bin_range(bin_end, t, G, t.tx, t.ty, k, start, end);
-        for (uint32_t i = start + slot; i < end; i += Cfg::SLOTS) {
-            const uint32_t m = (uint32_t)__ldg(perm + i);
-            float gx, gy;
-            plane_coords(xyz, m, t.p, inv_bound, fp16_coords, gx, gy);
-            const Tap tp = make_tap(gx, gy, R);
+    });   // (its barriers also publish the staged tile)
+    for (uint32_t j0 = slot; j0 < bt.total; j0 += kUnroll * Cfg::SLOTS) {
+        uint32_t m[kUnroll];
+        float gx[kUnroll], gy[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const uint32_t j = j0 + u * Cfg::SLOTS;
+            m[u] = j < bt.total ? (uint32_t)__ldg(perm + bin_lookup(bt, j)) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+            if (m[u] != 0xffffffffu) plane_coords(xyz, m[u], t.p, inv_bound, fp16_coords, gx[u], gy[u]);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (m[u] == 0xffffffffu) continue;
+            const Tap tp = make_tap(gx[u], gy[u], R);
             const float* base = tile + ((tp.y0 - y_base) * kTW + (tp.x0 - x_base)) * Cfg::PITCH + 4 * cq;
             float4 acc;
             {
@@ -119,7 +179,7 @@ k_tsample_fwd(const float* __restrict__ planes, const float* __restrict__ xyz, i
                 const float4 v = *reinterpret_cast<const float4*>(base + (kTW + 1) * Cfg::PITCH);
                 acc.x = fmaf(v.x, tp.se, acc.x); acc.y = fmaf(v.y, tp.se, acc.y); acc.z = fmaf(v.z, tp.se, acc.z); acc.w = fmaf(v.w, tp.se, acc.w);
             }
-            const size_t q4 = ((size_t)m * 3 + t.p) * C4 + cq;   // this thread's 4-channel group of feat[m][p*C ..]
+            const size_t q4 = ((size_t)m[u] * 3 + t.p) * C4 + cq;   // this thread's 4-channel group of feat[m][p*C ..]
             if (HALF) reinterpret_cast<uint2*>(feat_)[q4] = pack4h(acc);
             else reinterpret_cast<float4*>(feat_)[q4] = acc;
         }
@@ -152,35 +212,43 @@ k_tsample_bwd(const void* __restrict__ g_feat_, const float* __restrict__ xyz, i
     const int tid = threadIdx.x, cq = tid % C4, slot = tid / C4;
     const int x_base = t.tx * kTS, y_base = t.ty * kTS;
     for (int i = tid; i < kTS * kTS * Cfg::PITCH / 4; i += Cfg::NT) reinterpret_cast<float4*>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    // own column first, then the west / north / north-west neighbours, of which only the points on the shared edge count
-#pragma unroll 1
-    for (int nb = 0; nb < 4; ++nb) {
-        const int dxc = nb & 1, dyc = nb >> 1;
-        const int ta = t.tx - dxc, tb = t.ty - dyc;
-        if (ta < 0 || tb < 0) continue;
-        for (int k = 0; k < G; ++k) {
-            uint32_t start, end;
-            bin_range(bin_end, t, G, ta, tb, k, start, end);
-            for (uint32_t i = start + slot; i < end; i += Cfg::SLOTS) {
-                const uint32_t m = (uint32_t)__ldg(perm + i);
-                float gx, gy;
-                plane_coords(xyz, m, t.p, inv_bound, fp16_coords, gx, gy);
-                const Tap tp = make_tap(gx, gy, R);
-                // corners of this point inside the tile: local coordinates in [0, TS)
-                const int lx0 = tp.x0 - x_base, ly0 = tp.y0 - y_base;
-                const bool cx0 = lx0 >= 0 && lx0 < kTS, cx1 = tp.x1ok && lx0 + 1 >= 0 && lx0 + 1 < kTS;
-                const bool cy0 = ly0 >= 0 && ly0 < kTS, cy1 = tp.y1ok && ly0 + 1 >= 0 && ly0 + 1 < kTS;
-                if (!((cx0 || cx1) && (cy0 || cy1))) continue;
-                const size_t q4 = ((size_t)m * 3 + t.p) * C4 + cq;
-                const float4 g = HALF ? unpack4h(__ldg(reinterpret_cast<const uint2*>(g_feat_) + q4))
-                                      : __ldg(reinterpret_cast<const float4*>(g_feat_) + q4);
-                float* base = tile + (ly0 * kTS + lx0) * Cfg::PITCH + 4 * cq;
-                if (cx0 && cy0) smem_add4(base, g, tp.nw);
-                if (cx1 && cy0) smem_add4(base + Cfg::PITCH, g, tp.ne);
-                if (cx0 && cy1) smem_add4(base + kTS * Cfg::PITCH, g, tp.sw);
-                if (cx1 && cy1) smem_add4(base + (kTS + 1) * Cfg::PITCH, g, tp.se);
-            }
+    // bins of the own column (entries 0 .. G-1), then of the west / north / north-west neighbour columns, of which only the
+    // points on the shared edge contribute
+    uint32_t* words = reinterpret_cast<uint32_t*>(tile + kTS * kTS * Cfg::PITCH);
+    const BinTable bt = build_bin_table(words, 4 * G, [&](int e, uint32_t& start, uint32_t& end) {
+        const int nb = e / G, k = e % G;
+        const int ta = t.tx - (nb & 1), tb = t.ty - (nb >> 1);
+        if (ta < 0 || tb < 0) { start = end = 0; return; }
+        bin_range(bin_end, t, G, ta, tb, k, start, end);
+    });   // (its barriers also publish the zeroed tile)
+    for (uint32_t j0 = slot; j0 < bt.total; j0 += kUnroll * Cfg::SLOTS) {
+        uint32_t m[kUnroll];
+        float gx[kUnroll], gy[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const uint32_t j = j0 + u * Cfg::SLOTS;
+            m[u] = j < bt.total ? (uint32_t)__ldg(perm + bin_lookup(bt, j)) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+            if (m[u] != 0xffffffffu) plane_coords(xyz, m[u], t.p, inv_bound, fp16_coords, gx[u], gy[u]);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (m[u] == 0xffffffffu) continue;
+            const Tap tp = make_tap(gx[u], gy[u], R);
+            // corners of this point inside the tile: local coordinates in [0, TS)
+            const int lx0 = tp.x0 - x_base, ly0 = tp.y0 - y_base;
+            const bool cx0 = lx0 >= 0 && lx0 < kTS, cx1 = tp.x1ok && lx0 + 1 >= 0 && lx0 + 1 < kTS;
+            const bool cy0 = ly0 >= 0 && ly0 < kTS, cy1 = tp.y1ok && ly0 + 1 >= 0 && ly0 + 1 < kTS;
+            if (!((cx0 || cx1) && (cy0 || cy1))) continue;
+            const size_t q4 = ((size_t)m[u] * 3 + t.p) * C4 + cq;
+            const float4 g = HALF ? unpack4h(__ldg(reinterpret_cast<const uint2*>(g_feat_) + q4))
+                                  : __ldg(reinterpret_cast<const float4*>(g_feat_) + q4);
+            float* base = tile + (ly0 * kTS + lx0) * Cfg::PITCH + 4 * cq;
+            if (cx0 && cy0) smem_add4(base, g, tp.nw);
+            if (cx1 && cy0) smem_add4(base + Cfg::PITCH, g, tp.ne);
+            if (cx0 && cy1) smem_add4(base + kTS * Cfg::PITCH, g, tp.sw);
+            if (cx1 && cy1) smem_add4(base + (kTS + 1) * Cfg::PITCH, g, tp.se);
         }
     }
     __syncthreads();
@@ -217,20 +285,21 @@ static int launch_tsample(bool fwd, const void* in, void* out, const float* xyz,
                           int fp16_coords, const uint32_t* bin_end, const int32_t* perm, const int32_t* tile_ids,
                           const int32_t* n_tiles, uint32_t grid, int half, cudaStream_t s) {
     using Cfg = TCfg<C4>;
+    const size_t smem_f = Cfg::smem_fwd(G), smem_b = Cfg::smem_bwd(G);
     static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k_tsample_fwd<C4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_F);
-        cudaFuncSetAttribute(k_tsample_fwd<C4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_F);
-        cudaFuncSetAttribute(k_tsample_bwd<C4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_B);
-        cudaFuncSetAttribute(k_tsample_bwd<C4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_B);
+    if (!attr) {   // opt in to the largest dynamic shared-memory size these kernels can ask for (G <= 256)
+        cudaFuncSetAttribute(k_tsample_fwd<C4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_fwd(256));
+        cudaFuncSetAttribute(k_tsample_fwd<C4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_fwd(256));
+        cudaFuncSetAttribute(k_tsample_bwd<C4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bwd(256));
+        cudaFuncSetAttribute(k_tsample_bwd<C4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bwd(256));
         attr = true;
     }
     if (fwd) {
-        if (half) k_tsample_fwd<C4, true><<<grid, Cfg::NT, Cfg::SMEM_F, s>>>(static_cast<const float*>(in), xyz, (int)R, (int)G, inv_bound, fp16_coords, bin_end, perm, tile_ids, n_tiles, out);
-        else k_tsample_fwd<C4, false><<<grid, Cfg::NT, Cfg::SMEM_F, s>>>(static_cast<const float*>(in), xyz, (int)R, (int)G, inv_bound, fp16_coords, bin_end, perm, tile_ids, n_tiles, out);
+        if (half) k_tsample_fwd<C4, true><<<grid, Cfg::NT, smem_f, s>>>(static_cast<const float*>(in), xyz, (int)R, (int)G, inv_bound, fp16_coords, bin_end, perm, tile_ids, n_tiles, out);
+        else k_tsample_fwd<C4, false><<<grid, Cfg::NT, smem_f, s>>>(static_cast<const float*>(in), xyz, (int)R, (int)G, inv_bound, fp16_coords, bin_end, perm, tile_ids, n_tiles, out);
     } else {
-        if (half) k_tsample_bwd<C4, true><<<grid, Cfg::NT, Cfg::SMEM_B, s>>>(in, xyz, (int)R, (int)G, inv_bound, fp16_coords, bin_end, perm, tile_ids, n_tiles, static_cast<float*>(out));
-        else k_tsample_bwd<C4, false><<<grid, Cfg::NT, Cfg::SMEM_B, s>>>(in, xyz, (int)R, (int)G, inv_bound, fp16_coords, bin_end, perm, tile_ids, n_tiles, static_cast<float*>(out));
+        if (half) k_tsample_bwd<C4, true><<<grid, Cfg::NT, smem_b, s>>>(in, xyz, (int)R, (int)G, inv_bound, fp16_coords, bin_end, perm, tile_ids, n_tiles, static_cast<float*>(out));
+        else k_tsample_bwd<C4, false><<<grid, Cfg::NT, smem_b, s>>>(in, xyz, (int)R, (int)G, inv_bound, fp16_coords, bin_end, perm, tile_ids, n_tiles, static_cast<float*>(out));
     }
     return 0;
 }
