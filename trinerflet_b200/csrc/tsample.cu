@@ -134,7 +134,11 @@ k_tsample_fwd(const float* __restrict__ planes, const float* __restrict__ xyz, i
     if (!tile_geom(tile_ids, n_tiles, G, t)) return;
     const int tid = threadIdx.x, cq = tid % C4, slot = tid / C4;
     const int x_base = t.tx * kTS, y_base = t.ty * kTS;
-    // a tile without points has nothing to do (the 2*G range reads are uniform across the block)
+    uint32_t* words = reinterpret_cast<uint32_t*>(tile + kTW * kTW * Cfg::PITCH);
+    const BinTable bt = build_bin_table(words, G, [&](int k, uint32_t& start, uint32_t& end) {
+        bin_range(bin_end, t, G, t.tx, t.ty, k, start, end);
+    });
+    if (bt.total == 0) return;   // a listed tile without points (the halo tiles of a work-list step): nothing to stage
     // stage the tile: rows y_base .. y_base+TS, columns x_base .. x_base+TS, clipped to the plane
     const int rows = min(kTW, R - y_base), cols = min(kTW, R - x_base);
     for (int i = tid; i < rows * cols * C4; i += Cfg::NT) {
@@ -142,10 +146,7 @@ k_tsample_fwd(const float* __restrict__ planes, const float* __restrict__ xyz, i
         const float4 v = __ldg(reinterpret_cast<const float4*>(planes + (((size_t)t.p * R + (y_base + ly)) * R + (x_base + lx)) * C) + q);
         *reinterpret_cast<float4*>(tile + (ly * kTW + lx) * Cfg::PITCH + 4 * q) = v;
     }
-    uint32_t* words = reinterpret_cast<uint32_t*>(tile + kTW * kTW * Cfg::PITCH);
-    const BinTable bt = build_bin_table(words, G, [&](int k, uint32_t& start, uint32_t& end) {
-        bin_range(bin_end, t, G, t.tx, t.ty, k, start, end);
-    });   // (its barriers also publish the staged tile)
+    __syncthreads();
     for (uint32_t j0 = slot; j0 < bt.total; j0 += kUnroll * Cfg::SLOTS) {
         uint32_t m[kUnroll];
         float gx[kUnroll], gy[kUnroll];
