@@ -816,3 +816,35 @@ def test_tile_binned_sampling_empty_and_argument_errors():
     assert lib.tnl_tsample_forward(z16, z16, 5, 48, 16, 1.0, 0, None, z16, z16, None, None, 0, z16, 0, None) == -1   # R % 32
     assert lib.tnl_tsample_forward(z16, z16, 5, 64, 24, 1.0, 0, None, z16, z16, None, None, 0, z16, 0, None) == -1   # C
     assert lib.tnl_tsample_forward(z16, z16, 5, 64, 16, 1.0, 0, None, z16, z16, z16, None, 4, z16, 0, None) == -1    # list without count
+
+
+@pytest.mark.parametrize("bound,Hg,dt_gamma,max_steps", [(1.0, 128, 0.0, 256), (4.0, 128, 1.0 / 256, 512), (3.0, 32, 1.0 / 128, 128)])
+def test_march_train_other_bounds_cascades_and_grid_sizes(bound, Hg, dt_gamma, max_steps):
+    """the reference commands all use bound 1.5 (cascade 2, 128^3); the marcher's level selection / cone stepping for one, three
+    cascades and a coarser grid stay bit-exact with the C oracle as well"""
+    import math
+    from trinerflet_b200 import scene as sc
+    cas = 1 + math.ceil(math.log2(bound)) if bound > 1 else 1
+    o, d = synthetic_rays(400, seed=int(bound * 10))
+    o = (o * bound / 1.5).astype(np.float32)
+    grid = sc.ball_density_grid(bound, 0.6 * bound, 1.0, Hg).numpy()
+    rng = np.random.default_rng(1)
+    grid = np.where(rng.random(grid.shape) < 0.02, 1 - grid, grid).astype(np.float32)
+    bits = np.packbits(grid.reshape(-1) > 0.5, bitorder='little')
+    aabb = np.array([-bound] * 3 + [bound] * 3, np.float32)
+    N = len(o)
+    nears, fars = np.empty(N, np.float32), np.empty(N, np.float32)
+    kemu.call("tnl_near_far_from_aabb", o, d, aabb, N, 0.2, nears, fars, None)
+    n_o, f_o = orc.near_far_from_aabb(o, d, aabb, 0.2)
+    assert _bits_equal(nears, n_o) and _bits_equal(fars, f_o)
+    noises = rng.random(N).astype(np.float32)
+    M = N * max_steps
+    xyzs, dirs, deltas = np.zeros((M, 3), np.float32), np.zeros((M, 3), np.float32), np.zeros((M, 2), np.float32)
+    rays, counter = np.empty((N, 3), np.int32), np.zeros(2, np.int32)
+    wsz = kemu.lib().tnl_march_rays_train_workspace(N)
+    ws = np.zeros(wsz, np.uint8)
+    kemu.call("tnl_march_rays_train", o, d, bits, bound, dt_gamma, max_steps, N, cas, Hg, M, nears, fars, xyzs, dirs, deltas, rays, counter,
+              noises, ws, wsz, None)
+    x_o, d_o, l_o, r_o, c_o = orc.march_rays_train(o, d, bound, bits, cas, Hg, nears, fars, noises, M, dt_gamma, max_steps)
+    assert counter[0] > N and np.array_equal(counter, c_o) and np.array_equal(rays, r_o)
+    assert _bits_equal(xyzs, x_o) and _bits_equal(deltas, l_o)
