@@ -259,7 +259,6 @@ def next_rows(args, net, ts, sc, n_rays, dev, use_graph, devb=None):
                 del ts3
             finally:
                 enc.tiled_sampling = False
-                enc.sampling_tiles = None
     except Exception as ex:  # pragma: no cover
         out["tiled_sampling_ms_per_step"] = f"failed: {ex}"
     try:

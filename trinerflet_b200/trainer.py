@@ -66,12 +66,16 @@ class TrainStep:
     # ---- the three segments of a step ---------------------------------------------------------------------------------
     def _render_loss(self, rays_o, rays_d, images):
         model, opt = self.model, self.opt
-        with torch.autocast("cuda", dtype=torch.float16, enabled=opt.fp16):
-            bg = torch.zeros_like(images) + opt.background_color
-            out = model.render(rays_o.unsqueeze(0), rays_d.unsqueeze(0), staged=False, bg_color=bg, perturb=True,
-                               force_all_rays=False, dt_gamma=opt.dt_gamma, max_steps=opt.max_steps)
-            pred = out['image'].view(-1, 3)
-            return self.criterion(pred, images).mean(-1).mean()
+        try:
+            with torch.autocast("cuda", dtype=torch.float16, enabled=opt.fp16):
+                bg = torch.zeros_like(images) + opt.background_color
+                out = model.render(rays_o.unsqueeze(0), rays_d.unsqueeze(0), staged=False, bg_color=bg, perturb=True,
+                                   force_all_rays=False, dt_gamma=opt.dt_gamma, max_steps=opt.max_steps)
+                pred = out['image'].view(-1, 3)
+                return self.criterion(pred, images).mean(-1).mean()
+        finally:
+            # the tile list of the tile-binned sampler is valid for this step's render only (its backward keeps its own copy)
+            model.encoder.sampling_tiles = None
 
     def forward_backward(self, rays_o, rays_d, images, update_grid=None):
         """rays_o/rays_d/images: [N,3] device tensors (this rank's shard). Returns the detached loss tensor."""
