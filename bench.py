@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--rays", type=int, default=0, help="rays per GPU per step (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-next-rows", action="store_true", help="skip the extras.next_rows measurements (feeder, render loops)")
+    ap.add_argument("--tiled-sampling", action="store_true",
+                    help="run the whole benchmark with the opt-in tile-binned sampling kernels (encoder.tiled_sampling)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU work for the cpu_baseline leg")
     return ap.parse_args()
@@ -153,9 +155,9 @@ def algorithmic_bytes(name, meta, C, m_valid, plan=None):
             clean = (b - a) if plan.defer_clean_abs else (1 - a)
             return px * (((parts & 1) and a * (4 + 4)) + ((parts & 2) and clean * 3))
         return px * (((parts & 1) and b * (4 + 3 + 4)) + ((parts & 2) and (1 - b) * (3 + 4)))
-    if name == "tnl_sample_planes_forward":
-        return m_valid * (12 + g)
-    if name == "tnl_sample_planes_backward":
+    if name in ("tnl_sample_planes_forward", "tnl_tsample_forward"):       # the algorithm's bytes, whatever the
+        return m_valid * (12 + g)                                            # kernel's on-chip reuse makes of them
+    if name in ("tnl_sample_planes_backward", "tnl_tsample_backward"):
         return m_valid * 2 * g
     if name == "tnl_mlp_forward":
         return m_valid * (2 * 3 * C + 28)            # fp16 feature row + dirs in, sigma + rgb out
@@ -239,7 +241,8 @@ def next_rows(args, net, ts, sc, n_rays, dev, use_graph, devb=None):
         # A/B: the same captured step with encoder.tiled_sampling (csrc/tsample.cu) instead of the point-ordered kernels
         if use_graph and devb is not None:
             enc = net.encoder
-            enc.tiled_sampling = True
+            was = enc.tiled_sampling
+            enc.tiled_sampling = not was
             try:
                 ts3 = trainer.TrainStep(net, ts.opt, optimizer=None, world_size=1)
                 net.zero_grad(set_to_none=True)
@@ -254,11 +257,12 @@ def next_rows(args, net, ts, sc, n_rays, dev, use_graph, devb=None):
                     ts3.replay(*devb[args.warmup + i])
                 e1.record()
                 torch.cuda.synchronize()
-                out["tiled_sampling_ms_per_step"] = round(e0.elapsed_time(e1) / args.steps, 4)
-                out["tiled_sampling_note"] = "same captured fwd+bwd step with the opt-in tile-binned sampling kernels; compare with ms_per_step"
+                key = "point_ordered_sampling_ms_per_step" if was else "tiled_sampling_ms_per_step"
+                out[key] = round(e0.elapsed_time(e1) / args.steps, 4)
+                out["sampling_ab_note"] = "the same captured fwd+bwd step with the other sampling kernels (tile-binned <-> point-ordered); compare with ms_per_step"
                 del ts3
             finally:
-                enc.tiled_sampling = False
+                enc.tiled_sampling = was
     except Exception as ex:  # pragma: no cover
         out["tiled_sampling_ms_per_step"] = f"failed: {ex}"
     try:
@@ -348,6 +352,7 @@ def main():
                       triplane_wavelet_levels=S, hidden_dim=cfg["hidden"], hidden_dim_color=cfg["hidden"]).to(dev)
     scene.init_model_(net, seed=0)                      # identical replicas on every rank
     scene.install_ball_occupancy(net, 0.75)
+    net.encoder.tiled_sampling = bool(args.tiled_sampling)
     opt = trainer.default_opt()
     ts = trainer.TrainStep(net, opt, optimizer=None, world_size=world)
     sc = scene.make_scene()
