@@ -99,11 +99,19 @@ __device__ __forceinline__ BinTable build_bin_table(uint32_t* smem_words, int n,
         bt.gend[k] = end;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {   // n is at most a few hundred: a serial scan costs less than a barrier-based one
-        uint32_t run = 0;
-        for (int k = 0; k < n; ++k) {
-            run += bt.pref[k];
-            bt.pref[k] = run;
+    if (threadIdx.x < 32) {   // inclusive scan of the bin sizes by one warp, 32 entries per step (n is at most 1024)
+        const int lane = threadIdx.x;
+        uint32_t carry = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int k = base + lane;
+            uint32_t v = k < n ? bt.pref[k] : 0u;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += up;
+            }
+            if (k < n) bt.pref[k] = carry + v;
+            carry += __shfl_sync(0xffffffffu, v, 31);
         }
     }
     __syncthreads();
