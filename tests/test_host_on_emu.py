@@ -262,7 +262,7 @@ def test_sparse_plane_gradient_exchange_world2_gloo():
     assert out[0] and out[1]
 
 
-def _train_worker(rank, world, port, out):
+def _train_worker(rank, world, port, out, tiled=False):
     import torch.distributed as dist
     from _pytest.monkeypatch import MonkeyPatch
     mpatch = MonkeyPatch()
@@ -283,8 +283,10 @@ def _train_worker(rank, world, port, out):
         # this rank's shard through the ray-sharded step (dirty-tile exchange of the plane gradient, fp32 transport)
         net = _model()
         net.train()
+        net.encoder.tiled_sampling = tiled               # (opt-in tile-binned sampling: the exchange sees the same gradient)
         lo, hi = parallel.shard_range(N, rank, world)
-        ts = trainer.TrainStep(net, opt, None, world_size=world, check_sparse=True, transport=torch.float32)
+        ts = trainer.TrainStep(net, opt, None, world_size=world, check_sparse=not tiled, transport=torch.float32)
+        ts.plan_on_any_device = tiled                    # with it: work-list step, scatter restricted to the plan's zero list
         torch.manual_seed(5)
         torch.rand(lo)                                   # skip the jitter values of the rays before this shard
         loss = ts.forward_backward(ro[lo:hi], rd[lo:hi], tgt[lo:hi], update_grid=False)
@@ -300,7 +302,8 @@ def _train_worker(rank, world, port, out):
         mpatch.undo()
 
 
-def test_ray_sharded_training_step_world2_equals_single_rank():
+@pytest.mark.parametrize("tiled", [False, True])
+def test_ray_sharded_training_step_world2_equals_single_rank(tiled):
     """two ranks, half of the rays each, replicated parameters; render backward -> dirty-tile exchange of the
     plane gradient (gloo here, NCCL on the box) -> IDWT backward; MLP gradients in one bucket.  Loss and every parameter
     gradient equal the single-rank step on the whole batch."""
@@ -310,7 +313,7 @@ def test_ray_sharded_training_step_world2_equals_single_rank():
     s.close()
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_train_worker, args=(2, port, out), nprocs=2, join=True)
+    mp.spawn(_train_worker, args=(2, port, out, tiled), nprocs=2, join=True)
     assert out[0] and out[1]
 
 
