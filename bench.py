@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--rays", type=int, default=0, help="rays per GPU per step (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-next-rows", action="store_true", help="skip the extras.next_rows measurements (feeder, render loops)")
+    ap.add_argument("--occupancy-radius", type=float, default=0.75,
+                    help="radius of the occupied ball (SURVEY.md 8d: 0.75 = the metric's scene, 0.4 = the sparse preset that exposes the plane-bound regime)")
     ap.add_argument("--tiled-sampling", action="store_true",
                     help="run the whole benchmark with the opt-in tile-binned sampling kernels (encoder.tiled_sampling)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
@@ -351,7 +353,7 @@ def main():
     net = NeRFNetwork(bound=1.5, cuda_ray=True, density_thresh=10, min_near=0.2, triplane_channels=C, triplane_resolution=R,
                       triplane_wavelet_levels=S, hidden_dim=cfg["hidden"], hidden_dim_color=cfg["hidden"]).to(dev)
     scene.init_model_(net, seed=0)                      # identical replicas on every rank
-    scene.install_ball_occupancy(net, 0.75)
+    scene.install_ball_occupancy(net, args.occupancy_radius)
     net.encoder.tiled_sampling = bool(args.tiled_sampling)
     opt = trainer.default_opt()
     ts = trainer.TrainStep(net, opt, optimizer=None, world_size=world)
@@ -525,7 +527,8 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic",
             "config": {"workload": f"{args.config}: C={C} R={R} wavelet_levels={S} ({int(round(__import__('math').log2(S)))} IDWT levels), "
-                                   f"{n_rays} rays/GPU/step, synthetic 800x800 Blender-shaped scene, ball occupancy r=0.75, random-init",
+                                   f"{n_rays} rays/GPU/step, synthetic 800x800 Blender-shaped scene, ball occupancy r={args.occupancy_radius:g}, random-init",
+                       "sampling_kernels": "tile-binned (csrc/tsample.cu, --tiled-sampling)" if args.tiled_sampling else "point-ordered (csrc/sample.cu)",
                        "rays_per_gpu": n_rays, "global_rays": n_rays * world, "parallelism": (f"ray-sharded dp{world}, replicated coefficients; plane gradient exchanged as bf16 dirty tiles (NCCL all-reduce) "
                                                        "between the render backward and the IDWT backward" if world > 1 else "single GPU"),
                        "timed_region": "get_planes (work-list IDWT over the occupied tiles) + render + loss + backward (+ gradient exchange); optimizer and density-grid refresh excluded (metric definition), see extras",
