@@ -468,3 +468,31 @@ def test_tile_binned_sampling_training_step_equals_default(emu, sparse):
     assert abs(l_a - l_b) <= 1e-6 * abs(l_a)
     for a, b in zip(g_a, g_b):
         assert rel_l2(b, a) <= 2e-6
+
+
+@pytest.mark.parametrize("C,half", [(32, False), (48, True)])
+def test_field_mlp_function_wide_heads_hybrid_backward(emu, C, half):
+    """network._FieldMLP with the 128-wide heads of the "large" config: fused forward, backward = fused input-gradient chain
+    (tnl_mlp_backward_chain) + library GEMMs for the weight gradients, against the oracle's fp16-autocast autograd"""
+    from oracle import field as of
+    from trinerflet_b200.network import _FieldMLP
+    g = torch.Generator().manual_seed(C)
+    M = 160
+    W = of.init_mlp_weights(C, 128, 128, gen=g)
+    feat = 0.5 * torch.randn(M, 3 * C, generator=g)
+    d = torch.randn(M, 3, generator=g)
+    d = d / d.norm(dim=-1, keepdim=True)
+    gs, grgb = torch.randn(M, generator=g) * 64.0, torch.randn(M, 3, generator=g) * 64.0
+    W_o = [w.clone().requires_grad_(True) for w in W]
+    f_o = feat.clone().requires_grad_(True)
+    s_o, rgb_o, _ = of.mlp_forward(f_o, d, W_o, fp16=True)
+    ((s_o * gs).sum() + (rgb_o * grgb).sum()).backward()
+    W_g = [w.clone().requires_grad_(True) for w in W]
+    f_g = (feat.half() if half else feat.clone()).requires_grad_(True)
+    nv = torch.tensor([M], dtype=torch.int32)
+    s_g, rgb_g = _FieldMLP.apply(f_g, d, nv, *W_g)
+    assert (rgb_g - rgb_o).abs().max().item() <= 2e-3 and rel_l2(s_g, s_o) <= 2e-3
+    ((s_g * gs).sum() + (rgb_g * grgb).sum()).backward()
+    assert f_g.grad.dtype == f_g.dtype and rel_l2(f_g.grad.float(), f_o.grad) <= 1e-2
+    for a, b in zip(W_g, W_o):
+        assert a.grad.shape == b.grad.shape and rel_l2(a.grad, b.grad) <= 1e-2

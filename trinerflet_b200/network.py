@@ -22,11 +22,24 @@ from .encoding import get_encoder
 from .renderer import NeRFRenderer
 
 
-def fused_dims_supported(in_dim, hidden, hidden_color, need_grad):
+def fused_dims_supported(in_dim, hidden, hidden_color, need_grad, wide_backward=False):
     ok = in_dim in (48, 96, 144) and hidden == hidden_color and hidden in (64, 128)
     if need_grad:
-        ok = ok and hidden == 64  # fused backward covers the 64-wide heads (small / base configs) in this round
+        # the fully fused backward covers the 64-wide heads (small / base configs); the 128-wide heads ("large") have the
+        # opt-in hybrid of _FieldMLP.backward: fused input-gradient chain + library GEMMs for the weight gradients
+        ok = ok and (hidden == 64 or wide_backward)
     return ok
+
+
+def _mm_f32(a_t, b):
+    """fp16 x fp16 -> fp32 product of a weight gradient (dOut^T In): fp32 output where the library offers it (no fp16
+    overflow of loss-scaled sums over millions of points), plain fp32 GEMM otherwise"""
+    if a_t.is_cuda:
+        try:
+            return torch.mm(a_t, b, out_dtype=torch.float32)
+        except (TypeError, RuntimeError):
+            pass
+    return a_t.float() @ b.float()
 
 
 def pack_mlp_weights(dims, weights):
@@ -71,6 +84,25 @@ class _FieldMLP(Function):
         g_sigma = g_sigma.contiguous().float()
         g_rgb = g_rgb.contiguous().float()
         g_feat = torch.empty_like(feat)
+        if hidden != 64:
+            # 128-wide heads: their weight gradients (172 KB of fp32) fit neither the registers nor the shared memory of one
+            # CTA next to the operand tiles.  One fused kernel recomputes the activations, runs the input-gradient chain and
+            # dumps the fp16 operands of the five weight-gradient products; the products are plain library GEMMs.
+            lib = _lib.load()
+            halves = int(lib.tnl_mlp_chain_scratch_bytes(ctypes.byref(dims), M)) // 2
+            scratch = torch.empty(halves, device=feat.device, dtype=torch.float16)
+            call("tnl_mlp_backward_chain", ctypes.byref(dims), ptr(packed), ptr(feat), int(feat.dtype == torch.float16), ptr(dirs), M,
+                 ptr(n_valid) if has_nv else None, ptr(g_sigma), ptr(g_rgb), ptr(g_feat), ptr(scratch), stream())
+            mats, off = [], 0
+            for w in (hidden, 32, hidden_c, hidden_c, hidden, 16, hidden_c, hidden_c, 16):
+                mats.append(scratch[off:off + M * w].view(M, w))
+                off += M * w
+            h1, in2, h3, h4, d1, d2, d3, d4, d5 = mats
+            feat16 = feat if feat.dtype == torch.float16 else feat.half()
+            g2 = _mm_f32(d2.t(), h1)                          # internal row j < 15 <-> sigma_net[1] row j+1, 15 <-> row 0
+            gW = [_mm_f32(d1.t(), feat16), torch.cat([g2[15:16], g2[:15]], 0), _mm_f32(d3.t(), in2)[:, :31].contiguous(),
+                  _mm_f32(d4.t(), h3), _mm_f32(d5.t(), h4)[:3].contiguous()]
+            return (g_feat, None, None, *gW)
         gW = [torch.zeros(s, device=feat.device, dtype=torch.float32) for s in ctx.wshapes]
         call("tnl_mlp_backward", ctypes.byref(dims), ptr(packed), ptr(feat), int(feat.dtype == torch.float16), ptr(dirs), M,
              ptr(n_valid) if has_nv else None, ptr(g_sigma), ptr(g_rgb), ptr(g_feat), *[ptr(g) for g in gW], stream())
@@ -135,7 +167,8 @@ class NeRFNetwork(NeRFRenderer):
 
     def _fused(self, need_grad):
         return (torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.float16
-                and fused_dims_supported(self.in_dim, self.hidden_dim, self.hidden_dim_color, need_grad))
+                and fused_dims_supported(self.in_dim, self.hidden_dim, self.hidden_dim_color, need_grad,
+                                         getattr(self, "wide_fused_backward", False)))
 
     # visit the samples of a training step in the order of a coarse 3-D grid (L2 locality of the plane gather /
     # gradient scatter, see csrc/sort.cu); per-point results do not depend on it
