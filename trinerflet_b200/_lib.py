@@ -124,7 +124,7 @@ def check(rc, what):
 
 # number of kernels each ABI call launches (for the launch counter the benchmark reports)
 KERNELS_PER_CALL = {"tnl_march_rays_train": 5, "tnl_compact_alive": 3, "tnl_compact_alive_dev": 3, "tnl_cell_sort": 5, "tnl_tap_sort": 5,
-                    "tnl_mlp_pack_weights": 2}
+                    "tnl_mlp_pack_weights": 2, "tnl_tsample_forward": 2}   # (tsample forward: + the padding-row zero fill)
 # work-list IDWT calls launch one kernel per requested part (position of the `parts` argument from the end)
 _PARTS_ARG = {"tnl_idwt_level_forward_sparse": -2, "tnl_idwt_level_backward_sparse": -3}
 launch_count = 0
