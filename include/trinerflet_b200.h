@@ -193,7 +193,11 @@ int tnl_sample_planes_backward(const void* g_feat, int feat_fp16, const float* x
  *     every bin in perm (bin k = perm[end[k-1] .. end[k]), rows >= *n_valid in the last bin): pass it as `bin_end`.
  *   tile_ids / n_tiles (device, may both be NULL = every tile of the three planes): plane tiles to process, id =
  *     (p * R/32 + ty) * R/32 + tx as tnl_mark_dirty_tiles numbers them; the grid is sized by max_tiles.  The backward must be
- *     given every tile that is read afterwards (idwt_plan's zero list); points whose taps lie in unlisted tiles are dropped. */
+ *     given every tile that is read afterwards (idwt_plan's zero list) and every tile that holds points; points whose
+ *     north-west tap lies in an unlisted tile are dropped (including what their south / east taps would add to listed tiles).
+ *   backward: two passes (tile + one-texel halo accumulated in shared memory -> own texels to g_planes, halo to a per-tile
+ *     strip in `workspace`; then every tile adds its neighbours' strips to its first row / column).  tile_map (device uint8
+ *     [3 * (R/32)^2], required with a tile list: 1 for every listed tile) tells the second pass which neighbours exist. */
 size_t tnl_tap_sort_workspace(uint32_t M, uint32_t R);
 int tnl_tap_sort(const float* xyz, uint32_t M, const int32_t* n_valid, float inv_bound, int fp16_coords, uint32_t R,
                  int32_t* perm, void* workspace, size_t workspace_bytes, tnl_stream_t stream);
@@ -201,9 +205,11 @@ int tnl_tsample_forward(const float* planes, const float* xyz, uint32_t M, uint3
                         int fp16_coords, const int32_t* n_valid, const int32_t* perm, const void* bin_end,
                         const int32_t* tile_ids, const int32_t* n_tiles, uint32_t max_tiles, void* feat, int feat_fp16,
                         tnl_stream_t stream);
+size_t tnl_tsample_backward_workspace(uint32_t R, uint32_t C);
 int tnl_tsample_backward(const void* g_feat, int feat_fp16, const float* xyz, uint32_t M, uint32_t R, uint32_t C,
                          float inv_bound, int fp16_coords, const int32_t* perm, const void* bin_end, const int32_t* tile_ids,
-                         const int32_t* n_tiles, uint32_t max_tiles, float* g_planes, tnl_stream_t stream);
+                         const int32_t* n_tiles, uint32_t max_tiles, const uint8_t* tile_map, float* g_planes, void* workspace,
+                         size_t workspace_bytes, tnl_stream_t stream);
 
 /* Spatial binning of sample points: perm[i] = row of the i-th point in the order of a G^3 Morton grid over
  * [-bound, bound]^3 (rows >= *n_valid last).  Kernels taking `perm` visit points in that order, which makes the

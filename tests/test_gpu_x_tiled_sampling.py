@@ -50,8 +50,13 @@ def test_tiled_kernels_equal_point_ordered_kernels(C, R, fp16, use_list):
         gp_ref = torch.zeros(3, R, R, C, device="cuda")
         call("tnl_sample_planes_backward", ptr(gf), half, ptr(xyz), M, R, C, inv, int(fp16), ptr(nv), None, ptr(gp_ref), stream())
         gp = torch.full((3, R, R, C), float("nan"), device="cuda")   # no zero fill: every tile is written
+        halo = torch.full((_lib.load().tnl_tsample_backward_workspace(R, C) // 4,), float("nan"), device="cuda")
+        tmap = None
+        if use_list:
+            tmap = torch.zeros(3 * G * G, dtype=torch.uint8, device="cuda")
+            tmap[ids[:3 * G * G].long()] = 1
         call("tnl_tsample_backward", ptr(gf), half, ptr(xyz), M, R, C, inv, int(fp16), ptr(perm), ptr(bins), ptr(ids), ptr(cnt), cap,
-             ptr(gp), stream())
+             ptr(tmap), ptr(gp), ptr(halo), halo.numel() * 4, stream())
         assert bool(torch.isfinite(gp).all())
         assert (gp - gp_ref).abs().max().item() <= 3e-5 * gp_ref.abs().max().item()
 

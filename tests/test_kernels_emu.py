@@ -729,6 +729,19 @@ def test_mlp_backward_mma_kernels_match_fp16_oracle(C, M):
 
 
 # ------------------------------------------------------------------------------------------------ tile-binned sampling (opt-in)
+def _tsample_bwd(g_feat, half, xyz, M, R, C, inv_bound, fp16, perm, bin_end, ids, cnt, cap, gp):
+    """tnl_tsample_backward with its halo workspace (dirty on purpose) and, for a tile list, the matching tile map"""
+    wsz = kemu.lib().tnl_tsample_backward_workspace(R, C)
+    assert wsz == 4 * 3 * (R // 32) ** 2 * 65 * C
+    work = np.full(wsz // 4, np.nan, np.float32)
+    tmap = None
+    if ids is not None:
+        tmap = np.zeros(3 * (R // 32) ** 2, np.uint8)
+        tmap[ids[:int(cnt[0])]] = 1
+    kemu.call("tnl_tsample_backward", g_feat, half, xyz, M, R, C, inv_bound, int(fp16), perm, bin_end, ids, cnt, cap, tmap, gp, work,
+              work.nbytes, None)
+
+
 def _tap_sort(xyz, R, fp16, nv=None):
     M = len(xyz)
     inv_bound = float(np.float32(1.0) / np.float32(BOUND))
@@ -784,19 +797,18 @@ def test_tile_binned_sampling_equals_point_ordered_sampling(C, R, fp16, tiles):
     gp_ref = np.zeros((3, R, R, C), np.float32)
     kemu.call("tnl_sample_planes_backward", G_feat, 0, xyz, M, R, C, inv_bound, int(fp16), nv, None, gp_ref, None)
     gp = np.full((3, R, R, C), np.nan, np.float32)          # no zero fill: every listed tile is written
-    kemu.call("tnl_tsample_backward", G_feat, 0, xyz, M, R, C, inv_bound, int(fp16), perm, bin_end, ids, cnt, cap, gp, None)
+    _tsample_bwd(G_feat, 0, xyz, M, R, C, inv_bound, fp16, perm, bin_end, ids, cnt, cap, gp)
     assert np.isfinite(gp).all() and np.abs(gp - gp_ref).max() <= 2e-5 * np.abs(gp_ref).max()
     Gh = G_feat.astype(np.float16)
     gp_ref_h = np.zeros((3, R, R, C), np.float32)
     kemu.call("tnl_sample_planes_backward", Gh, 1, xyz, M, R, C, inv_bound, int(fp16), nv, None, gp_ref_h, None)
     gp_h = np.full((3, R, R, C), np.nan, np.float32)
-    kemu.call("tnl_tsample_backward", Gh, 1, xyz, M, R, C, inv_bound, int(fp16), perm, bin_end, ids, cnt, cap, gp_h, None)
+    _tsample_bwd(Gh, 1, xyz, M, R, C, inv_bound, fp16, perm, bin_end, ids, cnt, cap, gp_h)
     assert np.abs(gp_h - gp_ref_h).max() <= 2e-5 * np.abs(gp_ref_h).max()
-    if tiles == "list":         # a partial list: listed tiles as before, the others untouched
-        part = np.arange(0, 3 * G * G, 2, dtype=np.int32)
+    if tiles == "list":         # a partial list (two of the three planes: a listed tile's neighbours with points must be
+        part = np.arange(0, 2 * G * G, dtype=np.int32)   # listed too): listed tiles as before, the others untouched
         gp_p = np.full((3, R, R, C), 123.0, np.float32)
-        kemu.call("tnl_tsample_backward", G_feat, 0, xyz, M, R, C, inv_bound, int(fp16), perm, bin_end, part, np.array([len(part)], np.int32),
-                  len(part), gp_p, None)
+        _tsample_bwd(G_feat, 0, xyz, M, R, C, inv_bound, fp16, perm, bin_end, part, np.array([len(part)], np.int32), len(part), gp_p)
         tile_of = (np.arange(3)[:, None, None] * G + (np.arange(R) // 32)[None, :, None]) * G + (np.arange(R) // 32)[None, None, :]
         listed = np.isin(tile_of, part)[..., None]
         assert np.abs(np.where(listed, gp_p, 0) - np.where(listed, gp, 0)).max() <= 2e-5 * np.abs(gp).max()   # (order of the shared atomics)
@@ -810,7 +822,7 @@ def test_tile_binned_sampling_empty_and_argument_errors():
     perm, bin_end, work, inv_bound = _tap_sort(np.zeros((0, 3), np.float32), R, False)
     assert (bin_end == 0).all()
     gp = np.full((3, R, R, C), np.nan, np.float32)
-    kemu.call("tnl_tsample_backward", None, 0, None, 0, R, C, inv_bound, 0, None, bin_end, None, None, 0, gp, None)
+    _tsample_bwd(None, 0, None, 0, R, C, inv_bound, False, None, bin_end, None, None, 0, gp)
     assert (gp == 0).all()                                  # no points: every tile is written as zeros
     z16 = ctypes.c_void_p(64)
     assert lib.tnl_tsample_forward(z16, z16, 5, 48, 16, 1.0, 0, None, z16, z16, None, None, 0, z16, 0, None) == -1   # R % 32

@@ -10,12 +10,13 @@
 // that share its two in-plane tile indices, whatever their index along the third axis.  One CTA per plane tile:
 //   forward : stage the (TS+1)^2 x C texel tile (tile + the one-texel halo of the south / east taps) in shared memory once,
 //             stream the points of its G bins through it; the four corner reads of a point are shared-memory reads.
-//   backward: accumulate the corner contributions of a tile's OWN TS x TS texels in shared memory (shared atomics), from
-//             the points of its own bins and from the points of the north / west / north-west neighbour columns whose
-//             south / east taps fall into it; then write the tile with plain stores.  No global atomics, and no zero fill
-//             of the gradient buffer: every listed tile is written exactly once (zeros if nothing landed in it).
-// Per (point, plane) the backward reads 12 B of coordinates (x4 for the neighbour columns) and 2*C B of feature gradient
-// instead of issuing four C*4-byte vector atomics to L2.
+//   backward: accumulate the corner contributions of the tile's own points in shared memory (shared atomics), write the
+//             tile's TS x TS texels with plain stores and park the one-texel south / east halo in a small per-tile strip; a
+//             second, tiny pass adds each tile's west / north / north-west neighbour strips to its first column / row.
+//             No global atomics and no zero fill of the gradient buffer: every listed tile is written (zeros if nothing
+//             landed in it), every texel by exactly one CTA per pass.
+// Per (point, plane) the backward reads 12 B of coordinates and 2*C B of feature gradient instead of issuing four C*4-byte
+// vector atomics to L2.
 //
 // Results: forward bit-identical to sample.cu (same taps, same FMA order); backward identical up to the order of the
 // float additions (as between any two runs of sample.cu).
@@ -36,9 +37,8 @@ struct TCfg {
     static constexpr int SLOTS = C4 <= 4 ? 256 : (C4 <= 8 ? 128 : 64);
     static constexpr int NT = SLOTS * C4;               // thread <-> (point slot, 4-channel group); 1024 / 1024 / 768
     static constexpr size_t TILE_F = sizeof(float) * kTW * kTW * PITCH;   // forward: tile + halo
-    static constexpr size_t TILE_B = sizeof(float) * kTS * kTS * PITCH;   // backward: own texels only
     static size_t smem_fwd(uint32_t G) { return TILE_F + 2 * sizeof(uint32_t) * G; }        // + bin table (G entries)
-    static size_t smem_bwd(uint32_t G) { return TILE_B + 2 * sizeof(uint32_t) * 4 * G; }    // + bin table (4G entries)
+    static size_t smem_bwd(uint32_t G) { return TILE_F + 2 * sizeof(uint32_t) * G; }        // backward accumulates tile + halo too
 };
 
 struct TileGeom {
@@ -208,11 +208,19 @@ __global__ void k_tsample_zero_tail(void* __restrict__ feat_, uint32_t M, uint32
     }
 }
 
+// Backward, pass 1.  The CTA of tile (p, ty, tx) accumulates ALL four corner contributions of its own points (the G bins of
+// its column) in a (TS+1)^2 shared-memory tile, writes its own TS x TS texels to g_planes with plain stores, and parks the
+// south / east halo -- contributions that belong to the neighbours' first row / column -- in `halo[tile]` (65 texels:
+// row TS with lx = 0..TS, then column TS with ly = 0..TS-1).  Pass 2 (k_tsample_halo_fix) lets every tile add the strips of
+// its west / north / north-west neighbours to its own first column / row.  Every texel is written by exactly one CTA in
+// each pass: no atomics on global memory, no zero fill, and no CTA scans another tile's points.
+constexpr int kHaloTexels = 2 * kTS + 1;
+
 template <int C4, bool HALF>
 __global__ void __launch_bounds__(TCfg<C4>::NT, 1)
 k_tsample_bwd(const void* __restrict__ g_feat_, const float* __restrict__ xyz, int R, int G, float inv_bound, int fp16_coords,
               const uint32_t* __restrict__ bin_end, const int32_t* __restrict__ perm, const int32_t* __restrict__ tile_ids,
-              const int32_t* __restrict__ n_tiles, float* __restrict__ g_planes) {
+              const int32_t* __restrict__ n_tiles, float* __restrict__ g_planes, float* __restrict__ halo) {
     using Cfg = TCfg<C4>;
     constexpr int C = Cfg::C;
     extern __shared__ __align__(16) float tile[];
@@ -220,15 +228,10 @@ k_tsample_bwd(const void* __restrict__ g_feat_, const float* __restrict__ xyz, i
     if (!tile_geom(tile_ids, n_tiles, G, t)) return;
     const int tid = threadIdx.x, cq = tid % C4, slot = tid / C4;
     const int x_base = t.tx * kTS, y_base = t.ty * kTS;
-    for (int i = tid; i < kTS * kTS * Cfg::PITCH / 4; i += Cfg::NT) reinterpret_cast<float4*>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    // bins of the own column (entries 0 .. G-1), then of the west / north / north-west neighbour columns, of which only the
-    // points on the shared edge contribute
-    uint32_t* words = reinterpret_cast<uint32_t*>(tile + kTS * kTS * Cfg::PITCH);
-    const BinTable bt = build_bin_table(words, 4 * G, [&](int e, uint32_t& start, uint32_t& end) {
-        const int nb = e / G, k = e % G;
-        const int ta = t.tx - (nb & 1), tb = t.ty - (nb >> 1);
-        if (ta < 0 || tb < 0) { start = end = 0; return; }
-        bin_range(bin_end, t, G, ta, tb, k, start, end);
+    for (int i = tid; i < kTW * kTW * Cfg::PITCH / 4; i += Cfg::NT) reinterpret_cast<float4*>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t* words = reinterpret_cast<uint32_t*>(tile + kTW * kTW * Cfg::PITCH);
+    const BinTable bt = build_bin_table(words, G, [&](int k, uint32_t& start, uint32_t& end) {
+        bin_range(bin_end, t, G, t.tx, t.ty, k, start, end);
     });   // (its barriers also publish the zeroed tile)
     for (uint32_t j0 = slot; j0 < bt.total; j0 += kUnroll * Cfg::SLOTS) {
         uint32_t m[kUnroll];
@@ -238,34 +241,83 @@ k_tsample_bwd(const void* __restrict__ g_feat_, const float* __restrict__ xyz, i
             const uint32_t j = j0 + u * Cfg::SLOTS;
             m[u] = j < bt.total ? (uint32_t)__ldg(perm + bin_lookup(bt, j)) : 0xffffffffu;
         }
+        float4 g[kUnroll];
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u)
-            if (m[u] != 0xffffffffu) plane_coords(xyz, m[u], t.p, inv_bound, fp16_coords, gx[u], gy[u]);
+        for (int u = 0; u < kUnroll; ++u) {
+            if (m[u] == 0xffffffffu) continue;
+            plane_coords(xyz, m[u], t.p, inv_bound, fp16_coords, gx[u], gy[u]);
+            const size_t q4 = ((size_t)m[u] * 3 + t.p) * C4 + cq;
+            g[u] = HALF ? unpack4h(__ldg(reinterpret_cast<const uint2*>(g_feat_) + q4))
+                        : __ldg(reinterpret_cast<const float4*>(g_feat_) + q4);
+        }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
             if (m[u] == 0xffffffffu) continue;
             const Tap tp = make_tap(gx[u], gy[u], R);
-            // corners of this point inside the tile: local coordinates in [0, TS)
-            const int lx0 = tp.x0 - x_base, ly0 = tp.y0 - y_base;
-            const bool cx0 = lx0 >= 0 && lx0 < kTS, cx1 = tp.x1ok && lx0 + 1 >= 0 && lx0 + 1 < kTS;
-            const bool cy0 = ly0 >= 0 && ly0 < kTS, cy1 = tp.y1ok && ly0 + 1 >= 0 && ly0 + 1 < kTS;
-            if (!((cx0 || cx1) && (cy0 || cy1))) continue;
-            const size_t q4 = ((size_t)m[u] * 3 + t.p) * C4 + cq;
-            const float4 g = HALF ? unpack4h(__ldg(reinterpret_cast<const uint2*>(g_feat_) + q4))
-                                  : __ldg(reinterpret_cast<const float4*>(g_feat_) + q4);
-            float* base = tile + (ly0 * kTS + lx0) * Cfg::PITCH + 4 * cq;
-            if (cx0 && cy0) smem_add4(base, g, tp.nw);
-            if (cx1 && cy0) smem_add4(base + Cfg::PITCH, g, tp.ne);
-            if (cx0 && cy1) smem_add4(base + kTS * Cfg::PITCH, g, tp.sw);
-            if (cx1 && cy1) smem_add4(base + (kTS + 1) * Cfg::PITCH, g, tp.se);
+            float* base = tile + ((tp.y0 - y_base) * kTW + (tp.x0 - x_base)) * Cfg::PITCH + 4 * cq;
+            smem_add4(base, g[u], tp.nw);
+            if (tp.x1ok) smem_add4(base + Cfg::PITCH, g[u], tp.ne);
+            if (tp.y1ok) smem_add4(base + kTW * Cfg::PITCH, g[u], tp.sw);
+            if (tp.x1ok && tp.y1ok) smem_add4(base + (kTW + 1) * Cfg::PITCH, g[u], tp.se);
         }
     }
     __syncthreads();
     const int rows = min(kTS, R - y_base), cols = min(kTS, R - x_base);
     for (int i = tid; i < rows * cols * C4; i += Cfg::NT) {
         const int q = i % C4, xy = i / C4, lx = xy % cols, ly = xy / cols;
-        const float4 v = *reinterpret_cast<const float4*>(tile + (ly * kTS + lx) * Cfg::PITCH + 4 * q);
+        const float4 v = *reinterpret_cast<const float4*>(tile + (ly * kTW + lx) * Cfg::PITCH + 4 * q);
         *(reinterpret_cast<float4*>(g_planes + (((size_t)t.p * R + (y_base + ly)) * R + (x_base + lx)) * C) + q) = v;
+    }
+    const int id = (t.p * G + t.ty) * G + t.tx;
+    float4* strip = reinterpret_cast<float4*>(halo + (size_t)id * kHaloTexels * C);
+    for (int i = tid; i < kHaloTexels * C4; i += Cfg::NT) {
+        const int q = i % C4, e = i / C4;
+        const int lx = e <= kTS ? e : kTS, ly = e <= kTS ? kTS : e - kTW;   // row TS (lx 0..TS), then column TS (ly 0..TS-1)
+        strip[e * C4 + q] = *reinterpret_cast<const float4*>(tile + (ly * kTW + lx) * Cfg::PITCH + 4 * q);
+    }
+}
+
+// Backward, pass 2: first column / first row of every listed tile += the halo strips of its west / north / north-west
+// neighbours (those that were processed in pass 1: tile_map[id] != 0, or every tile when tile_map is NULL).
+template <int C4>
+__global__ void __launch_bounds__(256)
+k_tsample_halo_fix(int R, int G, const int32_t* __restrict__ tile_ids, const int32_t* __restrict__ n_tiles,
+                   const uint8_t* __restrict__ tile_map, const float* __restrict__ halo, float* __restrict__ g_planes) {
+    constexpr int C = 4 * C4;
+    TileGeom t;
+    if (!tile_geom(tile_ids, n_tiles, G, t)) return;
+    const int x_base = t.tx * kTS, y_base = t.ty * kTS;
+    auto listed = [&](int tx, int ty) {
+        if (tx < 0 || ty < 0) return false;
+        const int id = (t.p * G + ty) * G + tx;
+        return tile_map == nullptr || tile_map[id] != 0;
+    };
+    const bool west = listed(t.tx - 1, t.ty), north = listed(t.tx, t.ty - 1), nw = listed(t.tx - 1, t.ty - 1);
+    auto strip_of = [&](int tx, int ty) {
+        return reinterpret_cast<const float4*>(halo + (size_t)((t.p * G + ty) * G + tx) * kHaloTexels * C);
+    };
+    // work items: 0 = corner (0,0); 1..TS-1 = first row (lx, 0); TS..2TS-2 = first column (0, ly)
+    for (int i = threadIdx.x; i < (2 * kTS - 1) * C4; i += blockDim.x) {
+        const int q = i % C4, e = i / C4;
+        const int lx = (e > 0 && e < kTS) ? e : 0, ly = e >= kTS ? e - kTS + 1 : 0;
+        if (x_base + lx >= R || y_base + ly >= R) continue;
+        float4 add = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lx == 0 && west) {          // west neighbour's column TS, row ly
+            const float4 v = __ldg(strip_of(t.tx - 1, t.ty) + (kTW + ly) * C4 + q);
+            add.x += v.x; add.y += v.y; add.z += v.z; add.w += v.w;
+        }
+        if (ly == 0 && north) {         // north neighbour's row TS, column lx
+            const float4 v = __ldg(strip_of(t.tx, t.ty - 1) + lx * C4 + q);
+            add.x += v.x; add.y += v.y; add.z += v.z; add.w += v.w;
+        }
+        if (lx == 0 && ly == 0 && nw) { // north-west neighbour's corner (TS, TS)
+            const float4 v = __ldg(strip_of(t.tx - 1, t.ty - 1) + kTS * C4 + q);
+            add.x += v.x; add.y += v.y; add.z += v.z; add.w += v.w;
+        }
+        float4* dst = reinterpret_cast<float4*>(g_planes + (((size_t)t.p * R + (y_base + ly)) * R + (x_base + lx)) * C) + q;
+        float4 cur = *dst;
+        cur.x += add.x; cur.y += add.y; cur.z += add.z; cur.w += add.w;
+        *dst = cur;
     }
 }
 
@@ -292,7 +344,8 @@ __global__ void k_tap_hist(const float* __restrict__ xyz, uint32_t M, const int3
 template <int C4>
 static int launch_tsample(bool fwd, const void* in, void* out, const float* xyz, uint32_t R, uint32_t G, float inv_bound,
                           int fp16_coords, const uint32_t* bin_end, const int32_t* perm, const int32_t* tile_ids,
-                          const int32_t* n_tiles, uint32_t grid, int half, cudaStream_t s) {
+                          const int32_t* n_tiles, uint32_t grid, int half, cudaStream_t s, const uint8_t* tile_map = nullptr,
+                          float* halo = nullptr) {
     using Cfg = TCfg<C4>;
     const size_t smem_f = Cfg::smem_fwd(G), smem_b = Cfg::smem_bwd(G);
     static bool attr = false;
@@ -307,8 +360,9 @@ static int launch_tsample(bool fwd, const void* in, void* out, const float* xyz,
         if (half) k_tsample_fwd<C4, true><<<grid, Cfg::NT, smem_f, s>>>(static_cast<const float*>(in), xyz, (int)R, (int)G, inv_bound, fp16_coords, bin_end, perm, tile_ids, n_tiles, out);
         else k_tsample_fwd<C4, false><<<grid, Cfg::NT, smem_f, s>>>(static_cast<const float*>(in), xyz, (int)R, (int)G, inv_bound, fp16_coords, bin_end, perm, tile_ids, n_tiles, out);
     } else {
-        if (half) k_tsample_bwd<C4, true><<<grid, Cfg::NT, smem_b, s>>>(in, xyz, (int)R, (int)G, inv_bound, fp16_coords, bin_end, perm, tile_ids, n_tiles, static_cast<float*>(out));
-        else k_tsample_bwd<C4, false><<<grid, Cfg::NT, smem_b, s>>>(in, xyz, (int)R, (int)G, inv_bound, fp16_coords, bin_end, perm, tile_ids, n_tiles, static_cast<float*>(out));
+        if (half) k_tsample_bwd<C4, true><<<grid, Cfg::NT, smem_b, s>>>(in, xyz, (int)R, (int)G, inv_bound, fp16_coords, bin_end, perm, tile_ids, n_tiles, static_cast<float*>(out), halo);
+        else k_tsample_bwd<C4, false><<<grid, Cfg::NT, smem_b, s>>>(in, xyz, (int)R, (int)G, inv_bound, fp16_coords, bin_end, perm, tile_ids, n_tiles, static_cast<float*>(out), halo);
+        k_tsample_halo_fix<C4><<<grid, 256, 0, s>>>((int)R, (int)G, tile_ids, n_tiles, tile_map, halo, static_cast<float*>(out));
     }
     return 0;
 }
@@ -379,22 +433,36 @@ int tnl_tsample_forward(const float* planes, const float* xyz, uint32_t M, uint3
     return finish_launch("tsample_forward");
 }
 
+size_t tnl_tsample_backward_workspace(uint32_t R, uint32_t C) {
+    if (!tsample_geometry_ok(R, C)) return 0;
+    const size_t G = R / kTS;
+    return sizeof(float) * 3 * G * G * (size_t)kHaloTexels * C;
+}
+
 int tnl_tsample_backward(const void* g_feat, int feat_fp16, const float* xyz, uint32_t M, uint32_t R, uint32_t C, float inv_bound,
                          int fp16_coords, const int32_t* perm, const void* bin_end, const int32_t* tile_ids, const int32_t* n_tiles,
-                         uint32_t max_tiles, float* g_planes, tnl_stream_t stream) {
+                         uint32_t max_tiles, const uint8_t* tile_map, float* g_planes, void* workspace, size_t workspace_bytes,
+                         tnl_stream_t stream) {
     TNL_ARG_CHECK(g_planes && bin_end, "null pointer");
     TNL_ARG_CHECK(M == 0 || (g_feat && xyz && perm), "null pointer");
     TNL_ARG_CHECK(tsample_geometry_ok(R, C), "tile-binned sampling needs R % 32 == 0, R <= 8192 and C in {16, 32, 48}");
     TNL_ARG_CHECK((tile_ids == nullptr) == (n_tiles == nullptr), "tile_ids and n_tiles must be given together");
-    TNL_ARG_CHECK(((uintptr_t)g_planes & 15) == 0 && ((uintptr_t)g_feat & 15) == 0, "g_planes/g_feat must be 16-byte aligned");
+    TNL_ARG_CHECK(tile_ids != nullptr || tile_map == nullptr, "a tile map only makes sense with a tile list");
+    TNL_ARG_CHECK(((uintptr_t)g_planes & 15) == 0 && ((uintptr_t)g_feat & 15) == 0 && ((uintptr_t)workspace & 15) == 0,
+                  "g_planes / g_feat / workspace must be 16-byte aligned");
+    if (workspace == nullptr || workspace_bytes < tnl_tsample_backward_workspace(R, C)) {
+        set_error("tsample_backward: workspace too small");
+        return TNL_ERR_WORKSPACE;
+    }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const uint32_t G = R / kTS;
     const uint32_t grid = tile_ids ? max_tiles : 3 * G * G;
     if (grid == 0) return 0;
     const uint32_t* be = static_cast<const uint32_t*>(bin_end);
-    if (C == 16) launch_tsample<4>(false, g_feat, g_planes, xyz, R, G, inv_bound, fp16_coords, be, perm, tile_ids, n_tiles, grid, feat_fp16, s);
-    else if (C == 32) launch_tsample<8>(false, g_feat, g_planes, xyz, R, G, inv_bound, fp16_coords, be, perm, tile_ids, n_tiles, grid, feat_fp16, s);
-    else launch_tsample<12>(false, g_feat, g_planes, xyz, R, G, inv_bound, fp16_coords, be, perm, tile_ids, n_tiles, grid, feat_fp16, s);
+    float* halo = static_cast<float*>(workspace);
+    if (C == 16) launch_tsample<4>(false, g_feat, g_planes, xyz, R, G, inv_bound, fp16_coords, be, perm, tile_ids, n_tiles, grid, feat_fp16, s, tile_map, halo);
+    else if (C == 32) launch_tsample<8>(false, g_feat, g_planes, xyz, R, G, inv_bound, fp16_coords, be, perm, tile_ids, n_tiles, grid, feat_fp16, s, tile_map, halo);
+    else launch_tsample<12>(false, g_feat, g_planes, xyz, R, G, inv_bound, fp16_coords, be, perm, tile_ids, n_tiles, grid, feat_fp16, s, tile_map, halo);
     return finish_launch("tsample_backward");
 }
 

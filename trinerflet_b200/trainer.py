@@ -94,7 +94,7 @@ class TrainStep:
         # tile-binned sampling (opt-in, enc.tiled_sampling): a work-list step only needs the tiles the IDWT backward reads
         # (the plan's zero list); the debug mode of the exchange sums the whole gradient buffer, so it gets every tile
         z = self._plan.zero if (use_plan and self._plan is not None) else None
-        enc.sampling_tiles = (z["ids"], z["count"], z["cap"]) if (z is not None and not (self.reducer is not None and self.reducer.check)) else None
+        enc.sampling_tiles = (z["ids"], z["count"], z["cap"], z["map"]) if (z is not None and not (self.reducer is not None and self.reducer.check)) else None
         prefetch = self.prefetch_planes and not do_update and rays_o.is_cuda
         # work-list steps drive the IDWT backward themselves (two parts, see SplitIdwtBackward); its gradient-independent
         # part goes to the prefetch stream right away and overlaps the render

@@ -319,7 +319,7 @@ def tap_sort(coords, bound, R, fp16_coords, n_valid=None):
 
 class _SamplePlanesTiled(Function):
     """Opt-in tile-binned form of _SamplePlanes (csrc/tsample.cu): same features (bit-identical), gradient written tile by tile
-    with plain stores.  `tiles` = (ids, count, capacity) restricts both directions to the listed plane tiles (the work-list
+    with plain stores.  `tiles` = (ids, count, capacity, map) restricts both directions to the listed plane tiles (the work-list
     training step passes idwt_plan's zero list: every tile the IDWT backward reads); None = every tile."""
 
     @staticmethod
@@ -332,16 +332,17 @@ class _SamplePlanesTiled(Function):
         C, R = planes.shape[1], planes.shape[2]
         feat = torch.empty(M, 3 * C, device=planes.device, dtype=torch.float16 if half_out else torch.float32)
         inv = _inv_bound(bound)
-        ids, cnt, cap = tiles if tiles is not None else (None, None, 0)
+        ids, cnt, cap, tmap = tiles if tiles is not None else (None, None, 0, None)
         call("tnl_tsample_forward", ptr(planes_cl), ptr(coords), M, R, C, inv, int(bool(fp16_coords)), ptr(n_valid), ptr(perm),
              ptr(bins), ptr(ids), ptr(cnt), int(cap), ptr(feat), int(bool(half_out)), stream())
-        ctx.save_for_backward(coords, perm, bins, ids if ids is not None else torch.empty(0), cnt if cnt is not None else torch.empty(0))
+        ctx.save_for_backward(coords, perm, bins, ids if ids is not None else torch.empty(0), cnt if cnt is not None else torch.empty(0),
+                              tmap if tmap is not None else torch.empty(0))
         ctx.meta = (M, R, C, inv, int(bool(fp16_coords)), bool(half_out), tiles is not None, int(cap))
         return feat
 
     @staticmethod
     def backward(ctx, g_feat):
-        coords, perm, bins, ids, cnt = ctx.saved_tensors
+        coords, perm, bins, ids, cnt, tmap = ctx.saved_tensors
         M, R, C, inv, fp16_coords, half, has_tiles, cap = ctx.meta
         g_feat = g_feat.contiguous().half() if half else g_feat.contiguous().float()
         if ctx.grad_buf is not None:
@@ -350,8 +351,11 @@ class _SamplePlanesTiled(Function):
             torch.cuda.current_stream().wait_event(ready)
         else:   # no zero fill: every listed tile is written; with a tile list the rest of the buffer is never read
             g_planes = cl_empty_planes(C, R, device=g_feat.device)
+        from . import _lib
+        halo = torch.empty(max(int(_lib.load().tnl_tsample_backward_workspace(R, C)), 16), dtype=torch.uint8, device=g_feat.device)
         call("tnl_tsample_backward", ptr(g_feat), int(half), ptr(coords), M, R, C, inv, fp16_coords, ptr(perm), ptr(bins),
-             ptr(ids) if has_tiles else None, ptr(cnt) if has_tiles else None, cap, ptr(g_planes), stream())
+             ptr(ids) if has_tiles else None, ptr(cnt) if has_tiles else None, cap, ptr(tmap) if has_tiles else None, ptr(g_planes),
+             ptr(halo), halo.numel(), stream())
         return g_planes, None, None, None, None, None, None, None, None, None
 
 
@@ -432,7 +436,7 @@ class TriPlaneVolume(nn.Module):
         # (see idwt_plan.py); None = dense planes, the reference's semantics
         self.idwt_plan = None
         # opt-in: tile-binned sampling kernels (csrc/tsample.cu) when the caller supplies tap-sorted points (tap_sort);
-        # sampling_tiles = (ids, count, capacity) restricts them to the plane tiles a work-list step touches
+        # sampling_tiles = (ids, count, capacity, map) restricts them to the plane tiles a work-list step touches
         self.tiled_sampling = False
         self.sampling_tiles = None
         self._init_plane_features(planes_features)
