@@ -228,11 +228,24 @@ k_tsample_bwd(const void* __restrict__ g_feat_, const float* __restrict__ xyz, i
     if (!tile_geom(tile_ids, n_tiles, G, t)) return;
     const int tid = threadIdx.x, cq = tid % C4, slot = tid / C4;
     const int x_base = t.tx * kTS, y_base = t.ty * kTS;
-    for (int i = tid; i < kTW * kTW * Cfg::PITCH / 4; i += Cfg::NT) reinterpret_cast<float4*>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t* words = reinterpret_cast<uint32_t*>(tile + kTW * kTW * Cfg::PITCH);
     const BinTable bt = build_bin_table(words, G, [&](int k, uint32_t& start, uint32_t& end) {
         bin_range(bin_end, t, G, t.tx, t.ty, k, start, end);
-    });   // (its barriers also publish the zeroed tile)
+    });
+    const int id = (t.p * G + t.ty) * G + t.tx;
+    float4* strip = reinterpret_cast<float4*>(halo + (size_t)id * kHaloTexels * C);
+    const int rows = min(kTS, R - y_base), cols = min(kTS, R - x_base);
+    if (bt.total == 0) {   // a listed tile without points (the halo tiles of a work-list step): zeros, straight from registers
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < rows * cols * C4; i += Cfg::NT) {
+            const int q = i % C4, xy = i / C4, lx = xy % cols, ly = xy / cols;
+            *(reinterpret_cast<float4*>(g_planes + (((size_t)t.p * R + (y_base + ly)) * R + (x_base + lx)) * C) + q) = z;
+        }
+        for (int i = tid; i < kHaloTexels * C4; i += Cfg::NT) strip[i] = z;
+        return;
+    }
+    for (int i = tid; i < kTW * kTW * Cfg::PITCH / 4; i += Cfg::NT) reinterpret_cast<float4*>(tile)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
     for (uint32_t j0 = slot; j0 < bt.total; j0 += kUnroll * Cfg::SLOTS) {
         uint32_t m[kUnroll];
         float gx[kUnroll], gy[kUnroll];
@@ -262,14 +275,11 @@ k_tsample_bwd(const void* __restrict__ g_feat_, const float* __restrict__ xyz, i
         }
     }
     __syncthreads();
-    const int rows = min(kTS, R - y_base), cols = min(kTS, R - x_base);
     for (int i = tid; i < rows * cols * C4; i += Cfg::NT) {
         const int q = i % C4, xy = i / C4, lx = xy % cols, ly = xy / cols;
         const float4 v = *reinterpret_cast<const float4*>(tile + (ly * kTW + lx) * Cfg::PITCH + 4 * q);
         *(reinterpret_cast<float4*>(g_planes + (((size_t)t.p * R + (y_base + ly)) * R + (x_base + lx)) * C) + q) = v;
     }
-    const int id = (t.p * G + t.ty) * G + t.tx;
-    float4* strip = reinterpret_cast<float4*>(halo + (size_t)id * kHaloTexels * C);
     for (int i = tid; i < kHaloTexels * C4; i += Cfg::NT) {
         const int q = i % C4, e = i / C4;
         const int lx = e <= kTS ? e : kTS, ly = e <= kTS ? kTS : e - kTW;   // row TS (lx 0..TS), then column TS (ly 0..TS-1)
