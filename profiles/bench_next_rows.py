@@ -5,9 +5,10 @@
   render   SURVEY.md 8f-3: full-frame inference (800x800, max_steps as given) with the host-driven loop
            (model.infer_chunk = 0: one read-back per iteration) and the device-driven loop (infer_chunk = 4 / 8 / 16).
 
+  sampling kernel-level A/B of the point-ordered and the tile-binned gather / scatter at base-light size.
   wide     the "large" config (C=48, hidden 128) through the library path and through the hybrid 128-wide backward.
 
-  python profiles/bench_next_rows.py feeder|render|wide [--config base_light] [--max-steps 1024]
+  python profiles/bench_next_rows.py feeder|render|wide|sampling [--config base_light] [--max-steps 1024]
 
 CUDA events around the whole operation, 3 warm-ups, median of 5; prints one JSON line per measurement."""
 import argparse
@@ -88,6 +89,49 @@ def bench_render(config="base_light", max_steps=1024, chunks=(0, 4, 8, 16)):
                           "iterations": loop.iterations_done if loop else None, "state_reads": loop.reads if loop else None}))
 
 
+def bench_sampling(C=32, R=2048, n_rays=60000):
+    """kernel-level A/B at base-light size: cell sort + point-ordered gather / scatter (+ tile-wise zero fill) against tap
+    sort + tile-binned gather / scatter, on the samples a real march produces; tile list = the plan's zero list."""
+    import numpy as np
+    from trinerflet_b200 import _lib, raymarching as rm
+    from trinerflet_b200._lib import call, ptr, stream
+    from trinerflet_b200.idwt_plan import IdwtPlan
+    from trinerflet_b200.network import NeRFNetwork
+    from trinerflet_b200.triplane_encoder import cell_sort, cl_empty_planes, tap_sort
+    net = NeRFNetwork(bound=1.5, cuda_ray=True, density_thresh=10, min_near=0.2, triplane_channels=C, triplane_resolution=R,
+                      triplane_wavelet_levels=R // 64).cuda()
+    scene.install_ball_occupancy(net, 0.75)
+    plan = IdwtPlan.from_model(net)
+    z = plan.zero
+    sc = scene.make_scene()
+    ro, rd, _ = scene.sample_batch(sc, n_rays, torch.Generator().manual_seed(0))
+    ro, rd = ro.cuda(), rd.cuda()
+    nears, fars = rm.near_far_from_aabb(ro, rd, net.aabb_train, 0.2)
+    cnt = torch.zeros(2, dtype=torch.int32, device="cuda")
+    xyzs, dirs, deltas, rays = rm.march_rays_train(ro, rd, 1.5, net.density_bitfield, 2, 128, nears, fars, cnt, -1, True, 128, True, 0, 1024)
+    M = xyzs.shape[0]
+    nv = cnt[0:1].clone()
+    planes = cl_empty_planes(C, R, device="cuda").normal_().permute(0, 2, 3, 1)
+    feat = torch.empty(M, 3 * C, device="cuda", dtype=torch.float16)
+    gfeat = torch.randn(M, 3 * C, device="cuda").half()
+    gpl = cl_empty_planes(C, R, device="cuda").permute(0, 2, 3, 1)
+    inv = float(np.float32(1) / np.float32(1.5))
+    perm = cell_sort(xyzs, 1.5, nv, 64)
+    res = {"what": "sampling", "M": M, "C": C, "R": R}
+    res["ms_cell_sort"] = timed(lambda: cell_sort(xyzs, 1.5, nv, 64))
+    res["ms_point_fwd"] = timed(lambda: call("tnl_sample_planes_forward", ptr(planes), ptr(xyzs), M, R, C, inv, 1, ptr(nv), ptr(perm), ptr(feat), 1, stream()))
+    res["ms_zero_fill"] = timed(lambda: plan.zero_gradient_tiles(gpl))
+    res["ms_point_bwd"] = timed(lambda: call("tnl_sample_planes_backward", ptr(gfeat), 1, ptr(xyzs), M, R, C, inv, 1, ptr(nv), ptr(perm), ptr(gpl), stream()))
+    tperm, bins = tap_sort(xyzs, 1.5, R, True, nv)
+    halo = torch.empty(_lib.load().tnl_tsample_backward_workspace(R, C), dtype=torch.uint8, device="cuda")
+    res["ms_tap_sort"] = timed(lambda: tap_sort(xyzs, 1.5, R, True, nv))
+    res["ms_tiled_fwd"] = timed(lambda: call("tnl_tsample_forward", ptr(planes), ptr(xyzs), M, R, C, inv, 1, ptr(nv), ptr(tperm), ptr(bins),
+                                             ptr(z["ids"]), ptr(z["count"]), z["cap"], ptr(feat), 1, stream()))
+    res["ms_tiled_bwd"] = timed(lambda: call("tnl_tsample_backward", ptr(gfeat), 1, ptr(xyzs), M, R, C, inv, 1, ptr(tperm), ptr(bins),
+                                             ptr(z["ids"]), ptr(z["count"]), z["cap"], ptr(z["map"]), ptr(gpl), ptr(halo), halo.numel(), stream()))
+    print(json.dumps(res))
+
+
 def bench_wide(n_rays=60000):
     """'large' config (C=48, hidden 128): one eager fwd+bwd step through the library path (default) and through the hybrid
     backward (model.wide_fused_backward = True: fused forward, fused input-gradient chain + library GEMMs)."""
@@ -124,7 +168,7 @@ def bench_wide(n_rays=60000):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["feeder", "render", "wide"])
+    ap.add_argument("what", choices=["feeder", "render", "wide", "sampling"])
     ap.add_argument("--config", default="base_light")
     ap.add_argument("--max-steps", type=int, default=1024)
     a = ap.parse_args()
@@ -132,5 +176,7 @@ if __name__ == "__main__":
         bench_feeder()
     elif a.what == "wide":
         bench_wide()
+    elif a.what == "sampling":
+        bench_sampling()
     else:
         bench_render(a.config, a.max_steps)
