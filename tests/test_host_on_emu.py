@@ -496,3 +496,38 @@ def test_field_mlp_function_wide_heads_hybrid_backward(emu, C, half):
     assert f_g.grad.dtype == f_g.dtype and rel_l2(f_g.grad.float(), f_o.grad) <= 1e-2
     for a, b in zip(W_g, W_o):
         assert a.grad.shape == b.grad.shape and rel_l2(a.grad, b.grad) <= 1e-2
+
+
+def test_fp16_training_configuration_matches_fp16_oracle(emu, monkeypatch):
+    """the configuration every reference command trains with (--fp16): fp16 feature stream out of the sampler, fp16-rounded
+    projected coordinates, the fused MLP kernels (here the mma.sync ones: the host build reports the tcgen05 kernels as
+    unsupported) with their n_valid path -- against oracle/pipeline.py with its fp16-autocast emulation.  CUDA autocast
+    cannot be switched on without a device, so the two queries the package makes about it are answered "fp16" for the test."""
+    from oracle import pipeline
+    from trinerflet_b200 import scene, trainer
+    monkeypatch.setattr(torch, "is_autocast_enabled", lambda *a, **k: True)
+    monkeypatch.setattr(torch, "get_autocast_dtype", lambda *a, **k: torch.float16)
+    net = _model()
+    net.train()
+    sc = scene.make_scene()
+    N = 320
+    ro, rd, tgt = scene.sample_batch(sc, N, torch.Generator().manual_seed(3))
+    opt = trainer.default_opt(fp16=False)            # (no real autocast context, no loss scaling: scale 1)
+    ts = trainer.TrainStep(net, opt, None)
+    torch.manual_seed(5)
+    loss = ts.forward_backward(ro, rd, tgt, update_grid=False)
+    M = int(net.step_counter[0, 0])
+    torch.manual_seed(5)
+    noises = torch.rand(N).numpy()
+    pf = net.encoder.planes_features.detach().clone().contiguous().requires_grad_(True)
+    coefs = [p.detach().clone().contiguous().requires_grad_(True) for p in net.encoder.planes_features_wavelet_coefs]
+    W = [w.detach().clone().requires_grad_(True) for w in net._weights()]
+    loss_o, M_o = pipeline.train_step(pf, coefs, W, ro, rd, tgt, net.density_bitfield.numpy(), noises, lam=opt.wavelet_regularization,
+                                      fp16=True)
+    assert M_o == M
+    assert abs(float(loss) - loss_o) <= 2e-3 * abs(loss_o)
+    assert rel_l2(net.encoder.planes_features.grad, pf.grad) <= 1e-2
+    for p, c in zip(net.encoder.planes_features_wavelet_coefs, coefs):
+        assert rel_l2(p.grad, c.grad) <= 1e-2
+    for w, wo in zip(net._weights(), W):
+        assert rel_l2(w.grad, wo.grad) <= 1e-2
