@@ -23,12 +23,13 @@ def emu(monkeypatch):
     return emu_backend.install(monkeypatch)
 
 
-def _model(seed=0, radius=0.75):
+def _model(seed=0, radius=0.75, hidden=None):
     from trinerflet_b200 import scene
     from trinerflet_b200.network import NeRFNetwork
     c = scene.CONFIGS["tiny"]
+    hidden = hidden or c["hidden"]
     net = NeRFNetwork(bound=BOUND, cuda_ray=True, density_thresh=10, min_near=0.2, triplane_channels=c["C"],
-                      triplane_resolution=c["R"], triplane_wavelet_levels=c["S"], hidden_dim=c["hidden"], hidden_dim_color=c["hidden"])
+                      triplane_resolution=c["R"], triplane_wavelet_levels=c["S"], hidden_dim=hidden, hidden_dim_color=hidden)
     scene.init_model_(net, seed=seed)
     scene.install_ball_occupancy(net, radius)
     return net
@@ -498,7 +499,8 @@ def test_field_mlp_function_wide_heads_hybrid_backward(emu, C, half):
         assert a.grad.shape == b.grad.shape and rel_l2(a.grad, b.grad) <= 1e-2
 
 
-def test_fp16_training_configuration_matches_fp16_oracle(emu, monkeypatch):
+@pytest.mark.parametrize("hidden", [64, 128])
+def test_fp16_training_configuration_matches_fp16_oracle(emu, monkeypatch, hidden):
     """the configuration every reference command trains with (--fp16): fp16 feature stream out of the sampler, fp16-rounded
     projected coordinates, the fused MLP kernels (here the mma.sync ones: the host build reports the tcgen05 kernels as
     unsupported) with their n_valid path -- against oracle/pipeline.py with its fp16-autocast emulation.  CUDA autocast
@@ -507,7 +509,8 @@ def test_fp16_training_configuration_matches_fp16_oracle(emu, monkeypatch):
     from trinerflet_b200 import scene, trainer
     monkeypatch.setattr(torch, "is_autocast_enabled", lambda *a, **k: True)
     monkeypatch.setattr(torch, "get_autocast_dtype", lambda *a, **k: torch.float16)
-    net = _model()
+    net = _model(hidden=hidden)
+    net.wide_fused_backward = hidden == 128          # "large" heads: fused forward + hybrid backward (chain kernel + GEMMs)
     net.train()
     sc = scene.make_scene()
     N = 320
