@@ -534,3 +534,19 @@ def test_fp16_training_configuration_matches_fp16_oracle(emu, monkeypatch, hidde
         assert rel_l2(p.grad, c.grad) <= 1e-2
     for w, wo in zip(net._weights(), W):
         assert rel_l2(w.grad, wo.grad) <= 1e-2
+
+
+def test_smoke_opt_in_section_runs(emu, monkeypatch, capsys):
+    """__graft_entry__._smoke_opt_ins (the informational part of smoke()) on the host build: all three lines report success"""
+    import __graft_entry__ as ge
+    from trinerflet_b200 import scene, trainer
+    from trinerflet_b200.network import NeRFNetwork
+    monkeypatch.setattr(torch.nn.Module, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    c = scene.CONFIGS["tiny"]
+    sc = scene.make_scene()
+    ro, rd, tgt = scene.sample_batch(sc, 256, torch.Generator().manual_seed(0))
+    ge._smoke_opt_ins(scene, trainer, NeRFNetwork, c, sc, ro, rd, tgt)
+    out = capsys.readouterr().out
+    assert out.count("smoke opt-in") == 3 and "FAILED" not in out, out
+    assert "rays_o equal: True" in out
