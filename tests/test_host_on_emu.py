@@ -550,3 +550,44 @@ def test_smoke_opt_in_section_runs(emu, monkeypatch, capsys):
     out = capsys.readouterr().out
     assert out.count("smoke opt-in") == 3 and "FAILED" not in out, out
     assert "rays_o equal: True" in out
+
+
+def _render_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from _pytest.monkeypatch import MonkeyPatch
+    mpatch = MonkeyPatch()
+    try:
+        emu_backend.install(mpatch)
+        os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from trinerflet_b200 import parallel, scene
+        net = _model()
+        net.eval()
+        net.infer_chunk = 4 if rank == 1 else 0          # the two loops give identical pixels: mix them across ranks
+        ro, rd = scene.full_frame(scene.make_scene(), 5)
+        pick = torch.arange(0, ro.shape[0], 797)[:801]    # 801 rays: ragged shards (401 + 400)
+        ro, rd = ro[pick].contiguous(), rd[pick].contiguous()
+        with torch.no_grad():
+            full = net.render(ro.unsqueeze(0), rd.unsqueeze(0), staged=True, bg_color=1, perturb=False, max_steps=256)
+            net.infer_chunk = 4 if rank == 1 else 0
+            frame = parallel.render_frame_sharded(net, ro, rd, rank, world, bg_color=1, max_steps=256)
+        ok = frame["image"].shape == (801, 3) and frame["depth"].shape == (801,) and frame["weights_sum"].shape == (801,)
+        ok = ok and (frame["image"] - full["image"].view(-1, 3)).abs().max().item() <= 1e-4
+        ok = ok and (frame["weights_sum"] - full["weights_sum"].view(-1)).abs().max().item() <= 1e-4
+        out[rank] = bool(ok)
+        dist.destroy_process_group()
+    finally:
+        mpatch.undo()
+
+
+def test_full_frame_render_sharded_world2_gloo():
+    """BASELINE.json configs[4] / SURVEY.md 8e: a frame rendered as contiguous ray tiles on two ranks (no collective until the
+    final gather of image / depth / weights_sum) equals the frame rendered by one rank; the shards are ragged"""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_render_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] and out[1]
