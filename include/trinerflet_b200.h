@@ -182,35 +182,6 @@ int tnl_sample_planes_backward(const void* g_feat, int feat_fp16, const float* x
                                float inv_bound, int fp16_coords, const int32_t* n_valid, const int32_t* perm,
                                float* g_planes, tnl_stream_t stream);
 
-/* Tile-binned variant of the two sampling calls above (OPT-IN; same results: forward bit-identical, backward up to the order
- * of the float additions).  The points are counting-sorted by the 32 x 32-texel tile of their north-west tap on every axis
- * (tnl_tap_sort; key = (t_z * R/32 + t_y) * R/32 + t_x, computed with exactly the sampler's coordinate arithmetic); one CTA per plane
- * tile then serves the points of the R/32 bins that project onto it out of shared memory: the forward stages the 33 x 33 x C
- * texels once, the backward accumulates the tile in shared memory and writes it with plain stores -- no global atomics and
- * no zero fill of g_planes (every listed tile is written exactly once, zeros included).  R % 32 == 0, R <= 8192,
- * C in {16, 32, 48}.
- *   tnl_tap_sort: perm [M] as tnl_cell_sort; afterwards the first (R/32)^3 + 1 uint32 of `workspace` hold the END offset of
- *     every bin in perm (bin k = perm[end[k-1] .. end[k]), rows >= *n_valid in the last bin): pass it as `bin_end`.
- *   tile_ids / n_tiles (device, may both be NULL = every tile of the three planes): plane tiles to process, id =
- *     (p * R/32 + ty) * R/32 + tx as tnl_mark_dirty_tiles numbers them; the grid is sized by max_tiles.  The backward must be
- *     given every tile that is read afterwards (idwt_plan's zero list) and every tile that holds points; points whose
- *     north-west tap lies in an unlisted tile are dropped (including what their south / east taps would add to listed tiles).
- *   backward: two passes (tile + one-texel halo accumulated in shared memory -> own texels to g_planes, halo to a per-tile
- *     strip in `workspace`; then every tile adds its neighbours' strips to its first row / column).  tile_map (device uint8
- *     [3 * (R/32)^2], required with a tile list: 1 for every listed tile) tells the second pass which neighbours exist. */
-size_t tnl_tap_sort_workspace(uint32_t M, uint32_t R);
-int tnl_tap_sort(const float* xyz, uint32_t M, const int32_t* n_valid, float inv_bound, int fp16_coords, uint32_t R,
-                 int32_t* perm, void* workspace, size_t workspace_bytes, tnl_stream_t stream);
-int tnl_tsample_forward(const float* planes, const float* xyz, uint32_t M, uint32_t R, uint32_t C, float inv_bound,
-                        int fp16_coords, const int32_t* n_valid, const int32_t* perm, const void* bin_end,
-                        const int32_t* tile_ids, const int32_t* n_tiles, uint32_t max_tiles, void* feat, int feat_fp16,
-                        tnl_stream_t stream);
-size_t tnl_tsample_backward_workspace(uint32_t R, uint32_t C);
-int tnl_tsample_backward(const void* g_feat, int feat_fp16, const float* xyz, uint32_t M, uint32_t R, uint32_t C,
-                         float inv_bound, int fp16_coords, const int32_t* perm, const void* bin_end, const int32_t* tile_ids,
-                         const int32_t* n_tiles, uint32_t max_tiles, const uint8_t* tile_map, float* g_planes, void* workspace,
-                         size_t workspace_bytes, tnl_stream_t stream);
-
 /* Spatial binning of sample points: perm[i] = row of the i-th point in the order of a G^3 Morton grid over
  * [-bound, bound]^3 (rows >= *n_valid last).  Kernels taking `perm` visit points in that order, which makes the
  * plane gathers / gradient scatters of neighbouring threads hit the same texels (L2 locality); per-point results

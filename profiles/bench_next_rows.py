@@ -5,7 +5,7 @@
   render   SURVEY.md 8f-3: full-frame inference (800x800, max_steps as given) with the host-driven loop
            (model.infer_chunk = 0: one read-back per iteration) and the device-driven loop (infer_chunk = 4 / 8 / 16).
 
-  sampling kernel-level A/B of the point-ordered and the tile-binned gather / scatter at base-light size.
+  sampling kernel-level timing of the point-ordered gather / scatter at base-light size.
   wide     the "large" config (C=48, hidden 128) through the library path and through the hybrid 128-wide backward.
 
   python profiles/bench_next_rows.py feeder|render|wide|sampling [--config base_light] [--max-steps 1024]
@@ -90,14 +90,14 @@ def bench_render(config="base_light", max_steps=1024, chunks=(0, 4, 8, 16)):
 
 
 def bench_sampling(C=32, R=2048, n_rays=60000):
-    """kernel-level A/B at base-light size: cell sort + point-ordered gather / scatter (+ tile-wise zero fill) against tap
-    sort + tile-binned gather / scatter, on the samples a real march produces; tile list = the plan's zero list."""
+    """kernel-level timing at base-light size: cell sort + point-ordered gather / scatter (+ tile-wise zero fill) on the samples
+    a real march produces."""
     import numpy as np
     from trinerflet_b200 import _lib, raymarching as rm
     from trinerflet_b200._lib import call, ptr, stream
     from trinerflet_b200.idwt_plan import IdwtPlan
     from trinerflet_b200.network import NeRFNetwork
-    from trinerflet_b200.triplane_encoder import cell_sort, cl_empty_planes, tap_sort
+    from trinerflet_b200.triplane_encoder import cell_sort, cl_empty_planes
     net = NeRFNetwork(bound=1.5, cuda_ray=True, density_thresh=10, min_near=0.2, triplane_channels=C, triplane_resolution=R,
                       triplane_wavelet_levels=R // 64).cuda()
     scene.install_ball_occupancy(net, 0.75)
@@ -122,13 +122,6 @@ def bench_sampling(C=32, R=2048, n_rays=60000):
     res["ms_point_fwd"] = timed(lambda: call("tnl_sample_planes_forward", ptr(planes), ptr(xyzs), M, R, C, inv, 1, ptr(nv), ptr(perm), ptr(feat), 1, stream()))
     res["ms_zero_fill"] = timed(lambda: plan.zero_gradient_tiles(gpl))
     res["ms_point_bwd"] = timed(lambda: call("tnl_sample_planes_backward", ptr(gfeat), 1, ptr(xyzs), M, R, C, inv, 1, ptr(nv), ptr(perm), ptr(gpl), stream()))
-    tperm, bins = tap_sort(xyzs, 1.5, R, True, nv)
-    halo = torch.empty(_lib.load().tnl_tsample_backward_workspace(R, C), dtype=torch.uint8, device="cuda")
-    res["ms_tap_sort"] = timed(lambda: tap_sort(xyzs, 1.5, R, True, nv))
-    res["ms_tiled_fwd"] = timed(lambda: call("tnl_tsample_forward", ptr(planes), ptr(xyzs), M, R, C, inv, 1, ptr(nv), ptr(tperm), ptr(bins),
-                                             ptr(z["ids"]), ptr(z["count"]), z["cap"], ptr(feat), 1, stream()))
-    res["ms_tiled_bwd"] = timed(lambda: call("tnl_tsample_backward", ptr(gfeat), 1, ptr(xyzs), M, R, C, inv, 1, ptr(tperm), ptr(bins),
-                                             ptr(z["ids"]), ptr(z["count"]), z["cap"], ptr(z["map"]), ptr(gpl), ptr(halo), halo.numel(), stream()))
     print(json.dumps(res))
 
 

@@ -1,6 +1,6 @@
 """Runs a few base-light training steps (no CPU baseline, no timing) -- the target command for ncu captures:
    ncu --set full --clock-control none --import-source on -k regex:<kernel> -s <skip> -c 1 -o gpurun_out/<name> python profiles/prof_step.py
-   TNL_TILED=1 selects the tile-binned sampling kernels (k_tsample_fwd / k_tsample_bwd), TNL_CONFIG / TNL_STEPS the workload.
+   TNL_CONFIG / TNL_STEPS select the workload.
 """
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -15,7 +15,6 @@ net = NeRFNetwork(bound=1.5, cuda_ray=True, density_thresh=10, min_near=0.2, tri
                   hidden_dim_color=cfg["hidden"]).cuda()
 scene.init_model_(net, 0)
 scene.install_ball_occupancy(net, 0.75)
-net.encoder.tiled_sampling = os.environ.get("TNL_TILED", "0") == "1"     # opt-in tile-binned sampling kernels (csrc/tsample.cu)
 ts = trainer.TrainStep(net, trainer.default_opt(), None)
 sc = scene.make_scene()
 g = torch.Generator().manual_seed(0)

@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "trinerflet_b200", "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
-SOURCES = ["api.cu", "raymarch.cu", "sample.cu", "sort.cu", "tiles.cu", "optim.cu", "grid.cu", "rays.cu", "idwt.cu", "mlp.cu", "tsample.cu"]
+SOURCES = ["api.cu", "raymarch.cu", "sample.cu", "sort.cu", "tiles.cu", "optim.cu", "grid.cu", "rays.cu", "idwt.cu", "mlp.cu"]
 # TNL_KEMU_ASAN=1: AddressSanitizer build (run the tests with LD_PRELOAD=$(gcc -print-file-name=libasan.so)
 # ASAN_OPTIONS=detect_leaks=0): out-of-bounds reads / writes of the kernels on the callers' heap buffers become hard errors
 ASAN = os.environ.get("TNL_KEMU_ASAN") == "1"

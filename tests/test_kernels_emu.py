@@ -728,108 +728,7 @@ def test_mlp_backward_mma_kernels_match_fp16_oracle(C, M):
     assert rc == -2
 
 
-# ------------------------------------------------------------------------------------------------ tile-binned sampling (opt-in)
-def _tsample_bwd(g_feat, half, xyz, M, R, C, inv_bound, fp16, perm, bin_end, ids, cnt, cap, gp):
-    """tnl_tsample_backward with its halo workspace (dirty on purpose) and, for a tile list, the matching tile map"""
-    wsz = kemu.lib().tnl_tsample_backward_workspace(R, C)
-    assert wsz == 4 * 3 * (R // 32) ** 2 * 65 * C
-    work = np.full(wsz // 4, np.nan, np.float32)
-    tmap = None
-    if ids is not None:
-        tmap = np.zeros(3 * (R // 32) ** 2, np.uint8)
-        tmap[ids[:int(cnt[0])]] = 1
-    kemu.call("tnl_tsample_backward", g_feat, half, xyz, M, R, C, inv_bound, int(fp16), perm, bin_end, ids, cnt, cap, tmap, gp, work,
-              work.nbytes, None)
-
-
-def _tap_sort(xyz, R, fp16, nv=None):
-    M = len(xyz)
-    inv_bound = float(np.float32(1.0) / np.float32(BOUND))
-    G = R // 32
-    wsz = kemu.lib().tnl_tap_sort_workspace(M, R)
-    assert wsz >= 4 * (G ** 3 + 1 + M)
-    work = np.zeros(max(wsz, 16), np.uint8)
-    perm = np.full(M, -1, np.int32)
-    kemu.call("tnl_tap_sort", xyz, M, nv, inv_bound, int(fp16), R, perm, work, work.size, None)
-    bin_end = work[:4 * (G ** 3 + 1)].view(np.uint32)
-    return perm, bin_end, work, inv_bound
-
-
-@pytest.mark.parametrize("C,R,fp16,tiles", [(16, 64, False, "all"), (32, 96, True, "all"), (48, 64, True, "list"), (32, 128, False, "list")])
-def test_tile_binned_sampling_equals_point_ordered_sampling(C, R, fp16, tiles):
-    """csrc/tsample.cu (one CTA per plane tile, texels staged / accumulated in shared memory) against csrc/sample.cu:
-    forward bit-identical, backward equal up to the order of the float additions, also with a tile list and with n_valid"""
-    g = torch.Generator().manual_seed(C + R)
-    M = 2500
-    planes = torch.randn(3, C, R, R, generator=g)
-    xyz = ((torch.rand(M, 3, generator=g) * 2 - 1) * BOUND * 1.02).numpy().astype(np.float32)    # a few points outside the box
-    xyz[:7] = [[-1.5, -1.5, -1.5], [1.5, 1.5, 1.5], [0, 0, 0], [1.5, -1.5, 0.3], [-1.4999, 1.4999, 0], [1.5, 0, 0], [0.7031, 0.7032, -0.7031]]
-    nv = np.array([M - 77], np.int32)
-    perm, bin_end, work, inv_bound = _tap_sort(xyz, R, fp16, nv)
-    G = R // 32
-    assert np.array_equal(np.sort(perm), np.arange(M)) and np.array_equal(np.sort(perm[M - 77:]), np.arange(M - 77, M))
-    assert bin_end[-1] == M and bin_end[-2] == M - 77 and (np.diff(bin_end.astype(np.int64)) >= 0).all()
-    # every point sits in the bin of its tap tile (the sampler's own coordinate arithmetic, fp16 rounding included)
-    u = of.project_coords(torch.from_numpy(xyz), BOUND, fp16=fp16).numpy()
-    ix = np.clip((u + np.float32(1.0)) * np.float32(0.5) * np.float32(R - 1), 0, R - 1).astype(np.float32)
-    t = (np.floor(ix).astype(np.int64) // 32)
-    key = (t[:, 2] * G + t[:, 1]) * G + t[:, 0]
-    starts = np.concatenate([[0], bin_end[:-1].astype(np.int64)])
-    for k in np.unique(key[:M - 77]):
-        rows = perm[starts[k]:bin_end[k]]
-        assert (key[rows] == k).all() and len(rows) == int((key[:M - 77] == k).sum())
-    pl = _cl(planes)
-    ref = np.full((M, 3 * C), np.nan, np.float32)
-    kemu.call("tnl_sample_planes_forward", pl, xyz, M, R, C, inv_bound, int(fp16), nv, None, ref, 0, None)
-    ids = cnt = None
-    cap = 0
-    if tiles == "list":         # all tiles, shuffled, in an over-sized list with a device-side count
-        ids = np.concatenate([np.random.default_rng(0).permutation(3 * G * G), np.full(5, 10 ** 6)]).astype(np.int32)
-        cnt = np.array([3 * G * G], np.int32)
-        cap = len(ids)
-    for half in (0, 1):
-        feat = np.full((M, 3 * C), np.nan, np.float16 if half else np.float32)
-        kemu.call("tnl_tsample_forward", pl, xyz, M, R, C, inv_bound, int(fp16), nv, perm, bin_end, ids, cnt, cap, feat, half, None)
-        want = ref.astype(np.float16) if half else ref
-        assert np.array_equal(feat.view(np.uint16 if half else np.uint32), want.view(np.uint16 if half else np.uint32))
-    # backward
-    G_feat = torch.randn(M, 3 * C, generator=g).numpy()
-    gp_ref = np.zeros((3, R, R, C), np.float32)
-    kemu.call("tnl_sample_planes_backward", G_feat, 0, xyz, M, R, C, inv_bound, int(fp16), nv, None, gp_ref, None)
-    gp = np.full((3, R, R, C), np.nan, np.float32)          # no zero fill: every listed tile is written
-    _tsample_bwd(G_feat, 0, xyz, M, R, C, inv_bound, fp16, perm, bin_end, ids, cnt, cap, gp)
-    assert np.isfinite(gp).all() and np.abs(gp - gp_ref).max() <= 2e-5 * np.abs(gp_ref).max()
-    Gh = G_feat.astype(np.float16)
-    gp_ref_h = np.zeros((3, R, R, C), np.float32)
-    kemu.call("tnl_sample_planes_backward", Gh, 1, xyz, M, R, C, inv_bound, int(fp16), nv, None, gp_ref_h, None)
-    gp_h = np.full((3, R, R, C), np.nan, np.float32)
-    _tsample_bwd(Gh, 1, xyz, M, R, C, inv_bound, fp16, perm, bin_end, ids, cnt, cap, gp_h)
-    assert np.abs(gp_h - gp_ref_h).max() <= 2e-5 * np.abs(gp_ref_h).max()
-    if tiles == "list":         # a partial list (two of the three planes: a listed tile's neighbours with points must be
-        part = np.arange(0, 2 * G * G, dtype=np.int32)   # listed too): listed tiles as before, the others untouched
-        gp_p = np.full((3, R, R, C), 123.0, np.float32)
-        _tsample_bwd(G_feat, 0, xyz, M, R, C, inv_bound, fp16, perm, bin_end, part, np.array([len(part)], np.int32), len(part), gp_p)
-        tile_of = (np.arange(3)[:, None, None] * G + (np.arange(R) // 32)[None, :, None]) * G + (np.arange(R) // 32)[None, None, :]
-        listed = np.isin(tile_of, part)[..., None]
-        assert np.abs(np.where(listed, gp_p, 0) - np.where(listed, gp, 0)).max() <= 2e-5 * np.abs(gp).max()   # (order of the shared atomics)
-        assert (gp_p[~np.broadcast_to(listed, gp_p.shape)] == 123.0).all()
-
-
-def test_tile_binned_sampling_empty_and_argument_errors():
-    lib = kemu.lib()
-    assert lib.tnl_tap_sort_workspace(100, 48) == 0 and lib.tnl_tap_sort_workspace(100, 64) > 0
-    R, C = 64, 16
-    perm, bin_end, work, inv_bound = _tap_sort(np.zeros((0, 3), np.float32), R, False)
-    assert (bin_end == 0).all()
-    gp = np.full((3, R, R, C), np.nan, np.float32)
-    _tsample_bwd(None, 0, None, 0, R, C, inv_bound, False, None, bin_end, None, None, 0, gp)
-    assert (gp == 0).all()                                  # no points: every tile is written as zeros
-    z16 = ctypes.c_void_p(64)
-    assert lib.tnl_tsample_forward(z16, z16, 5, 48, 16, 1.0, 0, None, z16, z16, None, None, 0, z16, 0, None) == -1   # R % 32
-    assert lib.tnl_tsample_forward(z16, z16, 5, 64, 24, 1.0, 0, None, z16, z16, None, None, 0, z16, 0, None) == -1   # C
-    assert lib.tnl_tsample_forward(z16, z16, 5, 64, 16, 1.0, 0, None, z16, z16, z16, None, 4, z16, 0, None) == -1    # list without count
-
-
+# ------------------------------------------------------------------------------------------------ marcher: other geometries
 @pytest.mark.parametrize("bound,Hg,dt_gamma,max_steps", [(1.0, 128, 0.0, 256), (4.0, 128, 1.0 / 256, 512), (3.0, 32, 1.0 / 128, 128)])
 def test_march_train_other_bounds_cascades_and_grid_sizes(bound, Hg, dt_gamma, max_steps):
     """the reference commands all use bound 1.5 (cascade 2, 128^3); the marcher's level selection / cone stepping for one, three

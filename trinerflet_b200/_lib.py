@@ -49,11 +49,6 @@ SIGNATURES = {
     "tnl_idwt_level_backward": (_int, [_vp, _vp, _vp, _u32, _u32, _vp, _vp, _f32, _u32, _u32, _vp]),
     "tnl_sample_planes_forward": (_int, [_vp, _vp, _u32, _u32, _u32, _f32, _int, _vp, _vp, _vp, _int, _vp]),
     "tnl_sample_planes_backward": (_int, [_vp, _int, _vp, _u32, _u32, _u32, _f32, _int, _vp, _vp, _vp, _vp]),
-    "tnl_tap_sort_workspace": (_sz, [_u32, _u32]),
-    "tnl_tap_sort": (_int, [_vp, _u32, _vp, _f32, _int, _u32, _vp, _vp, _sz, _vp]),
-    "tnl_tsample_forward": (_int, [_vp, _vp, _u32, _u32, _u32, _f32, _int, _vp, _vp, _vp, _vp, _vp, _u32, _vp, _int, _vp]),
-    "tnl_tsample_backward_workspace": (_sz, [_u32, _u32]),
-    "tnl_tsample_backward": (_int, [_vp, _int, _vp, _u32, _u32, _u32, _f32, _int, _vp, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _sz, _vp]),
     "tnl_cell_sort_workspace": (_sz, [_u32, _u32]),
     "tnl_cell_sort": (_int, [_vp, _u32, _vp, _f32, _u32, _vp, _vp, _sz, _vp]),
     "tnl_mlp_packed_bytes": (_sz, [_DP]),
@@ -124,8 +119,8 @@ def check(rc, what):
 
 
 # number of kernels each ABI call launches (for the launch counter the benchmark reports)
-KERNELS_PER_CALL = {"tnl_march_rays_train": 5, "tnl_compact_alive": 3, "tnl_compact_alive_dev": 3, "tnl_cell_sort": 5, "tnl_tap_sort": 5,
-                    "tnl_mlp_pack_weights": 2, "tnl_tsample_forward": 2, "tnl_tsample_backward": 2}   # (tsample forward: + the padding-row zero fill)
+KERNELS_PER_CALL = {"tnl_march_rays_train": 5, "tnl_compact_alive": 3, "tnl_compact_alive_dev": 3, "tnl_cell_sort": 5,
+                    "tnl_mlp_pack_weights": 2}
 # work-list IDWT calls launch one kernel per requested part (position of the `parts` argument from the end)
 _PARTS_ARG = {"tnl_idwt_level_forward_sparse": -2, "tnl_idwt_level_backward_sparse": -3}
 launch_count = 0

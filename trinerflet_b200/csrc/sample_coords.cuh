@@ -1,4 +1,4 @@
-// Coordinate / tap arithmetic shared by the plane-sampling kernels (sample.cu, tsample.cu) and the tap-tile sort: everything
+// Coordinate / tap arithmetic used by the plane-sampling kernels (sample.cu): everything
 // that decides WHICH texels a point touches lives here, so that the binning and the samplers cannot disagree.
 // Arithmetic follows ATen's grid_sampler_2d (unnormalise ((g+1)/2)*(R-1), clip to [0,R-1], weights nw/ne/sw/se as products
 // of differences); see sample.cu for the behavioural contract.
@@ -56,14 +56,6 @@ __device__ __forceinline__ uint2 pack4h(float4 v) {
 __device__ __forceinline__ float4 unpack4h(uint2 u) {
     const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
     return make_float4(a.x, a.y, b.x, b.y);
-}
-
-// shared-memory accumulation of one weighted 4-channel contribution (tsample.cu)
-__device__ __forceinline__ void smem_add4(float* addr, float4 v, float w) {
-    atomicAdd(addr + 0, v.x * w);
-    atomicAdd(addr + 1, v.y * w);
-    atomicAdd(addr + 2, v.z * w);
-    atomicAdd(addr + 3, v.w * w);
 }
 
 }  // namespace tnl

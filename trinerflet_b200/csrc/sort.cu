@@ -131,21 +131,6 @@ __global__ void k_cell_scatter(const uint32_t* __restrict__ keys, uint32_t M, ui
     perm[slot] = (int32_t)m;
 }
 
-// passes 2 + 3 for a histogram / key array some other translation unit produced (tsample.cu: tap-tile keys); afterwards
-// hist[k] = END offset of bin k in perm (the scatter's cursors), so bin k is perm[hist[k-1] .. hist[k])
-void counting_sort_finish(uint32_t* hist, const uint32_t* keys, uint32_t* sums, uint32_t nbins, uint32_t M, int32_t* perm,
-                          cudaStream_t s) {
-    const uint32_t nblocks = ceil_div(nbins, (uint32_t)kBinsPerBlock);
-    k_cell_block_sums<<<nblocks, 1024, 0, s>>>(hist, nbins, sums);
-    k_cell_scan_sums<<<1, 1024, 0, s>>>(sums, nblocks);
-    k_cell_scan_apply<<<nblocks, 1024, 0, s>>>(hist, nbins, sums);
-    k_cell_scatter<<<ceil_div(M, 256u), 256, 0, s>>>(keys, M, hist, perm);
-}
-
-size_t counting_sort_workspace(size_t nbins, uint32_t M) {
-    return sizeof(uint32_t) * (nbins + M + (nbins + kBinsPerBlock - 1) / kBinsPerBlock + 1);
-}
-
 }  // namespace tnl
 
 using namespace tnl;

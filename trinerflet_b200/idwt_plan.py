@@ -147,10 +147,6 @@ class IdwtPlan:
             self.version += 1
         self.zero["ids"][:ids.numel()].copy_(ids)
         self.zero["count"].fill_(int(ids.numel()))
-        # the same set as a dense 0/1 map (the tile-binned scatter asks "was my neighbour processed?"); fixed size, updated in place
-        if "map" not in self.zero:
-            self.zero["map"] = torch.zeros(z.numel(), dtype=torch.uint8, device=self.device)
-        self.zero["map"].copy_(z.reshape(-1).to(torch.uint8))
         self.stats = dict(active_fraction_forward=frac_f, active_fraction_backward=frac_b, tile_fraction=float(f.float().mean()),
                           zero_fill_fraction=float(z.float().mean()))
         return self

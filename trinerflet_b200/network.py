@@ -176,21 +176,14 @@ class NeRFNetwork(NeRFRenderer):
 
     def forward(self, x, d, n_valid=None):
         """x [M,3] in [-bound, bound], d [M,3] unit dirs -> sigma [M] fp32, color [M,3]."""
-        perm = bins = None
-        enc = self.encoder
-        if getattr(enc, "tiled_sampling", False) and torch.is_grad_enabled() and x.shape[0] > 0:
-            # opt-in: points binned by the tile of their taps, sampled tile by tile through shared memory (csrc/tsample.cu)
-            from .triplane_encoder import tap_sort, tiled_sampling_supported
-            if tiled_sampling_supported(enc.number_of_features, enc.plane_resolution):
-                fp16_coords = torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.float16
-                perm, bins = tap_sort(x, self.bound, enc.plane_resolution, fp16_coords, n_valid)
-        if perm is None and x.is_cuda and x.shape[0] >= self.spatial_sort_min_points and torch.is_grad_enabled():
+        perm = None
+        if x.is_cuda and x.shape[0] >= self.spatial_sort_min_points and torch.is_grad_enabled():
             from .triplane_encoder import cell_sort
             perm = cell_sort(x, self.bound, n_valid, 64)
         need_grad = torch.is_grad_enabled() and any(w.requires_grad for w in self._weights())
         fused = self._fused(need_grad)
         # fused path: the feature stream between the gather and the MLP kernels is fp16 (the first Linear's own rounding)
-        feat = self.encoder(x, bound=self.bound, n_valid=n_valid, perm=perm, half_out=fused, bins=bins)
+        feat = self.encoder(x, bound=self.bound, n_valid=n_valid, perm=perm, half_out=fused)
         if fused:
             return _FieldMLP.apply(feat, d, n_valid, *self._weights())
         # reference op sequence (network.py:125-147); precision follows the ambient autocast state

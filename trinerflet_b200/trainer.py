@@ -66,16 +66,12 @@ class TrainStep:
     # ---- the three segments of a step ---------------------------------------------------------------------------------
     def _render_loss(self, rays_o, rays_d, images):
         model, opt = self.model, self.opt
-        try:
-            with torch.autocast("cuda", dtype=torch.float16, enabled=opt.fp16):
-                bg = torch.zeros_like(images) + opt.background_color
-                out = model.render(rays_o.unsqueeze(0), rays_d.unsqueeze(0), staged=False, bg_color=bg, perturb=True,
-                                   force_all_rays=False, dt_gamma=opt.dt_gamma, max_steps=opt.max_steps)
-                pred = out['image'].view(-1, 3)
-                return self.criterion(pred, images).mean(-1).mean()
-        finally:
-            # the tile list of the tile-binned sampler is valid for this step's render only (its backward keeps its own copy)
-            model.encoder.sampling_tiles = None
+        with torch.autocast("cuda", dtype=torch.float16, enabled=opt.fp16):
+            bg = torch.zeros_like(images) + opt.background_color
+            out = model.render(rays_o.unsqueeze(0), rays_d.unsqueeze(0), staged=False, bg_color=bg, perturb=True,
+                               force_all_rays=False, dt_gamma=opt.dt_gamma, max_steps=opt.max_steps)
+            pred = out['image'].view(-1, 3)
+            return self.criterion(pred, images).mean(-1).mean()
 
     def forward_backward(self, rays_o, rays_d, images, update_grid=None):
         """rays_o/rays_d/images: [N,3] device tensors (this rank's shard). Returns the detached loss tensor."""
@@ -91,10 +87,6 @@ class TrainStep:
             if self._plan is None:
                 self.refresh_plan()
             enc.idwt_plan = self._plan
-        # tile-binned sampling (opt-in, enc.tiled_sampling): a work-list step only needs the tiles the IDWT backward reads
-        # (the plan's zero list); the debug mode of the exchange sums the whole gradient buffer, so it gets every tile
-        z = self._plan.zero if (use_plan and self._plan is not None) else None
-        enc.sampling_tiles = (z["ids"], z["count"], z["cap"], z["map"]) if (z is not None and not (self.reducer is not None and self.reducer.check)) else None
         prefetch = self.prefetch_planes and not do_update and rays_o.is_cuda
         # work-list steps drive the IDWT backward themselves (two parts, see SplitIdwtBackward); its gradient-independent
         # part goes to the prefetch stream right away and overlaps the render

@@ -274,11 +274,9 @@ class _SamplePlanes(Function):
         M, R, C, inv, fp16_coords, has_nv, has_perm, half = ctx.meta
         g_feat = g_feat.contiguous().half() if half else g_feat.contiguous().float()
         if ctx.grad_buf is not None:     # zero-filled ahead of time on the prefetch stream (TriPlaneVolume.prefetch_planes)
-            g_planes, ready, zeroed = ctx.grad_buf
+            g_planes, ready = ctx.grad_buf
             ctx.grad_buf = None
             torch.cuda.current_stream().wait_event(ready)
-            if not zeroed:               # a buffer prepared for the tile-binned scatter ended up here: this kernel accumulates
-                g_planes.zero_()
         else:
             g_planes = cl_empty_planes(C, R, device=g_feat.device, zero=True)
         call("tnl_sample_planes_backward", ptr(g_feat), int(half), ptr(coords), M, R, C, inv, fp16_coords,
@@ -295,74 +293,6 @@ def cell_sort(coords, bound, n_valid=None, G=64):
     ws = torch.empty(max(int(_lib.load().tnl_cell_sort_workspace(M, G)), 16), dtype=torch.uint8, device=coords.device)
     call("tnl_cell_sort", ptr(coords), M, ptr(n_valid), _inv_bound(bound), G, ptr(perm), ptr(ws), ws.numel(), stream())
     return perm
-
-
-TILE = 32   # texels per side of a sampling tile (csrc/tsample.cu; the dirty-tile size of tiles.cu / idwt_plan.py)
-
-
-def tiled_sampling_supported(C, R):
-    return R >= TILE and R % TILE == 0 and R <= 8192 and C in (16, 32, 48)
-
-
-def tap_sort(coords, bound, R, fp16_coords, n_valid=None):
-    """Counting sort of the points by the tile of their north-west tap on every axis (tnl_tap_sort) ->
-    (perm [M] int32, bins): `bins` is the sort's workspace, whose head holds the end offset of every bin in perm."""
-    from . import _lib
-    coords = coords.detach().contiguous().float()
-    M = coords.shape[0]
-    perm = torch.empty(M, dtype=torch.int32, device=coords.device)
-    bins = torch.empty(max(int(_lib.load().tnl_tap_sort_workspace(M, R)), 16), dtype=torch.uint8, device=coords.device)
-    call("tnl_tap_sort", ptr(coords), M, ptr(n_valid), _inv_bound(bound), int(bool(fp16_coords)), R, ptr(perm), ptr(bins), bins.numel(),
-         stream())
-    return perm, bins
-
-
-class _SamplePlanesTiled(Function):
-    """Opt-in tile-binned form of _SamplePlanes (csrc/tsample.cu): same features (bit-identical), gradient written tile by tile
-    with plain stores.  `tiles` = (ids, count, capacity, map) restricts both directions to the listed plane tiles (the work-list
-    training step passes idwt_plan's zero list: every tile the IDWT backward reads); None = every tile."""
-
-    @staticmethod
-    def forward(ctx, planes, coords, bound, fp16_coords, n_valid, perm, bins, half_out=False, grad_buf=None, tiles=None):
-        _require_cuda_f32(planes, "planes")
-        ctx.grad_buf = grad_buf
-        planes_cl = to_cl_planes(planes.detach())
-        coords = coords.detach().contiguous().float()
-        M = coords.shape[0]
-        C, R = planes.shape[1], planes.shape[2]
-        feat = torch.empty(M, 3 * C, device=planes.device, dtype=torch.float16 if half_out else torch.float32)
-        inv = _inv_bound(bound)
-        ids, cnt, cap, tmap = tiles if tiles is not None else (None, None, 0, None)
-        call("tnl_tsample_forward", ptr(planes_cl), ptr(coords), M, R, C, inv, int(bool(fp16_coords)), ptr(n_valid), ptr(perm),
-             ptr(bins), ptr(ids), ptr(cnt), int(cap), ptr(feat), int(bool(half_out)), stream())
-        ctx.save_for_backward(coords, perm, bins, ids if ids is not None else torch.empty(0), cnt if cnt is not None else torch.empty(0),
-                              tmap if tmap is not None else torch.empty(0))
-        ctx.meta = (M, R, C, inv, int(bool(fp16_coords)), bool(half_out), tiles is not None, int(cap))
-        return feat
-
-    @staticmethod
-    def backward(ctx, g_feat):
-        coords, perm, bins, ids, cnt, tmap = ctx.saved_tensors
-        M, R, C, inv, fp16_coords, half, has_tiles, cap = ctx.meta
-        g_feat = g_feat.contiguous().half() if half else g_feat.contiguous().float()
-        if ctx.grad_buf is not None:
-            g_planes, ready, _ = ctx.grad_buf
-            ctx.grad_buf = None
-            torch.cuda.current_stream().wait_event(ready)
-        else:   # no zero fill: every listed tile is written; with a tile list the rest of the buffer is never read
-            g_planes = cl_empty_planes(C, R, device=g_feat.device)
-        from . import _lib
-        halo = torch.empty(max(int(_lib.load().tnl_tsample_backward_workspace(R, C)), 16), dtype=torch.uint8, device=g_feat.device)
-        call("tnl_tsample_backward", ptr(g_feat), int(half), ptr(coords), M, R, C, inv, fp16_coords, ptr(perm), ptr(bins),
-             ptr(ids) if has_tiles else None, ptr(cnt) if has_tiles else None, cap, ptr(tmap) if has_tiles else None, ptr(g_planes),
-             ptr(halo), halo.numel(), stream())
-        return g_planes, None, None, None, None, None, None, None, None, None
-
-
-def sample_planes_tiled(planes, coords, bound, perm, bins, fp16_coords=None, n_valid=None, half_out=False, grad_buf=None, tiles=None):
-    if fp16_coords is None:
-        fp16_coords = torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.float16
-    return _SamplePlanesTiled.apply(planes, coords, float(bound), bool(fp16_coords), n_valid, perm, bins, bool(half_out), grad_buf, tiles)
 
 
 def sample_planes(planes, coords, bound, fp16_coords=None, n_valid=None, perm=None, half_out=False, grad_buf=None):
@@ -435,10 +365,6 @@ class TriPlaneVolume(nn.Module):
         # training hot path only: an idwt_plan.IdwtPlan restricts the next reconstructions to the occupied tiles
         # (see idwt_plan.py); None = dense planes, the reference's semantics
         self.idwt_plan = None
-        # opt-in: tile-binned sampling kernels (csrc/tsample.cu) when the caller supplies tap-sorted points (tap_sort);
-        # sampling_tiles = (ids, count, capacity, map) restricts them to the plane tiles a work-list step touches
-        self.tiled_sampling = False
-        self.sampling_tiles = None
         self._init_plane_features(planes_features)
 
     # -- parameters (triplane_encoder.py:155-231) --------------------------------------------------
@@ -511,12 +437,7 @@ class TriPlaneVolume(nn.Module):
                 ready.record(side)
             gbuf = None
             if torch.is_grad_enabled() and planes.requires_grad:
-                zeroed = True
-                if self.tiled_sampling and tiled_sampling_supported(self.number_of_features, self.plane_resolution):
-                    # the tile-binned scatter writes every tile it is given with plain stores: nothing to clear
-                    gbuf = cl_empty_planes(self.number_of_features, self.plane_resolution, device=planes.device)
-                    zeroed = False
-                elif plan is not None and partial_zero:
+                if plan is not None and partial_zero:
                     # the work-list backward only reads the tiles around the occupied ones: zero those, leave the rest undefined
                     gbuf = cl_empty_planes(self.number_of_features, self.plane_resolution, device=planes.device)
                     plan.zero_gradient_tiles(gbuf.permute(0, 2, 3, 1))
@@ -524,7 +445,7 @@ class TriPlaneVolume(nn.Module):
                     gbuf = cl_empty_planes(self.number_of_features, self.plane_resolution, device=planes.device, zero=True)
                 gready = torch.cuda.Event()
                 gready.record(side)
-                gbuf = (gbuf, gready, zeroed)
+                gbuf = (gbuf, gready)
         self._prefetch = (ready, gbuf)
         return planes
 
@@ -580,17 +501,13 @@ class TriPlaneVolume(nn.Module):
         feat = sample_planes(plane_features, coordinates, lbound, n_valid=n_valid)
         return feat.view(feat.shape[0], 3, self.number_of_features)
 
-    def forward(self, coordinates, bound, n_valid=None, perm=None, half_out=False, bins=None):
+    def forward(self, coordinates, bound, n_valid=None, perm=None, half_out=False):
         """coordinates [M,3] in [-bound, bound] -> features [M, 3C] (index p*C + c); fp32 as the reference's
-        grid_sample, or fp16 (half_out) for the fused MLP path, which rounds its input to fp16 anyway.
-        bins (with perm, both from tap_sort): use the tile-binned kernels (opt-in, self.tiled_sampling)."""
+        grid_sample, or fp16 (half_out) for the fused MLP path, which rounds its input to fp16 anyway."""
         planes = self.get_planes()
         gbuf = self._join_prefetch()
         if gbuf is not None and not torch.is_grad_enabled():
             gbuf = None
-        if bins is not None:
-            return sample_planes_tiled(planes, coordinates, bound, perm, bins, n_valid=n_valid, half_out=half_out, grad_buf=gbuf,
-                                       tiles=self.sampling_tiles)
         return sample_planes(planes, coordinates, bound, n_valid=n_valid, perm=perm, half_out=half_out, grad_buf=gbuf)
 
     # -- checkpoints: accept reference (NCHW-contiguous) tensors, keep channels-last storage -------------
