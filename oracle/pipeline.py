@@ -60,12 +60,14 @@ def wavelet_regulariser(coefs, lam):
     return lam * sum(v.abs().mean() * (v.numel() / total) for v in coefs) / len(coefs)
 
 
-def train_step(pf, coefs, weights, rays_o, rays_d, target, bitfield, noises, lam=0.2, **kw):
-    """One fwd+bwd of the reference's step on the CPU; all of pf / coefs / weights must require grad. Returns loss, M."""
+def train_step(pf, coefs, weights, rays_o, rays_d, target, bitfield, noises, lam=0.2, loss_scale=1.0, **kw):
+    """One fwd+bwd of the reference's step on the CPU; all of pf / coefs / weights must require grad. Returns loss, M.
+    loss_scale: GradScaler's factor (scaler.scale(loss).backward(), nerf/utils.py:1166) -- the .grad fields then hold the
+    SCALED gradients, fp16 rounding points of the emulated autocast backward included, exactly as before scaler.step()."""
     planes = ow.build_planes(pf, coefs)
     image, ws, depth, M = render_train(planes, weights, rays_o, rays_d, bitfield, noises, **kw)
     loss = ((image - target) ** 2).mean(-1).mean() + wavelet_regulariser(coefs, lam)
-    loss.backward()
+    (loss * loss_scale).backward()
     return float(loss), M
 
 

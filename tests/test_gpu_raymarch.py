@@ -165,42 +165,70 @@ def test_composite_train_fwd_bwd():
         assert ((gs_r - sig.grad).abs().max() / gs_r.abs().max()).item() <= 1e-5
 
 
+def _hash_field(x):
+    """sigma [n], rgb [n,3] as a pure integer function of the BITS of the sample positions (numpy): the same sample gets the
+    same values in both loops, whatever slot it occupies"""
+    u = np.ascontiguousarray(x).view(np.uint32).astype(np.uint64)
+    h = (u[:, 0] * np.uint64(73856093)) ^ (u[:, 1] * np.uint64(19349663)) ^ (u[:, 2] * np.uint64(83492791))
+    h = (h ^ (h >> np.uint64(13))) * np.uint64(0x9E3779B1)
+    sig = ((h >> np.uint64(8)) & np.uint64(0xFFFF)).astype(np.float32) / np.float32(65535) * np.float32(30)
+    rgb = np.stack([((h >> np.uint64(s)) & np.uint64(0xFF)).astype(np.float32) / np.float32(255) for s in (24, 32, 40)], -1)
+    return sig, np.ascontiguousarray(rgb)
+
+
 def test_inference_march_composite_loop():
-    """march_rays / composite_rays / device compaction driven as renderer.py:342-368 does, vs the C oracle."""
+    """march_rays / composite_rays / device compaction driven as renderer.py:342-368 does, vs the C oracle.  The two loops run
+    with SEPARATE state from start to end (no re-synchronisation): sample positions / deltas are compared bit for bit while
+    the alive lists agree; a ray whose transmittance sits within float noise of T_thresh may terminate one chunk apart
+    (__expf vs expf), which changes the other loop's chunk schedule but not any ray's own sample sequence."""
     from oracle import raymarch as orc
     from trinerflet_b200 import raymarching as rm
     _, o, d, bits, ro, rd, bf, aabb, nears, fars = _setup(3000)
     N = ro.shape[0]
+    # ---- device loop
     ws = torch.zeros(N, device="cuda"); dp = torch.zeros(N, device="cuda"); im = torch.zeros(N, 3, device="cuda")
     alive = torch.arange(N, dtype=torch.int32, device="cuda"); rt = nears.clone()
-    ws_o, dp_o, im_o = np.zeros(N, np.float32), np.zeros(N, np.float32), np.zeros((N, 3), np.float32)
-    alive_o, rt_o = np.arange(N, dtype=np.int32), nears.cpu().numpy().copy()
-    n_alive, step = N, 0
-    gen = torch.Generator(device="cuda").manual_seed(0)
+    n_alive, step, trace_g = N, 0, []
     while step < 1024 and n_alive > 0:
         n_step = max(min(N // n_alive, 8), 1)
         x, dd, dl = rm.march_rays(n_alive, n_step, alive, rt, ro, rd, BOUND, bf, CAS, H, nears, fars, 128, False, 0, 1024)
+        sig, rgb = _hash_field(x.cpu().numpy())
+        trace_g.append((alive.cpu().numpy().copy(), x.cpu().numpy(), dl.cpu().numpy()))
+        rm.composite_rays(n_alive, n_step, alive, rt, torch.from_numpy(sig).cuda(), torch.from_numpy(rgb).cuda(), dl, ws, dp, im, 1e-4)
+        alive, cnt = rm.compact_rays_alive(alive, n_alive)
+        n_alive = int(cnt.item())
+        alive = alive[:n_alive]
+        step += n_step
+    # ---- oracle loop, its own state
+    ws_o, dp_o, im_o = np.zeros(N, np.float32), np.zeros(N, np.float32), np.zeros((N, 3), np.float32)
+    alive_o, rt_o = np.arange(N, dtype=np.int32), nears.cpu().numpy().copy()
+    n_alive, step, it, lockstep, compared = N, 0, 0, True, 0
+    diverged = set()
+    while step < 1024 and n_alive > 0:
+        n_step = max(min(N // n_alive, 8), 1)
         x_o, d_o, l_o = orc.march_rays(n_alive, n_step, alive_o, rt_o, o, d, BOUND, bits.numpy(), CAS, H,
                                        nears.cpu().numpy(), fars.cpu().numpy(), np.zeros(n_alive, np.float32), 128, 0.0, 1024)
-        assert np.array_equal(x.cpu().numpy().view(np.uint32), x_o.view(np.uint32))
-        assert np.array_equal(dl.cpu().numpy().view(np.uint32), l_o.view(np.uint32))
-        sig = torch.rand(x.shape[0], device="cuda", generator=gen) * 30
-        rgb = torch.rand(x.shape[0], 3, device="cuda", generator=gen)
-        rm.composite_rays(n_alive, n_step, alive, rt, sig, rgb, dl, ws, dp, im, 1e-4)
-        orc.composite_rays(n_alive, n_step, alive_o, rt_o, sig.cpu().numpy(), rgb.cpu().numpy(), l_o, ws_o, dp_o, im_o, 1e-4)
-        alive, cnt = rm.compact_rays_alive(alive, n_alive)
-        n_new = int(cnt.item())
-        alive = alive[:n_new]
+        if lockstep and it < len(trace_g) and np.array_equal(trace_g[it][0], alive_o):
+            assert np.array_equal(trace_g[it][1].view(np.uint32), x_o.view(np.uint32))
+            assert np.array_equal(trace_g[it][2].view(np.uint32), l_o.view(np.uint32))
+            compared += 1
+        elif lockstep:
+            lockstep = False
+            diverged = set(trace_g[it][0].tolist()) ^ set(alive_o.tolist()) if it < len(trace_g) else set(alive_o.tolist())
+        sig, rgb = _hash_field(x_o)
+        orc.composite_rays(n_alive, n_step, alive_o, rt_o, sig, rgb, l_o, ws_o, dp_o, im_o, 1e-4)
         alive_o = alive_o[alive_o >= 0].copy()
-        if not np.array_equal(alive.cpu().numpy(), alive_o):
-            # a ray whose transmittance sits within float noise of T_thresh may terminate one chunk apart: tolerate <= 0.1 %
-            a, b = set(alive.cpu().numpy().tolist()), set(alive_o.tolist())
-            assert len(a ^ b) <= max(1, N // 1000)
-            alive_o = alive.cpu().numpy().copy(); rt_o = rt.cpu().numpy().copy()
-            ws_o, dp_o, im_o = ws.cpu().numpy().copy(), dp.cpu().numpy().copy(), im.cpu().numpy().copy()
-        n_alive = n_new
+        n_alive = alive_o.shape[0]
         step += n_step
-    assert np.abs(ws.cpu().numpy() - ws_o).max() <= 5e-5 and np.abs(im.cpu().numpy() - im_o).max() <= 5e-5
+        it += 1
+    assert compared >= 20                                   # the bit-exact part covered a substantial prefix of the loop
+    # per-ray results do not depend on the chunk schedule; rays that terminated a sample apart differ by < T_thresh-weighted terms
+    bad = np.zeros(N, bool)
+    for a, b in ((ws.cpu().numpy(), ws_o), (im.cpu().numpy(), im_o), (dp.cpu().numpy(), dp_o)):
+        diff = np.abs(a - b).reshape(N, -1).max(-1)
+        bad |= diff > 5e-5
+        assert diff.max() <= 1e-3                           # extra samples carry weight < T_thresh = 1e-4 (depth: x t <= 6)
+    assert int(bad.sum()) <= max(1, N // 1000)              # <= 0.1 % of the rays 
 
 
 def test_sh_encoder():
