@@ -71,6 +71,74 @@ def train_step(pf, coefs, weights, rays_o, rays_d, target, bitfield, noises, lam
     return float(loss), M
 
 
+def timed_step_sample(C, R, S, hidden, batch, bitfield, n_sample, seed=0, planes_sub=3):
+    """DIRECT timing of one reference training step (fwd+bwd) on the CPU with a bounded number of rays: the multilevel IDWT
+    forward and backward run in full (all `planes_sub` of the three planes at full resolution; planes_sub < 3 only on hosts
+    too small to finish, stated by the caller), the ray part (march -> grid_sample -> MLP -> composite -> MSE, forward and
+    backward down to the plane gradient) runs on the first n_sample rays of `batch`.  The autograd graph is cut at the planes
+    only to attribute the time (same kernels, same order as one backward call).
+    Returns dict(idwt_fwd_s, rays_s, idwt_bwd_s, step_s, M)."""
+    g = torch.Generator().manual_seed(seed)
+    L = int(round(np.log2(S)))
+    n0 = R // S
+    pf = (0.1 * torch.randn(planes_sub, C, n0, n0, generator=g)).requires_grad_(True)
+    coefs = [(0.05 * torch.randn(planes_sub, C, 3, n0 * 2 ** l, n0 * 2 ** l, generator=g)).requires_grad_(True) for l in range(L)]
+    weights = [w.requires_grad_(True) for w in of.init_mlp_weights(C, hidden, hidden, gen=g)]
+    rays_o, rays_d, target = (t[:n_sample] for t in batch)
+    noises = torch.rand(n_sample, generator=g).numpy()
+    t0 = time.perf_counter()
+    planes = ow.build_planes(pf, coefs)
+    t1 = time.perf_counter()
+    full = planes if planes_sub == 3 else torch.cat([planes] * 3, 0)[:3]        # (the sampler needs three planes)
+    leaf = full.detach().requires_grad_(True)
+    image, ws, depth, M = render_train(leaf, weights, rays_o, rays_d, bitfield, noises)
+    loss = ((image - target) ** 2).mean(-1).mean()
+    loss.backward()
+    t2 = time.perf_counter()
+    reg = wavelet_regulariser(coefs, 0.2)
+    torch.autograd.backward([planes, reg], [leaf.grad[:planes_sub], None])
+    t3 = time.perf_counter()
+    return dict(idwt_fwd_s=t1 - t0, rays_s=t2 - t1, idwt_bwd_s=t3 - t2, step_s=t3 - t0, M=M)
+
+
+def cpu_config_benchmark(points=65536, C=16, R=512, S=8, hidden=64, iters=5, warmup=2, seed=0):
+    """the reference's torch path on the CPU config -- TriPlaneVolume (C=16, R=512, S=8: three IDWT
+    levels from a 64^2 base; pytorch_wavelets restated, oracle/wavelet.py) + grid_sample + sigma/color MLPs (fp32, SH restated)
+    forward AND backward on `points` uniform random points in [-1.5, 1.5]^3 with random unit directions, random-init, seed 0;
+    `warmup` + `iters` iterations, median.  Returns points/s, the IDWT-only GB/s (2P / t_fwd) and the breakdown."""
+    g = torch.Generator().manual_seed(seed)
+    L = int(round(np.log2(S)))
+    n0 = R // S
+    pf = (0.1 * torch.randn(3, C, n0, n0, generator=g)).requires_grad_(True)
+    coefs = [(0.05 * torch.randn(3, C, 3, n0 * 2 ** l, n0 * 2 ** l, generator=g)).requires_grad_(True) for l in range(L)]
+    weights = [w.requires_grad_(True) for w in of.init_mlp_weights(C, hidden, hidden, gen=g)]
+    xyz = (torch.rand(points, 3, generator=g) * 2 - 1) * 1.5
+    d = torch.randn(points, 3, generator=g)
+    d = d / d.norm(dim=-1, keepdim=True)
+    gs = torch.randn(points, generator=g)
+    grgb = torch.randn(points, 3, generator=g)
+    rows = []
+    for it in range(warmup + iters):
+        for t in [pf] + coefs + weights:
+            t.grad = None
+        t0 = time.perf_counter()
+        planes = ow.build_planes(pf, coefs)
+        t1 = time.perf_counter()
+        feat = of.sample_planes(planes, xyz, 1.5)
+        t2 = time.perf_counter()
+        sigma, rgb, _ = of.mlp_forward(feat, d, weights)
+        t3 = time.perf_counter()
+        ((sigma * gs).sum() + (rgb * grgb).sum()).backward()
+        t4 = time.perf_counter()
+        if it >= warmup:
+            rows.append((t4 - t0, t1 - t0, t2 - t1, t3 - t2, t4 - t3))
+    med = [float(np.median([r[k] for r in rows])) for k in range(5)]
+    P = 3 * C * R * R * 4
+    return dict(points=points, points_per_s=points / med[0], fwd_bwd_seconds=med[0], idwt_fwd_seconds=med[1],
+                idwt_fwd_GBps=2 * P / med[1] / 1e9, sample_fwd_seconds=med[2], mlp_fwd_seconds=med[3], backward_seconds=med[4],
+                iters=iters, warmup=warmup, config=f"C={C} R={R} S={S} hidden={hidden} fp32")
+
+
 def timed_components(C, R, S, hidden, n_rays_full, scene_batch, bitfield, planes_sub, r_div, n_small, n_large, seed=0):
     """Bounded-sample timing of one reference training step (fwd+bwd) on the CPU, extrapolated to the full workload:
       (a) multilevel IDWT forward+backward on planes_sub of the 3 planes (batch entries are independent: exact x3/planes_sub)

@@ -230,3 +230,41 @@ def test_cuda_graph_replay_equals_eager_step():
     assert all(p.grad is None for p in net.parameters())
     ts.replay(*b[2])
     assert all(p.grad is not None for p in net.parameters())
+
+
+def test_fused_adam_resumes_from_torch_adam_checkpoint():
+    """optimizer.load_state_dict of a reference / torch.optim.Adam checkpoint hands FusedAdam moments with the SAVED
+    (NCHW-contiguous) strides, a per-parameter `step`, possibly on the CPU.  The resumed update must pair every parameter
+    element with its own moments and continue the bias correction from the saved step count."""
+    import copy
+    from trinerflet_b200 import scene, trainer
+    sc = scene.make_scene()
+    g = torch.Generator().manual_seed(5)
+    batches = [tuple(t.cuda() for t in scene.sample_batch(sc, 2048, g)) for _ in range(4)]
+    net_a = _model("tiny")
+    opt = trainer.default_opt(fp16=False)
+    ts_a = trainer.TrainStep(net_a, opt, torch.optim.Adam(net_a.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15))
+    for i in range(3):
+        torch.manual_seed(i)
+        ts_a.step(*batches[i], update_grid=False)
+    # the checkpoint: parameters + optimizer state as torch saves them for NCHW tensors, mapped to the CPU
+    sd = copy.deepcopy(ts_a.optimizer.state_dict())
+    for st in sd["state"].values():
+        for k in ("exp_avg", "exp_avg_sq"):
+            st[k] = st[k].contiguous().cpu()              # logical NCHW order, dense: NOT the channels-last storage order
+        st["step"] = st["step"].cpu()
+    net_b = _model("tiny")
+    net_b.load_state_dict(net_a.state_dict())
+    fused = trainer.make_optimizer(net_b, 1e-2, fused=True)
+    fused.load_state_dict(sd)
+    # one more step on identical gradients
+    net_a.zero_grad(set_to_none=True)
+    torch.manual_seed(9)
+    ts_a.forward_backward(*batches[3], update_grid=False)
+    for pa, pb in zip(net_a.parameters(), net_b.parameters()):
+        pb.grad = pa.grad.clone()
+    ts_a.optimizer.step()
+    fused.step()
+    assert float(fused.param_groups[0]["_tnl_state"][0]) == 4.0
+    for (n, pa), pb in zip(net_a.named_parameters(), net_b.parameters()):
+        assert rel_l2(pb, pa) <= 1e-6, (n, rel_l2(pb, pa))

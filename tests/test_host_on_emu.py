@@ -317,6 +317,64 @@ def test_ray_sharded_training_step_world2_equals_single_rank(worklist):
     assert out[0] and out[1]
 
 
+def _grid_refresh_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from _pytest.monkeypatch import MonkeyPatch
+    mpatch = MonkeyPatch()
+    try:
+        emu_backend.install(mpatch)
+        os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from trinerflet_b200 import parallel, scene, trainer
+        N = 301                                          # ragged shards: the ranks also draw different numbers of jitter values
+        sc = scene.make_scene()
+        ro, rd, tgt = scene.sample_batch(sc, N, torch.Generator().manual_seed(0))
+        lo, hi = parallel.shard_range(N, rank, world)
+        net = _model()
+        net.train()
+        ts = trainer.TrainStep(net, trainer.default_opt(fp16=False), None, world_size=world, transport=torch.float32)
+        ts.plan_on_any_device = True
+        torch.manual_seed(100 + rank)                    # every rank its own RNG stream, as bench.py seeds them
+        l0 = ts.forward_backward(ro[lo:hi], rd[lo:hi], tgt[lo:hi], update_grid=False)      # steady-state step (builds the lists)
+        gen0, tiles0 = net.bitfield_generation, ts.reducer.tile_ids.clone()
+        net.zero_grad(set_to_none=True)
+        l1 = ts.forward_backward(ro[lo:hi], rd[lo:hi], tgt[lo:hi], update_grid=True)       # dense step + update_extra_state
+        net.zero_grad(set_to_none=True)
+        l2 = ts.forward_backward(ro[lo:hi], rd[lo:hi], tgt[lo:hi], update_grid=False)      # work-list step on the NEW lists
+        sig = torch.stack([net.density_bitfield.long().sum(), (net.density_bitfield.long() * torch.arange(net.density_bitfield.numel()) % 9973).sum(),
+                           torch.tensor(ts.reducer.n_tiles), ts.reducer.tile_ids.long().sum()])
+        both = [torch.zeros_like(sig) for _ in range(world)]
+        dist.all_gather(both, sig)
+        ok = all(torch.equal(b, both[0]) for b in both)                                    # identical occupancy + tile lists
+        ok = ok and net.bitfield_generation > gen0 and ts._plan_gen == net.bitfield_generation == ts._reducer_gen
+        ok = ok and not torch.equal(tiles0, ts.reducer.tile_ids) if tiles0.shape == ts.reducer.tile_ids.shape else ok
+        ok = ok and all(bool(torch.isfinite(l)) for l in (l0, l1, l2))
+        ok = ok and all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in net.parameters())
+        # replicated parameters received identical (averaged) gradients
+        for p in net.parameters():
+            gs = [torch.zeros_like(p.grad.contiguous()) for _ in range(world)]
+            dist.all_gather(gs, p.grad.contiguous())
+            ok = ok and rel_l2(gs[1], gs[0]) <= 1e-6
+        out[rank] = bool(ok)
+        dist.destroy_process_group()
+    finally:
+        mpatch.undo()
+
+
+def test_grid_refresh_keeps_ranks_consistent_world2_gloo():
+    """update_extra_state runs on every rank from its own RNG stream; without synchronisation the density
+    bitfields, hence the dirty-tile lists and the all-reduce buffer sizes, diverge.  Two gloo ranks, different seeds, ragged
+    shards, update_grid=True: occupancy and tile lists stay identical, the next work-list step runs on the refreshed lists."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_grid_refresh_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] and out[1]
+
+
 def test_worklist_training_step_equals_dense_step(emu):
     """the optimised steady-state step (work-list IDWT forward, SplitIdwtBackward: clean part + active part, |yh| sums
     completed by the backward, gap lists) against the dense step on the same rays: same loss, same gradients"""
@@ -341,39 +399,23 @@ def test_worklist_training_step_equals_dense_step(emu):
         assert rel_l2(a, b) <= 1e-6
 
 
-def test_bench_next_rows_render_section_runs(emu, monkeypatch):
-    """bench.py's extras.next_rows (render part) executed on the host build with a small frame and fake CUDA events: the
-    keys the bench reports exist and both loops agree.  (The feeder part needs a captured CUDA graph: GPU only.)"""
+def test_bench_cpu_legs_and_kernel_attribution(capsys):
+    """bench.py's host-only pieces: the reference arm prints the contract's JSON line from a directly timed, bounded sample;
+    roofline attribution is per kernel (the work-list IDWT entry points split by their `parts` argument)."""
+    import json
     import types
     import bench
     from trinerflet_b200 import scene
-
-    class FakeEvent:
-        def __init__(self, enable_timing=False):
-            pass
-
-        def record(self):
-            pass
-
-        def elapsed_time(self, other):
-            return 2.0
-
-    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
-    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
-    full = scene.full_frame
-
-    def small_frame(sc, idx=0):
-        ro, rd = full(sc, idx)
-        pick = torch.arange(0, ro.shape[0], 1601)
-        return ro[pick].contiguous(), rd[pick].contiguous()
-
-    monkeypatch.setattr(scene, "full_frame", small_frame)
-    net = _model()
-    net.train()
-    out = bench.next_rows(types.SimpleNamespace(steps=2), net, None, scene.make_scene(), 64, torch.device("cpu"), use_graph=False)
-    assert out["render_800x800_ms_host_loop"] == 1.0 and out["render_800x800_ms_device_loop_chunk8"] == 1.0, out
-    assert out["render_max_abs_diff_between_loops"] == 0.0 and out["render_state_reads"] < out["render_iterations"]
-    assert net.training and net.infer_chunk == 0
+    assert bench.kernel_key("tnl_idwt_level_backward_sparse", (64, 32, 0.1, 128, 128, 1)) == "tnl_idwt_level_backward_sparse[active]"
+    assert bench.kernel_key("tnl_idwt_level_backward_sparse", (64, 32, 0.1, 128, 128, 2)) == "tnl_idwt_level_backward_sparse[clean]"
+    assert bench.kernel_key("tnl_mlp_backward", (1000,)) == "tnl_mlp_backward"
+    assert bench.mlp_params(32, 64) == 13440 and bench.mlp_params(48, 128) == 41216          # SURVEY.md 8 table
+    args = types.SimpleNamespace(steps=1, warmup=0, gpus=1, config="tiny", scaling="weak")
+    bench.run_reference(args, scene.CONFIGS["tiny"], 512)
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "rays/s" and line["value"] > 0 and line["higher_is_better"]
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "timed directly" in line["cpu_baseline"]["sample"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and abs(line["value"] - 512 / (line["ms_per_step"] * 1e-3)) <= 1e-6 * line["value"]
 
 
 def test_mark_untrained_grid_matches_brute_force(emu):

@@ -64,6 +64,15 @@ class FusedAdam(torch.optim.Optimizer):
                 if len(st) == 0:
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                else:
+                    # moments restored by load_state_dict (e.g. from a reference / torch.optim.Adam checkpoint) keep the SAVED
+                    # strides (NCHW-contiguous) and possibly another device: bring them into p's memory order, once
+                    for k in ("exp_avg", "exp_avg_sq"):
+                        if st[k].stride() != p.stride() or st[k].device != p.device or st[k].dtype != torch.float32:
+                            st[k] = torch.empty_like(p, dtype=torch.float32).copy_(st[k])
+                    if "step" in st:        # torch.optim.Adam's per-parameter step count: the group's counter starts from it
+                        loaded = float(st.pop("step"))
+                        group["_tnl_loaded_step"] = max(loaded, group.get("_tnl_loaded_step", 0.0))
                 work.append((gi, group, p, self._flat_like(p, p.grad), st["exp_avg"], st["exp_avg_sq"]))
         if not work:
             return None
@@ -80,8 +89,14 @@ class FusedAdam(torch.optim.Optimizer):
         for gi, group, p, g, m, v in work:
             if gi not in states:
                 key = "_tnl_state"
-                if key not in group or group[key].device != dev:
+                if key not in group:
                     group[key] = torch.zeros(4, dtype=torch.float32, device=dev)
+                elif group[key].device != dev:      # e.g. a checkpoint mapped to the CPU: move, do not restart the bias correction
+                    group[key] = group[key].to(dev)
+                if "_tnl_loaded_step" in group:
+                    loaded = group.pop("_tnl_loaded_step")
+                    if float(group[key][0]) < loaded:
+                        group[key][0] = loaded
                 b1, b2 = group["betas"]
                 call("tnl_adam_prepare", ptr(group[key]), ptr(found_inf), float(b1), float(b2), stream())
                 states[gi] = group[key]

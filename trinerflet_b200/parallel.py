@@ -84,6 +84,15 @@ class PlaneGradReducer:
              ptr(flags), stream())
         self.tile_ids = torch.nonzero(flags).squeeze(-1).int().contiguous()          # one sync, once per grid refresh
         self.n_tiles = int(self.tile_ids.shape[0])
+        if self.world_size > 1 and dist.is_initialized():
+            # the exchange sums buffers of n_tiles tiles position by position: every rank must hold the same list
+            sig = torch.tensor([self.n_tiles, int(self.tile_ids.long().sum())], dtype=torch.int64, device=flags.device)
+            lo, hi = sig.clone(), sig.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            if not torch.equal(lo, hi):
+                raise RuntimeError("PlaneGradReducer: the ranks derived different dirty-tile lists -- their density bitfields "
+                                   "diverged (call parallel.sync_occupancy(model) after update_extra_state)")
         per_plane = torch.bincount(self.tile_ids.long() // (nt * nt), minlength=3).tolist()   # ids ascend: plane-major
         self.plane_ranges = []
         start = 0
@@ -162,6 +171,21 @@ def allreduce_small(params, world_size):
         n = g.numel()
         g.copy_(flat[off:off + n].view_as(g))
         off += n
+
+
+def sync_occupancy(model, src=0):
+    """Make the occupancy state replica-consistent after update_extra_state: density_grid, density_bitfield, mean_density and
+    iter_density of rank `src` replace everyone's (17 MB broadcast every 16th step).  The per-rank grids differ because each
+    rank jitters its cell samples from its own RNG stream; mean_count / step_counter stay per rank (they describe the rank's
+    own ray shard)."""
+    if not dist.is_initialized() or dist.get_world_size() <= 1:
+        return
+    dist.broadcast(model.density_grid, src)
+    dist.broadcast(model.density_bitfield, src)
+    t = torch.tensor([float(model.mean_density), float(model.iter_density)], dtype=torch.float64, device=model.density_grid.device)
+    dist.broadcast(t, src)
+    model.mean_density, model.iter_density = float(t[0]), int(t[1])
+    model.mark_bitfield_changed()
 
 
 def gather_frame(local, n_total, rank, world_size):

@@ -43,6 +43,18 @@ class NeRFRenderer(nn.Module):
             self.register_buffer('step_counter', torch.zeros(16, 2, dtype=torch.int32))
             self.mean_count = 0
             self.local_step = 0
+        # bumped whenever density_bitfield changes (update_extra_state, reset_extra_state, load_state_dict, or a caller that
+        # writes the buffer itself and calls mark_bitfield_changed()): everything derived from the bitfield -- the IDWT work
+        # lists and the dirty-tile list of the multi-GPU exchange (trainer.TrainStep) -- is rebuilt when it lags behind
+        self.bitfield_generation = 0
+
+    def mark_bitfield_changed(self):
+        self.bitfield_generation += 1
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        if prefix + "density_bitfield" in state_dict:
+            self.mark_bitfield_changed()
 
     # subclasses provide the field --------------------------------------------------------------
     def forward(self, x, d, n_valid=None):
@@ -230,6 +242,7 @@ class NeRFRenderer(nn.Module):
         self.iter_density += 1
         thresh = min(self.mean_density, self.density_thresh)
         self.density_bitfield = raymarching.packbits(self.density_grid, thresh, self.density_bitfield)
+        self.mark_bitfield_changed()
         total_step = min(16, self.local_step)
         if total_step > 0:
             self.mean_count = int(self.step_counter[:total_step, 0].sum().item() / total_step)

@@ -139,4 +139,5 @@ def install_ball_occupancy(model, radius=0.75):
     model.density_bitfield.copy_(packbits_cpu(grid, 0.5).to(model.density_bitfield.device))
     model.mean_density = float(grid.clamp(min=0).mean())
     model.iter_density = 16
+    model.mark_bitfield_changed()
     return model

@@ -60,6 +60,7 @@ class TrainStep:
         # (idwt_plan.py); steps that refresh the density grid query the field everywhere and stay dense
         self.sparse_idwt = True
         self._plan = None
+        self._plan_gen = self._reducer_gen = None     # model.bitfield_generation the plan / the dirty-tile list were built from
         self.plan_on_any_device = False   # test hook: the CPU suite runs the work-list step over the host build of the kernels
         self._graphs = None
 
@@ -83,8 +84,14 @@ class TrainStep:
         enc.idwt_plan = None
         use_plan = (self.sparse_idwt and not do_update and (rays_o.is_cuda or self.plan_on_any_device) and model.cuda_ray
                     and self._plan_supported())
+        # anything derived from the density bitfield must follow it (update_extra_state here or in the caller's own loop,
+        # load_state_dict of a checkpoint, ...): rebuild when the model's bitfield generation moved on
+        gen = getattr(model, "bitfield_generation", 0)
+        if self.reducer is not None and self.reducer.tile_ids is not None and self._reducer_gen != gen:
+            self.reducer.refresh()
+            self._reducer_gen = gen
         if use_plan:
-            if self._plan is None:
+            if self._plan is None or self._plan_gen != gen:
                 self.refresh_plan()
             enc.idwt_plan = self._plan
         prefetch = self.prefetch_planes and not do_update and rays_o.is_cuda
@@ -113,8 +120,13 @@ class TrainStep:
         if do_update:
             with torch.autocast("cuda", dtype=torch.float16, enabled=opt.fp16):
                 model.update_extra_state()
+            if self.world_size > 1:
+                # every rank refreshed its grid from its own RNG stream (jittered cell samples): the replicas must agree on the
+                # occupancy, or the dirty-tile lists (and the all-reduce buffer sizes) derived from it diverge -> rank 0's wins
+                parallel.sync_occupancy(model)
             if self.reducer is not None:
                 self.reducer.refresh()
+                self._reducer_gen = model.bitfield_generation
             if self._plan is not None:
                 self.refresh_plan()
         capturing = torch.cuda.is_current_stream_capturing()
@@ -193,6 +205,7 @@ class TrainStep:
         """(Re)build the IDWT work lists from the current density bitfield; must follow every change of the bitfield."""
         from .idwt_plan import IdwtPlan
         self._plan = IdwtPlan.from_model(self.model, plan=self._plan)
+        self._plan_gen = getattr(self.model, "bitfield_generation", 0)
         return self._plan
 
     def _exchange(self):
@@ -287,6 +300,7 @@ class TrainStep:
         self._static = tuple(t.clone() for t in (rays_o, rays_d, images))
         if self.reducer is not None:
             self.reducer.refresh()
+            self._reducer_gen = getattr(self.model, "bitfield_generation", 0)
         if self.sparse_idwt and self._plan_supported():
             self.refresh_plan()
         side = torch.cuda.Stream()
@@ -320,6 +334,12 @@ class TrainStep:
         for dst, src in zip(self._static, (rays_o, rays_d, images)):
             dst.copy_(src, non_blocking=True)
         gA, gB = self._graphs
+        gen = getattr(self.model, "bitfield_generation", 0)
+        if self._plan is not None and self._plan_gen != gen:
+            self.refresh_plan()            # the lists are rewritten in place: the captured graphs stay valid unless they grew
+        if self.reducer is not None and self._reducer_gen != gen:
+            self.reducer.refresh()
+            self._reducer_gen = gen
         if self._plan is not None and self._plan.version != self._graph_plan_version:
             raise RuntimeError("the IDWT work lists were reallocated after capture(): capture the step again")
         gA.replay()
