@@ -211,24 +211,12 @@ int tnl_mlp_forward(const tnl_mlp_dims* dims, const void* packed, const void* fe
                     uint32_t M, const int32_t* n_valid, float* sigma, float* rgb, float* geo,
                     tnl_stream_t stream);
 /* Backward of tnl_mlp_forward: recomputes activations from feat; g_sigma [M], g_rgb [M][3] in;
- * g_feat [M][3C] out, same dtype as feat (may be NULL); g_W1..g_W5 fp32 accumulated with atomics (caller zero-fills). */
+ * g_feat [M][3C] out, same dtype as feat (may be NULL); g_W1..g_W5 fp32 accumulated with atomics (caller zero-fills).
+ * H = Hc = 128 (the "large" config) requires the fp16 feature stream (feat_fp16 != 0: tcgen05 kernels, csrc/mlp_tc128.cu). */
 int tnl_mlp_backward(const tnl_mlp_dims* dims, const void* packed, const void* feat, int feat_fp16, const float* dirs,
                      uint32_t M, const int32_t* n_valid, const float* g_sigma, const float* g_rgb,
                      void* g_feat, float* g_W1, float* g_W2, float* g_W3, float* g_W4, float* g_W5,
                      tnl_stream_t stream);
-
-/* Input-gradient half of the backward for heads whose weight gradients do not fit one CTA (the 128-wide "large" config;
- * also valid for 64): recomputes the activations, runs the input-gradient chain (g_feat as tnl_mlp_backward) and writes
- * the fp16 operands of the five weight-gradient products to `scratch` as nine row-major matrices, in this order:
- *   relu(h1) [M][H]  in2 = [SH16 | geo15 | 0] [M][32]  relu(h3) [M][Hc]  relu(h4) [M][Hc]
- *   dh1 [M][H]  dh2 [M][16]  dh3 [M][Hc]  dh4 [M][Hc]  d5 [M][16]          (rows >= *n_valid are zeros)
- * with the internal neuron order of the kernels: dh2 column j < 15 <-> sigma_net[1] row j+1, column 15 <-> row 0 (sigma);
- * d5 columns 0..2 = color_net[2] rows, the rest zero.  The caller forms dW_l = dOut_l^T In_l with library GEMMs
- * (dW1 = dh1^T feat, dW2 = dh2^T relu(h1), dW3 = dh3^T in2[:, :31], dW4 = dh4^T relu(h3), dW5 = d5[:, :3]^T relu(h4)). */
-size_t tnl_mlp_chain_scratch_bytes(const tnl_mlp_dims* dims, uint32_t M);
-int tnl_mlp_backward_chain(const tnl_mlp_dims* dims, const void* packed, const void* feat, int feat_fp16, const float* dirs,
-                           uint32_t M, const int32_t* n_valid, const float* g_sigma, const float* g_rgb, void* g_feat,
-                           void* scratch, tnl_stream_t stream);
 
 /* Diagnostic: ONE tcgen05.mma product D[M x N] = A B^T with fp16 operands given as plain row-major matrices
  * (A: [a_rows][a_cols] = [M][K] if a_mn == 0, [K][M] if a_mn != 0; B likewise with N), staged in the un-swizzled

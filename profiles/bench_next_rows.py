@@ -6,7 +6,6 @@
            (model.infer_chunk = 0: one read-back per iteration) and the device-driven loop (infer_chunk = 4 / 8 / 16).
 
   sampling kernel-level timing of the point-ordered gather / scatter at base-light size.
-  wide     the "large" config (C=48, hidden 128) through the library path and through the hybrid 128-wide backward.
 
   python profiles/bench_next_rows.py feeder|render|wide|sampling [--config base_light] [--max-steps 1024]
 
@@ -125,50 +124,14 @@ def bench_sampling(C=32, R=2048, n_rays=60000):
     print(json.dumps(res))
 
 
-def bench_wide(n_rays=60000):
-    """'large' config (C=48, hidden 128): one eager fwd+bwd step through the library path (default) and through the hybrid
-    backward (model.wide_fused_backward = True: fused forward, fused input-gradient chain + library GEMMs)."""
-    from trinerflet_b200 import trainer
-    from trinerflet_b200.network import NeRFNetwork
-    c = scene.CONFIGS["large"]
-    sc = scene.make_scene()
-    g = torch.Generator().manual_seed(0)
-    batches = [tuple(t.cuda() for t in scene.sample_batch(sc, n_rays, g)) for _ in range(4)]
-    for wide in (False, True):
-        net = NeRFNetwork(bound=1.5, cuda_ray=True, density_thresh=10, min_near=0.2, triplane_channels=c["C"],
-                          triplane_resolution=c["R"], triplane_wavelet_levels=c["S"], hidden_dim=c["hidden"],
-                          hidden_dim_color=c["hidden"]).cuda()
-        scene.init_model_(net, seed=0)
-        scene.install_ball_occupancy(net, 0.75)
-        net.wide_fused_backward = wide
-        ts = trainer.TrainStep(net, trainer.default_opt(), None)
-        ts.forward_backward(*batches[0], update_grid=False)
-        net.mean_count = int(net.step_counter[0, 0].item())
-        net.local_step = 0
-        i = [0]
-
-        def step():
-            net.zero_grad(set_to_none=True)
-            ts.forward_backward(*batches[1 + i[0] % 3], update_grid=False)
-            i[0] += 1
-
-        ms = timed(step, warm=3, reps=7)
-        print(json.dumps({"what": "wide_heads", "config": "large", "wide_fused_backward": wide, "ms_per_step_eager": ms,
-                          "rays_per_s": n_rays / ms * 1e3}))
-        del net, ts
-        torch.cuda.empty_cache()
-
-
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["feeder", "render", "wide", "sampling"])
+    ap.add_argument("what", choices=["feeder", "render", "sampling"])
     ap.add_argument("--config", default="base_light")
     ap.add_argument("--max-steps", type=int, default=1024)
     a = ap.parse_args()
     if a.what == "feeder":
         bench_feeder()
-    elif a.what == "wide":
-        bench_wide()
     elif a.what == "sampling":
         bench_sampling()
     else:

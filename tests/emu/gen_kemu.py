@@ -125,10 +125,10 @@ MLP_TC_STUB = '''// GENERATED by tests/emu/gen_kemu.py -- test-only
 #include <stdlib.h>
 namespace tnl {
 bool mlp_tc_supported(uint32_t, uint32_t, uint32_t) { return false; }
-size_t mlp_tc_packed_bytes(uint32_t) { return 0; }
-void mlp_tc_pack(uint32_t, const float*, const float*, const float*, const float*, const float*, void*, cudaStream_t) { abort(); }
-void mlp_tc_forward(uint32_t, const void*, const void*, const float*, uint32_t, const int32_t*, float*, float*, float*, cudaStream_t) { abort(); }
-void mlp_tc_backward(uint32_t, const void*, const void*, const float*, uint32_t, const int32_t*, const float*, const float*, void*,
+size_t mlp_tc_packed_bytes(uint32_t, uint32_t) { return 0; }
+void mlp_tc_pack(uint32_t, uint32_t, const float*, const float*, const float*, const float*, const float*, void*, cudaStream_t) { abort(); }
+void mlp_tc_forward(uint32_t, uint32_t, const void*, const void*, const float*, uint32_t, const int32_t*, float*, float*, float*, cudaStream_t) { abort(); }
+void mlp_tc_backward(uint32_t, uint32_t, const void*, const void*, const float*, uint32_t, const int32_t*, const float*, const float*, void*,
                      float*, float*, float*, float*, float*, cudaStream_t) { abort(); }
 }  // namespace tnl
 '''

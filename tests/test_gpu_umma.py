@@ -33,3 +33,12 @@ def test_m64_weight_gradient_products(N):
     D, out = _probe(64, N, 128, True, True, N)
     lanes = np.array([(i // 16) * 32 + i % 16 for i in range(64)])
     assert np.array_equal(out[lanes, :N], D)    # rows 16w..16w+15 live in lanes 32w..32w+15
+
+
+@pytest.mark.parametrize("N,K,a_mn,b_mn", [(144, 128, True, True), (128, 128, True, True), (32, 128, True, True), (16, 128, True, True),
+                                            (144, 128, False, True), (128, 16, False, True), (16, 128, False, True), (128, 144, False, False)])
+def test_m128_products_of_the_wide_heads(N, K, a_mn, b_mn):
+    """the product shapes of csrc/mlp_tc128.cu: M = 128 weight-gradient products (both operands MN-major, contraction over the
+    128 points), N = 144 (in_dim of C = 48), K = 144"""
+    D, out = _probe(128, N, K, a_mn, b_mn, N if N % 8 == 0 else N + 8 - N % 8)
+    assert np.array_equal(out[:, :N], D)

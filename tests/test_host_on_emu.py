@@ -486,9 +486,10 @@ def test_stage_growth_checkpoint_adds_a_zero_level(emu):
 
 
 @pytest.mark.parametrize("C,half", [(32, False), (48, True)])
-def test_field_mlp_function_wide_heads_hybrid_backward(emu, C, half):
-    """network._FieldMLP with the 128-wide heads of the "large" config: fused forward, backward = fused input-gradient chain
-    (tnl_mlp_backward_chain) + library GEMMs for the weight gradients, against the oracle's fp16-autocast autograd"""
+def test_field_mlp_function_wide_heads_forward(emu, C, half):
+    """network._FieldMLP with the 128-wide heads of the "large" config on the host build: the forward (here the mma.sync
+    kernels; the tcgen05 kernels of csrc/mlp_tc128.cu are GPU-only, tests/test_gpu_wide_heads.py) against the oracle's
+    fp16-autocast emulation; the fused backward of the wide heads exists on the tensor cores only and says so"""
     from oracle import field as of
     from trinerflet_b200.network import _FieldMLP
     g = torch.Generator().manual_seed(C)
@@ -497,24 +498,17 @@ def test_field_mlp_function_wide_heads_hybrid_backward(emu, C, half):
     feat = 0.5 * torch.randn(M, 3 * C, generator=g)
     d = torch.randn(M, 3, generator=g)
     d = d / d.norm(dim=-1, keepdim=True)
-    gs, grgb = torch.randn(M, generator=g) * 64.0, torch.randn(M, 3, generator=g) * 64.0
-    W_o = [w.clone().requires_grad_(True) for w in W]
-    f_o = feat.clone().requires_grad_(True)
-    s_o, rgb_o, _ = of.mlp_forward(f_o, d, W_o, fp16=True)
-    ((s_o * gs).sum() + (rgb_o * grgb).sum()).backward()
+    s_o, rgb_o, _ = of.mlp_forward(feat, d, W, fp16=True)
     W_g = [w.clone().requires_grad_(True) for w in W]
     f_g = (feat.half() if half else feat.clone()).requires_grad_(True)
     nv = torch.tensor([M], dtype=torch.int32)
     s_g, rgb_g = _FieldMLP.apply(f_g, d, nv, *W_g)
     assert (rgb_g - rgb_o).abs().max().item() <= 2e-3 and rel_l2(s_g, s_o) <= 2e-3
-    ((s_g * gs).sum() + (rgb_g * grgb).sum()).backward()
-    assert f_g.grad.dtype == f_g.dtype and rel_l2(f_g.grad.float(), f_o.grad) <= 1e-2
-    for a, b in zip(W_g, W_o):
-        assert a.grad.shape == b.grad.shape and rel_l2(a.grad, b.grad) <= 1e-2
+    with pytest.raises(RuntimeError, match="128-wide heads"):
+        (s_g.sum() + rgb_g.sum()).backward()
 
 
-@pytest.mark.parametrize("hidden", [64, 128])
-def test_fp16_training_configuration_matches_fp16_oracle(emu, monkeypatch, hidden):
+def test_fp16_training_configuration_matches_fp16_oracle(emu, monkeypatch, hidden=64):
     """the configuration every reference command trains with (--fp16): fp16 feature stream out of the sampler, fp16-rounded
     projected coordinates, the fused MLP kernels (here the mma.sync ones: the host build reports the tcgen05 kernels as
     unsupported) with their n_valid path -- against oracle/pipeline.py with its fp16-autocast emulation.  CUDA autocast
@@ -524,7 +518,6 @@ def test_fp16_training_configuration_matches_fp16_oracle(emu, monkeypatch, hidde
     monkeypatch.setattr(torch, "is_autocast_enabled", lambda *a, **k: True)
     monkeypatch.setattr(torch, "get_autocast_dtype", lambda *a, **k: torch.float16)
     net = _model(hidden=hidden)
-    net.wide_fused_backward = hidden == 128          # "large" heads: fused forward + hybrid backward (chain kernel + GEMMs)
     net.train()
     sc = scene.make_scene()
     N = 320

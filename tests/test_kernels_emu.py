@@ -761,66 +761,3 @@ def test_march_train_other_bounds_cascades_and_grid_sizes(bound, Hg, dt_gamma, m
     assert _bits_equal(xyzs, x_o) and _bits_equal(deltas, l_o)
 
 
-def _chain_backward_emu(C, hidden, W, feat, d, gs, grgb, half=False, nv=None):
-    """tnl_mlp_backward_chain + the five weight-gradient products formed from its fp16 scratch (what network.py does with
-    library GEMMs) -> g_feat, [dW1..dW5] in the reference's nn.Linear layouts"""
-    M = feat.shape[0]
-    dims, packed = _mlp_pack_emu(C, hidden, W)
-    H = hidden
-    nbytes = kemu.lib().tnl_mlp_chain_scratch_bytes(ctypes.byref(dims), M)
-    assert nbytes == 2 * M * (2 * H + 4 * H + 64)
-    scratch = np.full(nbytes // 2, np.nan, np.float16)
-    f = feat.numpy().astype(np.float16) if half else feat.numpy()
-    g_feat = np.full((M, 3 * C), np.nan, np.float16 if half else np.float32)
-    kemu.call("tnl_mlp_backward_chain", ctypes.byref(dims), packed, f, int(half), d.numpy(), M, nv, gs.numpy(), grgb.numpy(), g_feat,
-              scratch, None)
-    widths = [H, 32, H, H, H, 16, H, H, 16]
-    mats, off = [], 0
-    for w in widths:
-        mats.append(scratch[off:off + M * w].reshape(M, w).astype(np.float32))
-        off += M * w
-    h1, in2, h3, h4, d1, d2, d3, d4, d5 = mats
-    assert np.isfinite(scratch).all()
-    feat16 = feat.numpy().astype(np.float16).astype(np.float32)
-    dW2i = d2.T @ h1                                            # internal row j < 15 <-> reference row j+1, 15 <-> row 0
-    dW2 = np.concatenate([dW2i[15:16], dW2i[:15]], 0)
-    return g_feat, [d1.T @ feat16, dW2, (d3.T @ in2)[:, :31], d4.T @ h3, (d5.T @ h4)[:3]], mats
-
-
-@pytest.mark.parametrize("C,hidden,M", [(16, 64, 200), (32, 128, 150), (48, 128, 90)])
-def test_mlp_chain_backward_plus_library_gemms(C, hidden, M):
-    """the input-gradient chain kernel for the wide heads (k_mlp_bwd in DUMP mode) + weight gradients from its fp16 operand
-    dump: against the oracle's fp16-autocast autograd, and (64-wide) against the fully fused backward kernel"""
-    g = torch.Generator().manual_seed(7 + C + hidden)
-    W = of.init_mlp_weights(C, hidden, hidden, gen=g)
-    feat = 0.5 * torch.randn(M, 3 * C, generator=g)
-    d = torch.randn(M, 3, generator=g)
-    d = d / d.norm(dim=-1, keepdim=True)
-    gs = torch.randn(M, generator=g) * 64.0
-    grgb = torch.randn(M, 3, generator=g) * 64.0
-    W_o = [w.clone().requires_grad_(True) for w in W]
-    f_o = feat.clone().requires_grad_(True)
-    s_o, rgb_o, _ = of.mlp_forward(f_o, d, W_o, fp16=True)
-    ((s_o * gs).sum() + (rgb_o * grgb).sum()).backward()
-    g_feat, dW, mats = _chain_backward_emu(C, hidden, W, feat, d, gs, grgb)
-    assert np.linalg.norm(g_feat - f_o.grad.numpy()) / np.linalg.norm(f_o.grad.numpy()) <= 1e-2
-    for a, b in zip(dW, W_o):
-        assert a.shape == tuple(b.shape)
-        assert np.linalg.norm(a - b.grad.numpy()) / np.linalg.norm(b.grad.numpy()) <= 1e-2, a.shape
-    if hidden == 64:     # same phase-1 code as the fused kernel: identical input gradient, weight gradients equal up to fp32 summation
-        dims, packed = _mlp_pack_emu(C, 64, W)
-        g_ref = np.zeros((M, 3 * C), np.float32)
-        gW = [np.zeros(tuple(w.shape), np.float32) for w in W]
-        kemu.call("tnl_mlp_backward", ctypes.byref(dims), packed, feat.numpy(), 0, d.numpy(), M, None, gs.numpy(), grgb.numpy(), g_ref, *gW, None)
-        assert np.array_equal(g_feat, g_ref)
-        for a, b in zip(dW, gW):
-            assert np.allclose(a, b, rtol=1e-4, atol=1e-4 * np.abs(b).max())
-    # n_valid: rows past it are dumped as zeros and receive a zero input gradient
-    nv = np.array([M // 2], np.int32)
-    g_feat_v, dW_v, mats_v = _chain_backward_emu(C, hidden, W, feat, d, gs, grgb, nv=nv)
-    assert (g_feat_v[M // 2:] == 0).all() and np.array_equal(g_feat_v[:M // 2], g_feat[:M // 2])
-    for m_ in mats_v[4:]:
-        assert (m_[M // 2:] == 0).all()                         # every dOut row past n_valid is zero: no contribution
-    # fp16 feature stream
-    g_feat_h, dW_h, _ = _chain_backward_emu(C, hidden, W, feat, d, gs, grgb, half=True)
-    assert np.array_equal(g_feat_h.astype(np.float32), g_feat)

@@ -423,27 +423,19 @@ __device__ __forceinline__ void relu_mask(uint32_t (&d)[KS][4], const uint32_t (
         }
 }
 
-// DUMP (the 128-wide heads, whose weight gradients fit neither registers nor shared memory of one CTA):
-// phase 1 only; the operand tiles a weight gradient needs -- relu(h1), [SH | geo], relu(h3), relu(h4), dh1 .. d5, fp16 --
-// are copied from shared memory to `dump` (nine row-major [M][width] matrices, see MlpDump) and the five products
-// dW_l = dOut_l^T In_l are left to library GEMMs; gW1..gW5 are not touched.
-struct MlpDump {
-    __half *h1, *in2, *h3, *h4, *d1, *d2, *d3, *d4, *d5;
-};
-
-template <int K1, int H, int HC, int NW, bool FH, bool DUMP = false>
-__global__ void __launch_bounds__(NW * 32, (NW == 4 && !DUMP) ? 2 : 1)
+template <int K1, int H, int HC, int NW, bool FH>
+__global__ void __launch_bounds__(NW * 32, NW == 4 ? 2 : 1)
 k_mlp_bwd(const uint32_t* __restrict__ wp, const void* __restrict__ feat, const float* __restrict__ dirs, uint32_t M,
           const int32_t* __restrict__ n_valid_ptr, const float* __restrict__ g_sigma, const float* __restrict__ g_rgb,
           void* __restrict__ g_feat, float* __restrict__ gW1, float* __restrict__ gW2, float* __restrict__ gW3,
-          float* __restrict__ gW4, float* __restrict__ gW5, MlpDump dump = MlpDump{}) {
-    static_assert(DUMP || (H == 64 && HC == 64), "backward kernel: weight-gradient register tiling is laid out for 64-wide heads");
+          float* __restrict__ gW4, float* __restrict__ gW5) {
+    static_assert(H == 64 && HC == 64, "backward kernel: weight-gradient register tiling is laid out for 64-wide heads");
     static_assert(NW == 4 || NW == 8, "4 or 8 warps");
     constexpr MlpLayout L = make_layout(K1, H, HC);
     using SM = BwdSmem<K1, H, HC, NW>;
     constexpr int SPLIT = NW / 4;            // warps sharing one 16-row block of a weight gradient
-    constexpr int T1 = DUMP ? 1 : (K1 / 8) / SPLIT;     // k-in tiles of dW1 per warp
-    constexpr int T4 = DUMP ? 1 : 8 / SPLIT, T3 = DUMP ? 1 : 4 / SPLIT, T25 = DUMP ? 1 : 8 / NW;
+    constexpr int T1 = (K1 / 8) / SPLIT;     // k-in tiles of dW1 per warp
+    constexpr int T4 = 8 / SPLIT, T3 = 4 / SPLIT, T25 = 8 / NW;
     extern __shared__ __align__(16) __half sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     uint32_t nvalid = M;
@@ -467,7 +459,7 @@ k_mlp_bwd(const uint32_t* __restrict__ wp, const void* __restrict__ feat, const 
         acc5[i][0] = acc5[i][1] = acc5[i][2] = acc5[i][3] = 0.f;
     }
 
-    const uint32_t ntiles = ceil_div(DUMP ? M : nvalid, (uint32_t)SM::PTS);   // DUMP: rows past n_valid are dumped as zeros
+    const uint32_t ntiles = ceil_div(nvalid, (uint32_t)SM::PTS);
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         // ------------------------------ phase 1 ------------------------------
         const int row0 = warp * 16 + g;  // row inside the 128-point tile
@@ -584,30 +576,6 @@ k_mlp_bwd(const uint32_t* __restrict__ wp, const void* __restrict__ feat, const 
             }
         }
         __syncthreads();
-        if (DUMP) {
-            // ------------------------------ dump the operand tiles (coalesced 16-byte rows) ------------------------------
-            const uint32_t row_base = tile * SM::PTS;
-            auto copy = [&](const __half* src, int pitch, __half* dst, int width) {
-                const int vec = width / 8;   // 16-byte chunks per row
-                for (int i = threadIdx.x; i < SM::PTS * vec; i += NW * 32) {
-                    const int r = i / vec, c = i % vec;
-                    if (row_base + r < M)
-                        *(reinterpret_cast<uint4*>(dst + (size_t)(row_base + r) * width) + c) =
-                            *reinterpret_cast<const uint4*>(src + (size_t)r * pitch + 8 * c);
-                }
-            };
-            copy(sm + SM::O_H1, SM::P_H, dump.h1, H);
-            copy(sm + SM::O_I2, SM::P_I, dump.in2, 32);
-            copy(sm + SM::O_H3, SM::P_C, dump.h3, HC);
-            copy(sm + SM::O_H4, SM::P_C, dump.h4, HC);
-            copy(sm + SM::O_D1, SM::P_H, dump.d1, H);
-            copy(sm + SM::O_D2, SM::P_S, dump.d2, 16);
-            copy(sm + SM::O_D3, SM::P_C, dump.d3, HC);
-            copy(sm + SM::O_D4, SM::P_C, dump.d4, HC);
-            copy(sm + SM::O_D5, SM::P_S, dump.d5, 16);
-            __syncthreads();
-            continue;
-        }
         // ------------------------------ phase 2 ------------------------------
         {
             const int nb = warp / SPLIT, hf = warp % SPLIT;
@@ -623,7 +591,7 @@ k_mlp_bwd(const uint32_t* __restrict__ wp, const void* __restrict__ feat, const 
         __syncthreads();
     }
     // ------------------------------ flush weight gradients ------------------------------
-    if (!DUMP) {
+    {
         const int nb = warp / SPLIT, hf = warp % SPLIT;
         const int n0 = nb * 16 + g, n1 = n0 + 8;
 #pragma unroll
@@ -683,7 +651,7 @@ static size_t legacy_packed_bytes(const tnl_mlp_dims* d) {
     const size_t b = sizeof(uint32_t) * (size_t)make_layout((int)d->in_dim, (int)d->hidden, (int)d->hidden_c).total;
     return (b + 255) & ~(size_t)255;
 }
-// tcgen05 path: fp16 feature stream, 64-wide heads (TNL_MLP_LEGACY=1 forces the mma.sync kernels)
+// tcgen05 path: fp16 feature stream (TNL_MLP_LEGACY=1 forces the mma.sync kernels)
 static bool use_tc(const tnl_mlp_dims* d, int feat_fp16) {
     static const bool legacy = getenv("TNL_MLP_LEGACY") != nullptr;
     return !legacy && feat_fp16 && mlp_tc_supported(d->in_dim, d->hidden, d->hidden_c);
@@ -704,7 +672,7 @@ extern "C" {
 
 size_t tnl_mlp_packed_bytes(const tnl_mlp_dims* dims) {
     if (!dims_supported(dims)) return 0;
-    return legacy_packed_bytes(dims) + (mlp_tc_supported(dims->in_dim, dims->hidden, dims->hidden_c) ? mlp_tc_packed_bytes(dims->in_dim) : 0);
+    return legacy_packed_bytes(dims) + (mlp_tc_supported(dims->in_dim, dims->hidden, dims->hidden_c) ? mlp_tc_packed_bytes(dims->in_dim, dims->hidden) : 0);
 }
 
 int tnl_mlp_pack_weights(const tnl_mlp_dims* dims, const float* W1, const float* W2, const float* W3, const float* W4,
@@ -718,7 +686,7 @@ int tnl_mlp_pack_weights(const tnl_mlp_dims* dims, const float* W1, const float*
     k_mlp_pack<<<ceil_div(L.total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         L, W1, W2, W3, W4, W5, static_cast<uint32_t*>(packed));
     if (mlp_tc_supported(dims->in_dim, dims->hidden, dims->hidden_c))
-        mlp_tc_pack(dims->in_dim, W1, W2, W3, W4, W5, static_cast<uint8_t*>(packed) + legacy_packed_bytes(dims),
+        mlp_tc_pack(dims->in_dim, dims->hidden, W1, W2, W3, W4, W5, static_cast<uint8_t*>(packed) + legacy_packed_bytes(dims),
                     reinterpret_cast<cudaStream_t>(stream));
     return finish_launch("mlp_pack_weights");
 }
@@ -738,7 +706,7 @@ int tnl_mlp_forward(const tnl_mlp_dims* dims, const void* packed, const void* fe
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (use_tc(dims, feat_fp16)) {
         TNL_ARG_CHECK(((uintptr_t)feat & 15) == 0, "feat must be 16-byte aligned");
-        mlp_tc_forward(dims->in_dim, static_cast<const uint8_t*>(packed) + legacy_packed_bytes(dims), feat, dirs, M, n_valid, sigma,
+        mlp_tc_forward(dims->in_dim, dims->hidden, static_cast<const uint8_t*>(packed) + legacy_packed_bytes(dims), feat, dirs, M, n_valid, sigma,
                        rgb, geo, s);
         return finish_launch("mlp_forward(tcgen05)");
     }
@@ -756,8 +724,8 @@ int tnl_mlp_backward(const tnl_mlp_dims* dims, const void* packed, const void* f
                      uint32_t M, const int32_t* n_valid, const float* g_sigma, const float* g_rgb, void* g_feat, float* g_W1,
                      float* g_W2, float* g_W3, float* g_W4, float* g_W5, tnl_stream_t stream) {
     if (M == 0) return 0;
-    if (!dims_supported(dims) || dims->hidden != 64) {
-        set_error("mlp_backward: fused backward currently covers hidden = hidden_color = 64 (small/base configs)");
+    if (!dims_supported(dims) || (dims->hidden != 64 && !use_tc(dims, feat_fp16))) {
+        set_error("mlp_backward: the 128-wide heads take the fp16 feature stream (tcgen05 kernels); fp32 features: hidden = hidden_color = 64 only");
         return TNL_ERR_UNSUPPORTED;
     }
     TNL_ARG_CHECK(packed && feat && dirs && g_sigma && g_rgb && g_W1 && g_W2 && g_W3 && g_W4 && g_W5, "null pointer");
@@ -766,7 +734,7 @@ int tnl_mlp_backward(const tnl_mlp_dims* dims, const void* packed, const void* f
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (use_tc(dims, feat_fp16)) {
         TNL_ARG_CHECK(((uintptr_t)feat & 15) == 0 && ((uintptr_t)g_feat & 15) == 0, "feat/g_feat must be 16-byte aligned");
-        mlp_tc_backward(dims->in_dim, static_cast<const uint8_t*>(packed) + legacy_packed_bytes(dims), feat, dirs, M, n_valid,
+        mlp_tc_backward(dims->in_dim, dims->hidden, static_cast<const uint8_t*>(packed) + legacy_packed_bytes(dims), feat, dirs, M, n_valid,
                         g_sigma, g_rgb, g_feat, g_W1, g_W2, g_W3, g_W4, g_W5, s);
         return finish_launch("mlp_backward(tcgen05)");
     }
@@ -804,61 +772,6 @@ int tnl_mlp_backward(const tnl_mlp_dims* dims, const void* packed, const void* f
 #undef CALLB_NW
 #undef CALLB_FH
     return finish_launch("mlp_backward");
-}
-
-size_t tnl_mlp_chain_scratch_bytes(const tnl_mlp_dims* dims, uint32_t M) {
-    if (!dims_supported(dims)) return 0;
-    return sizeof(__half) * (size_t)M * (2 * (size_t)dims->hidden + 4 * (size_t)dims->hidden_c + 64);
-}
-
-int tnl_mlp_backward_chain(const tnl_mlp_dims* dims, const void* packed, const void* feat, int feat_fp16, const float* dirs,
-                           uint32_t M, const int32_t* n_valid, const float* g_sigma, const float* g_rgb, void* g_feat,
-                           void* scratch, tnl_stream_t stream) {
-    if (M == 0) return 0;
-    if (!dims_supported(dims)) {
-        set_error("mlp: unsupported dims");
-        return TNL_ERR_UNSUPPORTED;
-    }
-    TNL_ARG_CHECK(packed && feat && dirs && g_sigma && g_rgb && scratch, "null pointer");
-    TNL_ARG_CHECK(((uintptr_t)feat & 7) == 0 && ((uintptr_t)g_feat & 7) == 0, "feat/g_feat must be 8-byte aligned");
-    TNL_ARG_CHECK(((uintptr_t)scratch & 15) == 0, "scratch must be 16-byte aligned");
-    const size_t h = dims->hidden, hc = dims->hidden_c;
-    __half* b = static_cast<__half*>(scratch);
-    MlpDump d;
-    d.h1 = b;             b += (size_t)M * h;
-    d.in2 = b;            b += (size_t)M * 32;
-    d.h3 = b;             b += (size_t)M * hc;
-    d.h4 = b;             b += (size_t)M * hc;
-    d.d1 = b;             b += (size_t)M * h;
-    d.d2 = b;             b += (size_t)M * 16;
-    d.d3 = b;             b += (size_t)M * hc;
-    d.d4 = b;             b += (size_t)M * hc;
-    d.d5 = b;
-    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    const bool fh = feat_fp16 != 0;
-#define CALLC_FH(K, HH, FHV)                                                                                             \
-    do {                                                                                                                \
-        using SMB = BwdSmem<K, HH, HH, 4>;                                                                              \
-        static bool attr = false;                                                                                       \
-        if (!attr) {                                                                                                    \
-            cudaFuncSetAttribute(k_mlp_bwd<K, HH, HH, 4, FHV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMB::BYTES); \
-            attr = true;                                                                                                \
-        }                                                                                                               \
-        const uint32_t ntiles = ceil_div(M, 64u);                                                                        \
-        const uint32_t blocks = min(ntiles, (uint32_t)kNumSM);                                                           \
-        k_mlp_bwd<K, HH, HH, 4, FHV, true><<<blocks, 128, SMB::BYTES, s>>>(static_cast<const uint32_t*>(packed), feat, dirs, M, n_valid, \
-                                                                           g_sigma, g_rgb, g_feat, nullptr, nullptr, nullptr, \
-                                                                           nullptr, nullptr, d);                          \
-    } while (0)
-#define CALLC(K, HH, HCC)                  \
-    do {                                   \
-        if (fh) CALLC_FH(K, HH, true);     \
-        else CALLC_FH(K, HH, false);       \
-    } while (0)
-    TNL_MLP_DISPATCH(dims, CALLC);
-#undef CALLC
-#undef CALLC_FH
-    return finish_launch("mlp_backward_chain");
 }
 
 }  // extern "C"

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "mlp_math.cuh"
 #include "mlp_tc.cuh"
+#include "mlp_tc_util.cuh"
 #include "umma.cuh"
 #include <stdlib.h>
 
@@ -38,45 +39,21 @@ struct TcW {
     static constexpr uint32_t END = W5 + tile_bytes(16, 64);
 };
 
-__global__ void k_mlp_tc_pack(int K1, const float* __restrict__ W1, const float* __restrict__ W2, const float* __restrict__ W3,
+__global__ void k_mlp_tc_pack(int K1, int H, const float* __restrict__ W1, const float* __restrict__ W2, const float* __restrict__ W3,
                               const float* __restrict__ W4, const float* __restrict__ W5, uint8_t* __restrict__ out) {
-    const uint32_t n1 = 64 * K1, n2 = 16 * 64, n3 = 64 * 32, n4 = 64 * 64, n5 = 16 * 64;
+    // H = hidden = hidden_color (64: this file, 128: mlp_tc128.cu); tile shapes W1 (H, K1) | W2 (16, H) | W3 (H, 32) | W4 (H, H) | W5 (16, H)
+    const uint32_t n1 = H * K1, n2 = 16 * H, n3 = H * 32, n4 = H * H, n5 = 16 * H;
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t base = 0, R, Cc;
     float v;
-    if (i < n1) { R = 64; Cc = K1; v = W1[i]; }
-    else if ((i -= n1, base += n1 * 2, i < n2)) { R = 16; Cc = 64; v = W2[i]; }
-    else if ((i -= n2, base += n2 * 2, i < n3)) { R = 64; Cc = 32; const uint32_t r = i / 32, c = i % 32; v = c < 31 ? W3[r * 31 + c] : 0.f; }
-    else if ((i -= n3, base += n3 * 2, i < n4)) { R = 64; Cc = 64; v = W4[i]; }
-    else if ((i -= n4, base += n4 * 2, i < n5)) { R = 16; Cc = 64; v = (i / 64) < 3 ? W5[i] : 0.f; }
+    if (i < n1) { R = H; Cc = K1; v = W1[i]; }
+    else if ((i -= n1, base += n1 * 2, i < n2)) { R = 16; Cc = H; v = W2[i]; }
+    else if ((i -= n2, base += n2 * 2, i < n3)) { R = H; Cc = 32; const uint32_t r = i / 32, c = i % 32; v = c < 31 ? W3[r * 31 + c] : 0.f; }
+    else if ((i -= n3, base += n3 * 2, i < n4)) { R = H; Cc = H; v = W4[i]; }
+    else if ((i -= n4, base += n4 * 2, i < n5)) { R = 16; Cc = H; v = (i / H) < 3 ? W5[i] : 0.f; }
     else return;
     const uint32_t r = i / Cc, c = i % Cc;
     *reinterpret_cast<__half*>(out + base + tile_off(R, r, c)) = __float2half_rn(v);
-}
-
-// 8 fp32 -> 8 fp16 (one 16-byte tile row chunk), optional ReLU on the rounded values
-template <bool RELU>
-__device__ __forceinline__ uint4 pack8(const float* v) {
-    uint4 o;
-    o.x = pack_h2(v[0], v[1]);
-    o.y = pack_h2(v[2], v[3]);
-    o.z = pack_h2(v[4], v[5]);
-    o.w = pack_h2(v[6], v[7]);
-    if (RELU) { o.x = relu_h2(o.x); o.y = relu_h2(o.y); o.z = relu_h2(o.z); o.w = relu_h2(o.w); }
-    return o;
-}
-// zero the fp16 lanes of `d` whose counterpart in `h` (a ReLU output, never negative) is zero
-__device__ __forceinline__ uint32_t mask_h2(uint32_t d, uint32_t h) {
-    const uint32_t m = (((h & 0x7fffu) != 0u) ? 0x0000ffffu : 0u) | (((h & 0x7fff0000u) != 0u) ? 0xffff0000u : 0u);
-    return d & m;
-}
-__device__ __forceinline__ uint4 mask8(uint4 d, uint4 h) {
-    return make_uint4(mask_h2(d.x, h.x), mask_h2(d.y, h.y), mask_h2(d.z, h.z), mask_h2(d.w, h.w));
-}
-__device__ __forceinline__ uint32_t clamp_valid(const int32_t* n_valid_ptr, uint32_t M) {
-    if (!n_valid_ptr) return M;
-    const int32_t nv = *n_valid_ptr;
-    return nv < 0 ? 0u : ((uint32_t)nv < M ? (uint32_t)nv : M);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -679,27 +656,29 @@ k_umma_bench2(uint32_t a_lbo, uint32_t a_sbo, uint32_t a_step, uint32_t a_type, 
 // host side (called from mlp.cu's C-ABI entry points)
 // ------------------------------------------------------------------------------------------------
 bool mlp_tc_supported(uint32_t in_dim, uint32_t hidden, uint32_t hidden_c) {
-    return (in_dim == 48 || in_dim == 96) && hidden == 64 && hidden_c == 64;   // C = 16 / 32 with 64-wide heads
+    if (hidden != hidden_c) return false;
+    if (hidden == 64) return in_dim == 48 || in_dim == 96;                       // C = 16 / 32 (small / base configs): this file
+    if (hidden == 128) return in_dim == 48 || in_dim == 96 || in_dim == 144;      // "large" heads: mlp_tc128.cu
+    return false;
 }
 
-size_t mlp_tc_packed_bytes(uint32_t in_dim) { return (size_t)64 * in_dim * 2 + 2048 + 4096 + 8192 + 2048; }
+size_t mlp_tc_packed_bytes(uint32_t in_dim, uint32_t hidden) {
+    return 2 * ((size_t)hidden * in_dim + 16 * hidden + 32 * hidden + (size_t)hidden * hidden + 16 * hidden);
+}
 
-void mlp_tc_pack(uint32_t in_dim, const float* W1, const float* W2, const float* W3, const float* W4, const float* W5, void* out,
-                 cudaStream_t s) {
-    const uint32_t total = 64 * in_dim + 16 * 64 + 64 * 32 + 64 * 64 + 16 * 64;
-    k_mlp_tc_pack<<<ceil_div(total, 256u), 256, 0, s>>>((int)in_dim, W1, W2, W3, W4, W5, static_cast<uint8_t*>(out));
+void mlp_tc_pack(uint32_t in_dim, uint32_t hidden, const float* W1, const float* W2, const float* W3, const float* W4, const float* W5,
+                 void* out, cudaStream_t s) {
+    const uint32_t total = (uint32_t)(mlp_tc_packed_bytes(in_dim, hidden) / 2);
+    k_mlp_tc_pack<<<ceil_div(total, 256u), 256, 0, s>>>((int)in_dim, (int)hidden, W1, W2, W3, W4, W5, static_cast<uint8_t*>(out));
 }
 
 template <int K1>
 static void launch_fwd(const void* wpk, const void* feat, const float* dirs, uint32_t M, const int32_t* n_valid, float* sigma,
                        float* rgb, float* geo, cudaStream_t s) {
     using S = TcFwdSmem<K1>;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k_mlp_tc_fwd<K1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL);
-        cudaFuncSetAttribute(k_mlp_tc_fwd<K1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL);
-        attr = true;
-    }
+    // (the attribute is per device and setting it is cheap: no process-wide "already set" flag)
+    cudaFuncSetAttribute(k_mlp_tc_fwd<K1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL);
+    cudaFuncSetAttribute(k_mlp_tc_fwd<K1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL);
     const uint32_t per_sm = (227u * 1024u) / (S::TOTAL + 1024u);
     const uint32_t blocks = min(ceil_div(M, 128u), (uint32_t)kNumSM * (per_sm < 1 ? 1u : per_sm));
     if (dirs)
@@ -710,8 +689,9 @@ static void launch_fwd(const void* wpk, const void* feat, const float* dirs, uin
                                                                n_valid, sigma, rgb, geo);
 }
 
-void mlp_tc_forward(uint32_t in_dim, const void* wpk, const void* feat, const float* dirs, uint32_t M, const int32_t* n_valid,
-                    float* sigma, float* rgb, float* geo, cudaStream_t s) {
+void mlp_tc_forward(uint32_t in_dim, uint32_t hidden, const void* wpk, const void* feat, const float* dirs, uint32_t M,
+                    const int32_t* n_valid, float* sigma, float* rgb, float* geo, cudaStream_t s) {
+    if (hidden == 128) { mlp_tc128_forward(in_dim, wpk, feat, dirs, M, n_valid, sigma, rgb, geo, s); return; }
     if (in_dim == 48) launch_fwd<48>(wpk, feat, dirs, M, n_valid, sigma, rgb, geo, s);
     else launch_fwd<96>(wpk, feat, dirs, M, n_valid, sigma, rgb, geo, s);
 }
@@ -723,19 +703,16 @@ template <int K1>
 static void launch_bwd(const void* wpk, const void* feat, const float* dirs, uint32_t M, const int32_t* n_valid, const float* g_sigma,
                        const float* g_rgb, void* g_feat, float* gW1, float* gW2, float* gW3, float* gW4, float* gW5, cudaStream_t s) {
     using S = TcBwdSmem<K1>;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k_mlp_tc_bwd<K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL);
-        attr = true;
-    }
+    cudaFuncSetAttribute(k_mlp_tc_bwd<K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL);
     const uint32_t blocks = min(ceil_div(M, 256u), (uint32_t)kNumSM);   // one CTA per SM: it owns all 512 TMEM columns
     k_mlp_tc_bwd<K1><<<blocks, 288, S::TOTAL, s>>>(static_cast<const uint8_t*>(wpk), static_cast<const __half*>(feat), dirs, M, n_valid,
                                                    g_sigma, g_rgb, static_cast<__half*>(g_feat), gW1, gW2, gW3, gW4, gW5, g_tc_dbg);
 }
 
-void mlp_tc_backward(uint32_t in_dim, const void* wpk, const void* feat, const float* dirs, uint32_t M, const int32_t* n_valid,
-                     const float* g_sigma, const float* g_rgb, void* g_feat, float* gW1, float* gW2, float* gW3, float* gW4, float* gW5,
-                     cudaStream_t s) {
+void mlp_tc_backward(uint32_t in_dim, uint32_t hidden, const void* wpk, const void* feat, const float* dirs, uint32_t M,
+                     const int32_t* n_valid, const float* g_sigma, const float* g_rgb, void* g_feat, float* gW1, float* gW2, float* gW3,
+                     float* gW4, float* gW5, cudaStream_t s) {
+    if (hidden == 128) { mlp_tc128_backward(in_dim, wpk, feat, dirs, M, n_valid, g_sigma, g_rgb, g_feat, gW1, gW2, gW3, gW4, gW5, s); return; }
     if (in_dim == 48) launch_bwd<48>(wpk, feat, dirs, M, n_valid, g_sigma, g_rgb, g_feat, gW1, gW2, gW3, gW4, gW5, s);
     else launch_bwd<96>(wpk, feat, dirs, M, n_valid, g_sigma, g_rgb, g_feat, gW1, gW2, gW3, gW4, gW5, s);
 }

@@ -22,24 +22,10 @@ from .encoding import get_encoder
 from .renderer import NeRFRenderer
 
 
-def fused_dims_supported(in_dim, hidden, hidden_color, need_grad, wide_backward=False):
-    ok = in_dim in (48, 96, 144) and hidden == hidden_color and hidden in (64, 128)
-    if need_grad:
-        # the fully fused backward covers the 64-wide heads (small / base configs); the 128-wide heads ("large") have the
-        # opt-in hybrid of _FieldMLP.backward: fused input-gradient chain + library GEMMs for the weight gradients
-        ok = ok and (hidden == 64 or wide_backward)
-    return ok
-
-
-def _mm_f32(a_t, b):
-    """fp16 x fp16 -> fp32 product of a weight gradient (dOut^T In): fp32 output where the library offers it (no fp16
-    overflow of loss-scaled sums over millions of points), plain fp32 GEMM otherwise"""
-    if a_t.is_cuda:
-        try:
-            return torch.mm(a_t, b, out_dtype=torch.float32)
-        except (TypeError, RuntimeError):
-            pass
-    return a_t.float() @ b.float()
+def fused_dims_supported(in_dim, hidden, hidden_color):
+    """the fused kernels cover the reference's configurations: C in {16, 32, 48}, hidden = hidden_color in {64, 128}
+    (forward and backward; the 128-wide heads on the tcgen05 kernels of csrc/mlp_tc128.cu)"""
+    return in_dim in (48, 96, 144) and hidden == hidden_color and hidden in (64, 128)
 
 
 def pack_mlp_weights(dims, weights):
@@ -53,13 +39,33 @@ def pack_mlp_weights(dims, weights):
     return packed
 
 
+_warned_library_path = False
+
+
+def _warn_library_path(net, x):
+    """The fused kernels implement the fp16-autocast arithmetic every reference command trains with (--fp16).  Outside CUDA fp16
+    autocast, or with head sizes other than 64 / 128, the heads run the reference's literal op sequence through torch's
+    library GEMMs: a documented precision switch, never silent."""
+    global _warned_library_path
+    if not _warned_library_path and x.is_cuda:
+        import warnings
+        why = ("MLP dimensions outside the fused kernels" if not fused_dims_supported(net.in_dim, net.hidden_dim, net.hidden_dim_color)
+               else "no CUDA fp16 autocast is active")
+        warnings.warn(f"trinerflet_b200.NeRFNetwork: {why}; the sigma/color heads run as plain torch ops (library GEMMs), not the "
+                      "fused sm_100a kernels. Wrap the call in torch.autocast('cuda', dtype=torch.float16) as the reference's --fp16 does.")
+        _warned_library_path = True
+
+
 class _FieldMLP(Function):
     """(feat [M,3C], dirs [M,3]) -> sigma [M] fp32, rgb [M,3] fp32 (fp16-representable values)."""
 
     @staticmethod
     def forward(ctx, feat, dirs, n_valid, W1, W2, W3, W4, W5):
         feat = feat.contiguous()
-        if feat.dtype != torch.float16:
+        ctx.in_dtype = feat.dtype
+        if W1.shape[0] != 64:
+            feat = feat.half()          # 128-wide heads: tcgen05 kernels only, fp16 feature stream (the first Linear's own rounding)
+        elif feat.dtype != torch.float16:
             feat = feat.float()
         fh = int(feat.dtype == torch.float16)
         dirs = dirs.detach().contiguous().float()
@@ -84,30 +90,12 @@ class _FieldMLP(Function):
         g_sigma = g_sigma.contiguous().float()
         g_rgb = g_rgb.contiguous().float()
         g_feat = torch.empty_like(feat)
-        if hidden != 64:
-            # 128-wide heads: their weight gradients (172 KB of fp32) fit neither the registers nor the shared memory of one
-            # CTA next to the operand tiles.  One fused kernel recomputes the activations, runs the input-gradient chain and
-            # dumps the fp16 operands of the five weight-gradient products; the products are plain library GEMMs.
-            lib = _lib.load()
-            halves = int(lib.tnl_mlp_chain_scratch_bytes(ctypes.byref(dims), M)) // 2
-            scratch = torch.empty(halves, device=feat.device, dtype=torch.float16)
-            call("tnl_mlp_backward_chain", ctypes.byref(dims), ptr(packed), ptr(feat), int(feat.dtype == torch.float16), ptr(dirs), M,
-                 ptr(n_valid) if has_nv else None, ptr(g_sigma), ptr(g_rgb), ptr(g_feat), ptr(scratch), stream())
-            mats, off = [], 0
-            for w in (hidden, 32, hidden_c, hidden_c, hidden, 16, hidden_c, hidden_c, 16):
-                mats.append(scratch[off:off + M * w].view(M, w))
-                off += M * w
-            h1, in2, h3, h4, d1, d2, d3, d4, d5 = mats
-            feat16 = feat if feat.dtype == torch.float16 else feat.half()
-            g2 = _mm_f32(d2.t(), h1)                          # internal row j < 15 <-> sigma_net[1] row j+1, 15 <-> row 0
-            gW = [_mm_f32(d1.t(), feat16), torch.cat([g2[15:16], g2[:15]], 0), _mm_f32(d3.t(), in2)[:, :31].contiguous(),
-                  _mm_f32(d4.t(), h3), _mm_f32(d5.t(), h4)[:3].contiguous()]
-            return (g_feat, None, None, *gW)
         gW = [torch.zeros(s, device=feat.device, dtype=torch.float32) for s in ctx.wshapes]
         call("tnl_mlp_backward", ctypes.byref(dims), ptr(packed), ptr(feat), int(feat.dtype == torch.float16), ptr(dirs), M,
              ptr(n_valid) if has_nv else None, ptr(g_sigma), ptr(g_rgb), ptr(g_feat), *[ptr(g) for g in gW], stream())
-        if has_nv:
-            pass  # rows >= *n_valid of g_feat are never read: the sampling backward skips them with the same counter
+        # (rows >= *n_valid of g_feat are never read: the sampling backward skips them with the same counter)
+        if g_feat.dtype != ctx.in_dtype:
+            g_feat = g_feat.to(ctx.in_dtype)
         return (g_feat, None, None, *gW)
 
 
@@ -165,10 +153,9 @@ class NeRFNetwork(NeRFRenderer):
         return (self.sigma_net[0].weight, self.sigma_net[1].weight, self.color_net[0].weight, self.color_net[1].weight,
                 self.color_net[2].weight)
 
-    def _fused(self, need_grad):
+    def _fused(self):
         return (torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.float16
-                and fused_dims_supported(self.in_dim, self.hidden_dim, self.hidden_dim_color, need_grad,
-                                         getattr(self, "wide_fused_backward", False)))
+                and fused_dims_supported(self.in_dim, self.hidden_dim, self.hidden_dim_color))
 
     # visit the samples of a training step in the order of a coarse 3-D grid (L2 locality of the plane gather /
     # gradient scatter, see csrc/sort.cu); per-point results do not depend on it
@@ -180,12 +167,12 @@ class NeRFNetwork(NeRFRenderer):
         if x.is_cuda and x.shape[0] >= self.spatial_sort_min_points and torch.is_grad_enabled():
             from .triplane_encoder import cell_sort
             perm = cell_sort(x, self.bound, n_valid, 64)
-        need_grad = torch.is_grad_enabled() and any(w.requires_grad for w in self._weights())
-        fused = self._fused(need_grad)
+        fused = self._fused()
         # fused path: the feature stream between the gather and the MLP kernels is fp16 (the first Linear's own rounding)
         feat = self.encoder(x, bound=self.bound, n_valid=n_valid, perm=perm, half_out=fused)
         if fused:
             return _FieldMLP.apply(feat, d, n_valid, *self._weights())
+        _warn_library_path(self, x)
         # reference op sequence (network.py:125-147); precision follows the ambient autocast state
         h = F.relu(self.sigma_net[0](feat))
         h = self.sigma_net[1](h)
@@ -198,7 +185,7 @@ class NeRFNetwork(NeRFRenderer):
         return sigma, color
 
     def density(self, x):
-        fused = not torch.is_grad_enabled() and self._fused(False)
+        fused = not torch.is_grad_enabled() and self._fused()
         feat = self.encoder(x, bound=self.bound, half_out=fused)
         if fused:
             sigma, geo = _DensityMLP.apply(feat, *self._weights())
