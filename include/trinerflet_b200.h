@@ -260,9 +260,15 @@ int tnl_adam_step(float* p, const float* g, float* m, float* v, uint64_t n, cons
  * indices [n] int32 Morton codes, noise [n][3] uniform [0,1) -> xyz [n][3] */
 int tnl_grid_cell_positions(const int32_t* indices, uint32_t n, uint32_t H, float bound_c, const float* noise,
                             float* xyz, tnl_stream_t stream);
-/* grid[idx] = max(grid[idx]*decay, sigma*density_scale) where both >= 0 (renderer.py:526-527) for the
- * full sweep (indices == NULL => idx = i) or scattered cells; see DESIGN.md for the tmp_grid semantics. */
-int tnl_grid_ema_update(float* grid, const float* tmp_grid, uint32_t n, float decay, tnl_stream_t stream);
+/* The tail of update_extra_state without a host round trip (renderer.py:526-534): grid = max(grid*decay, tmp_grid) where both >= 0, plus
+ * *sum = sum_i max(grid[i], 0) in double (zeroed here); then mean = *sum / n_cells -> *mean_out, thresh = min(mean, thresh_cap),
+ * bitfield = packbits(grid > thresh).  n_cells % 32 == 0. */
+int tnl_grid_ema_update_sum(float* grid, const float* tmp_grid, uint32_t n, float decay, double* sum, tnl_stream_t stream);
+int tnl_packbits_mean(const float* grid, uint32_t n_cells, const double* sum, float thresh_cap, float* mean_out,
+                      uint8_t* bitfield, tnl_stream_t stream);
+/* tmp_grid_cascade[indices[i]] = sigma[i] * scale   (renderer.py:486-488: `tmp_grid[cas, indices] = sigmas * density_scale`) */
+int tnl_grid_scatter(const int32_t* indices, const float* sigma, uint32_t n, float scale, float* tmp_grid_cascade,
+                     tnl_stream_t stream);
 
 /* ------------------------------------------------------------------ step feeder -- */
 /* replaces, for one step's batch, get_rays (reconstruction/nerf/utils.py:64-149), the index into the shuffled ray table

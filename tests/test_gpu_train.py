@@ -268,3 +268,67 @@ def test_fused_adam_resumes_from_torch_adam_checkpoint():
     assert float(fused.param_groups[0]["_tnl_state"][0]) == 4.0
     for (n, pa), pb in zip(net_a.named_parameters(), net_b.parameters()):
         assert rel_l2(pb, pa) <= 1e-6, (n, rel_l2(pb, pa))
+
+
+@pytest.mark.parametrize("partial", [False, True])
+def test_update_extra_state_matches_oracle(partial):
+    """the density-grid refresh on the device (cell positions -> plane gather -> density head -> scatter ->
+    EMA-max -> mean -> packbits; one host read, threshold kept on the device) against oracle/grid.py, which restates
+    renderer.py:448-542, fed the SAME random draws (the product's torch.rand / torch.randint sequence replayed on the same
+    seeded CUDA generator).  sigma carries the fp16-autocast tolerance (2e-3 relative); occupancy bits must be exact wherever
+    a cell is not within that band of the threshold; cells the partial sweep drew twice are a race in the reference itself."""
+    from oracle import field as of, grid as og, wavelet as ow
+    net = _model("tiny")
+    with torch.no_grad():
+        net.sigma_net[1].weight[0].mul_(40.0)      # spread the density logits (random init puts every sigma within a few % of 1)
+    H, N = 128, 128 ** 3 // 4
+    if partial:
+        net.iter_density = 16
+    else:
+        net.density_grid.zero_(); net.iter_density = 0; net.mean_density = 0
+    net.local_step = 5
+    net.step_counter[:5, 0] = torch.tensor([1000, 2000, 3000, 4000, 5001], dtype=torch.int32)
+    grid0 = net.density_grid.detach().cpu().clone()
+    counter0 = net.step_counter.cpu().clone()
+    # ---- replay of the draws (same seed, same call order as NeRFRenderer.update_extra_state) ----
+    torch.manual_seed(77)
+    draws = []
+    for cas in range(2):
+        if partial:
+            coords = torch.randint(0, H, (N, 3), device="cuda")
+            n_occ = int((grid0[cas] > 0).sum())
+            pick = torch.randint(0, n_occ, [N], dtype=torch.long, device="cuda") if n_occ > 0 else None
+            noise = torch.rand(N + (N if n_occ > 0 else 0), 3, device="cuda")
+            draws.append((coords.cpu(), None if pick is None else pick.cpu(), noise.cpu()))
+        else:
+            draws.append(torch.rand(H ** 3, 3, device="cuda").cpu())
+    torch.manual_seed(77)
+    with torch.autocast("cuda", dtype=torch.float16):
+        net.update_extra_state()
+    # ---- oracle ----
+    planes = ow.build_planes(net.encoder.planes_features.detach().cpu().contiguous(),
+                             [p.detach().cpu().contiguous() for p in net.encoder.planes_features_wavelet_coefs])
+    W = [w.detach().cpu() for w in net._weights()]
+
+    fp16 = net.density_grid.is_cuda        # (the CPU dry run of this file has no autocast: fp32 on both sides there)
+
+    def density(xyz):
+        return of.density_forward(of.sample_planes(planes, xyz, 1.5, fp16=fp16), W, fp16=fp16)[0]
+
+    ref = og.update_extra_state(grid0, 16 if partial else 0, density, draws, step_counter=counter0, local_step=5)
+    got = net.density_grid.detach().cpu()
+    ok = ~ref["duplicated"]
+    rel = ((got - ref["grid"]).abs() / ref["grid"].abs().clamp_min(1e-3))[ok]
+    assert rel.max().item() <= 4e-3, rel.max().item()
+    assert abs(net.mean_density - ref["mean_density"]) <= 2e-3 * ref["mean_density"]
+    assert net.mean_count == ref["mean_count"] == 3000 and net.local_step == 0 and net.iter_density == (17 if partial else 1)
+    # occupancy bits: exact outside the tolerance band around the threshold
+    thresh = ref["thresh"]
+    bits_g = np.unpackbits(net.density_bitfield.cpu().numpy(), bitorder="little").astype(bool).reshape(2, -1)
+    bits_o = np.unpackbits(ref["bitfield"], bitorder="little").astype(bool).reshape(2, -1)
+    band = ((ref["grid"] - thresh).abs() <= 6e-3 * max(thresh, 1e-3)).numpy() | ref["duplicated"].numpy()
+    assert np.array_equal(bits_g[~band], bits_o[~band])
+    assert band.mean() < (0.2 if partial else 0.05) and 0.01 < bits_g.mean() < 0.99     # (partial sweep: ~8 % of the cells are drawn twice)
+    # and the packed bits are self-consistent with the device grid and the device threshold
+    from trinerflet_b200 import raymarching as rm
+    assert torch.equal(net.density_bitfield, rm.packbits(net.density_grid, min(net.mean_density, net.density_thresh)))

@@ -357,8 +357,24 @@ def test_grid_cell_positions_and_ema():
     tmp = rng.random(n).astype(np.float32)
     tmp[::5] = -1.0
     want = np.where((grid >= 0) & (tmp >= 0), np.maximum(grid * np.float32(0.95), tmp), grid)
-    kemu.call("tnl_grid_ema_update", grid, tmp, n, 0.95, None)
+    acc = np.full(1, 123.0, np.float64)                 # (zeroed by the call)
+    kemu.call("tnl_grid_ema_update_sum", grid, tmp, n, 0.95, acc, None)
     assert np.array_equal(grid, want)
+    assert abs(acc[0] - np.clip(want, 0, None).astype(np.float64).sum()) <= 1e-3
+    # mean / threshold / packbits on the device (renderer.py:528-534)
+    for cap in (10.0, 0.2):
+        mean, bits = np.zeros(1, np.float32), np.zeros(n // 8, np.uint8)
+        kemu.call("tnl_packbits_mean", grid, n, acc, cap, mean, bits, None)
+        assert abs(mean[0] - np.clip(want, 0, None).mean()) <= 1e-6
+        assert np.array_equal(bits, np.packbits(want > min(mean[0], np.float32(cap)), bitorder="little"))
+    # tmp_grid[indices] = sigma * density_scale
+    sel = rng.permutation(n)[:1000].astype(np.int32)
+    sig = rng.random(1000).astype(np.float32)
+    tmp2 = np.full(n, -1.0, np.float32)
+    kemu.call("tnl_grid_scatter", sel, sig, 1000, 2.0, tmp2, None)
+    want2 = np.full(n, -1.0, np.float32)
+    want2[sel] = sig * np.float32(2.0)
+    assert np.array_equal(tmp2, want2)
 
 
 # ------------------------------------------------------------------------------------------------ step feeder

@@ -69,7 +69,9 @@ SIGNATURES = {
     "tnl_adam_prepare": (_int, [_vp, _vp, _f32, _f32, _vp]),
     "tnl_adam_step": (_int, [_vp, _vp, _vp, _vp, ctypes.c_uint64, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _f32, _vp]),
     "tnl_grid_cell_positions": (_int, [_vp, _u32, _u32, _f32, _vp, _vp, _vp]),
-    "tnl_grid_ema_update": (_int, [_vp, _vp, _u32, _f32, _vp]),
+    "tnl_grid_ema_update_sum": (_int, [_vp, _vp, _u32, _f32, _vp, _vp]),
+    "tnl_packbits_mean": (_int, [_vp, _u32, _vp, _f32, _vp, _vp, _vp]),
+    "tnl_grid_scatter": (_int, [_vp, _vp, _u32, _f32, _vp, _vp]),
     "tnl_rays_from_ids": (_int, [_vp, _u32, _f32, _f32, _f32, _f32, _u32, _u32, _vp, ctypes.c_int64, _u32, _vp, _u32, _vp, _vp,
                                  _vp, _vp]),
 }

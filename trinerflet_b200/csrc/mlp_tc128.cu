@@ -381,14 +381,17 @@ k_mlp_tc_bwd128(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat
             const uint32_t pn = (tile + gridDim.x) * 128 + t;
             load_x_async<K1>(smem + S::XR, t, feat, pn, pn < nvalid);
         }
-        if (g_feat && p < M) {
+        {   // (tcgen05.ld is warp-collective: every lane executes it, the stores are predicated)
             uint4* dst = reinterpret_cast<uint4*>(g_feat + (size_t)p * K1);
+            const bool st = g_feat != nullptr && p < M;
 #pragma unroll
             for (int c0 = 0; c0 < K1; c0 += 48) {
                 float a[48];
                 tmem_load_row<48>(trow + c0, a);
+                if (st) {
 #pragma unroll
-                for (int kc = 0; kc < 6; ++kc) dst[c0 / 8 + kc] = v ? pack8<false>(a + 8 * kc) : make_uint4(0u, 0u, 0u, 0u);
+                    for (int kc = 0; kc < 6; ++kc) dst[c0 / 8 + kc] = v ? pack8<false>(a + 8 * kc) : make_uint4(0u, 0u, 0u, 0u);
+                }
             }
         }
         // the next tile's first product is ordered behind these loads by the stage's __syncthreads

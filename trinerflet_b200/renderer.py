@@ -202,50 +202,85 @@ class NeRFRenderer(nn.Module):
         self.density_grid[count == 0] = -1
         print(f'[mark untrained grid] {(count == 0).sum()} from {H ** 3 * self.cascade}')
 
-    def _query_cells(self, cas, indices):
-        """Jittered cell-centre density for Morton cells `indices` of cascade `cas` (renderer.py:477-486, 507-516)."""
+    def _sweep_cells(self, cas, idx32, tmp_grid):
+        """Jittered cell-centre density of the Morton cells `idx32` of cascade `cas`, written to tmp_grid[cas, idx]
+        (renderer.py:477-488, 507-518): positions, field query and the scatter are three launches, nothing returns to the host."""
         H = self.grid_size
         bound_c = min(2 ** cas, self.bound)
-        n = indices.shape[0]
-        noise = torch.rand(n, 3, device=indices.device, dtype=torch.float32)  # == torch.rand_like(cas_xyzs)
-        xyz = torch.empty(n, 3, device=indices.device, dtype=torch.float32)
-        idx32 = indices.int().contiguous()
+        n = idx32.shape[0]
+        noise = torch.rand(n, 3, device=idx32.device, dtype=torch.float32)  # == torch.rand_like(cas_xyzs)
+        xyz = torch.empty(n, 3, device=idx32.device, dtype=torch.float32)
         call("tnl_grid_cell_positions", ptr(idx32), n, H, float(bound_c), ptr(noise), ptr(xyz), stream())
-        sigmas = self.density(xyz)['sigma'].reshape(-1).detach().float()
-        return sigmas * self.density_scale
+        sigmas = self.density(xyz)['sigma'].reshape(-1).detach().float().contiguous()
+        call("tnl_grid_scatter", ptr(idx32), ptr(sigmas), n, float(self.density_scale), ptr(tmp_grid[cas]), stream())
+
+    @property
+    def mean_density(self):
+        """renderer.py:528.  Kept on the device by update_extra_state; the float is fetched (one 4-byte read) only when somebody
+        looks at it -- the reference reads it back inside every update."""
+        t = self.__dict__.get("_mean_density_t")
+        if t is not None:
+            self.__dict__["_mean_density"] = float(t.item())
+            self.__dict__["_mean_density_t"] = None
+        return self.__dict__.get("_mean_density", 0)
+
+    @mean_density.setter
+    def mean_density(self, v):
+        self.__dict__["_mean_density"] = v
+        self.__dict__["_mean_density_t"] = None
 
     @torch.no_grad()
     def update_extra_state(self, decay=0.95, S=128):
+        """renderer.py:448-542 with the same RNG call sequence (torch.rand / torch.randint draws, in the reference's order, so a
+        seeded run consumes the generator identically) and ONE host synchronisation: the two data-dependent integers the
+        reference's own control flow needs on the host -- the occupied-cell counts that bound `torch.randint` in the partial
+        sweep (:500-501) and the sample-count average `mean_count` (:538-539) -- are fetched together up front.  The threshold
+        (mean density) stays on the device: EMA-max + mean + packbits are two kernels (tnl_grid_ema_update_sum,
+        tnl_packbits_mean)."""
         if not self.cuda_ray:
             return
         H = self.grid_size
-        tmp_grid = -torch.ones_like(self.density_grid)
-        if self.iter_density < 16:  # full sweep
-            _, indices = self._all_cells()
-            indices = indices.long()
+        dev = self.density_bitfield.device
+        total_step = min(16, self.local_step)
+        partial = self.iter_density >= 16
+        # ---- the one read-back: [occupied cells per cascade (partial sweep only), sum of the step counters] ----
+        head = []
+        if partial:
+            occ_mask = self.density_grid > 0
+            head.append(occ_mask.sum(dim=1).to(torch.int64))
+        if total_step > 0:
+            head.append(self.step_counter[:total_step, 0].sum().to(torch.int64).reshape(1))
+        host = torch.cat(head).tolist() if head else []
+        n_occ = host[:self.cascade] if partial else None
+        tmp_grid = torch.full_like(self.density_grid, -1.0)
+        if not partial:  # full sweep: every cell of every cascade, in the reference's meshgrid('ij') order
+            cells = self.__dict__.get("_cells_cache")
+            if cells is None or cells.device != dev:
+                cells = self._all_cells()[1].int().contiguous()
+                self.__dict__["_cells_cache"] = cells
             for cas in range(self.cascade):
-                tmp_grid[cas, indices] = self._query_cells(cas, indices)
+                self._sweep_cells(cas, cells, tmp_grid)
         else:  # H^3/4 uniform cells + H^3/4 cells drawn from the occupied set, per cascade
             N = H ** 3 // 4
-            dev = self.density_bitfield.device
             for cas in range(self.cascade):
                 coords = torch.randint(0, H, (N, 3), device=dev)
-                indices = raymarching.morton3D(coords).long()
-                occ = torch.nonzero(self.density_grid[cas] > 0).squeeze(-1)
-                if occ.shape[0] > 0:
-                    pick = torch.randint(0, occ.shape[0], [N], dtype=torch.long, device=dev)
-                    indices = torch.cat([indices, occ[pick]], dim=0)
-                tmp_grid[cas, indices] = self._query_cells(cas, indices)
+                indices = raymarching.morton3D(coords)
+                if n_occ[cas] > 0:
+                    occ = torch.nonzero_static(occ_mask[cas], size=int(n_occ[cas])).squeeze(-1)
+                    pick = torch.randint(0, int(n_occ[cas]), [N], dtype=torch.long, device=dev)
+                    indices = torch.cat([indices.long(), occ[pick]], dim=0)
+                self._sweep_cells(cas, indices.int().contiguous(), tmp_grid)
         flat = self.density_grid.view(-1)
-        call("tnl_grid_ema_update", ptr(flat), ptr(tmp_grid.view(-1)), flat.numel(), float(decay), stream())
-        self.mean_density = torch.mean(self.density_grid.clamp(min=0)).item()
+        acc = torch.empty(1, dtype=torch.float64, device=dev)
+        mean_t = torch.empty(1, dtype=torch.float32, device=dev)
+        call("tnl_grid_ema_update_sum", ptr(flat), ptr(tmp_grid.view(-1)), flat.numel(), float(decay), ptr(acc), stream())
         self.iter_density += 1
-        thresh = min(self.mean_density, self.density_thresh)
-        self.density_bitfield = raymarching.packbits(self.density_grid, thresh, self.density_bitfield)
+        call("tnl_packbits_mean", ptr(flat), flat.numel(), ptr(acc), float(self.density_thresh), ptr(mean_t), ptr(self.density_bitfield),
+             stream())
+        self.__dict__["_mean_density_t"] = mean_t
         self.mark_bitfield_changed()
-        total_step = min(16, self.local_step)
         if total_step > 0:
-            self.mean_count = int(self.step_counter[:total_step, 0].sum().item() / total_step)
+            self.mean_count = int(host[-1] / total_step)
         self.local_step = 0
 
     def render(self, rays_o, rays_d, staged=False, max_ray_batch=4096, **kwargs):
