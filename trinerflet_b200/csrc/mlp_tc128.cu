@@ -229,7 +229,10 @@ k_mlp_tc_fwd128(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward: CTA = one warpgroup = one 128-point tile per iteration; warp 0 issues the MMAs of a stage
+// backward: CTA = 256 threads = one 128-point tile per iteration.  Thread (t, hf): point t = tid & 127 (TMEM lane t; warps w and
+// w + 4 share a lane quarter), column half hf = tid >> 7: after every product the two halves read / convert / store their own
+// 64 of the 128 accumulator columns, which halves the (latency-bound) epilogue of the single tile a CTA can hold.  Warp 0
+// issues the MMAs of a stage.
 // ------------------------------------------------------------------------------------------------
 template <int K1>
 struct TcBwd128Smem {
@@ -245,8 +248,20 @@ struct TcBwd128Smem {
     static constexpr uint32_t TOTAL = BAR + 16;
 };
 
+// half of thread t's feature row (chunks [hf * K1/16, (hf + 1) * K1/16)) -> the X tile, asynchronously
 template <int K1>
-__global__ void __launch_bounds__(128, 1)
+__device__ __forceinline__ void load_x_half_async(uint8_t* xtile, uint32_t t, uint32_t hf, const __half* __restrict__ feat, uint32_t p, bool valid) {
+    constexpr int NCH = K1 / 16;
+    const __half* src = (valid ? feat + (size_t)p * K1 : feat) + hf * NCH * 8;
+    const uint32_t dst = smem_u32(xtile) + (hf * NCH * 128u + t) * 16u;
+    const uint32_t nbytes = valid ? 16u : 0u;
+#pragma unroll
+    for (int kc = 0; kc < NCH; ++kc)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + kc * 2048u), "l"(src + kc * 8), "r"(nbytes) : "memory");
+}
+
+template <int K1>
+__global__ void __launch_bounds__(256, 1)
 k_mlp_tc_bwd128(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat, const float* __restrict__ dirs, uint32_t M,
                 const int32_t* __restrict__ n_valid_ptr, const float* __restrict__ g_sigma, const float* __restrict__ g_rgb,
                 __half* __restrict__ g_feat, float* __restrict__ gW1, float* __restrict__ gW2, float* __restrict__ gW3,
@@ -257,13 +272,14 @@ k_mlp_tc_bwd128(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat
     constexpr uint32_t CW = K1 < 128 ? 128 : K1;
     constexpr uint32_t TM_C = 0, TM_W1 = CW, TM_W4 = TM_W1 + K1, TM_W3 = TM_W4 + 128, TM_W2 = TM_W3 + 32, TM_W5 = TM_W2 + 16;
     constexpr uint32_t TM_COLS = 512;
+    constexpr int KH = K1 / 2;             // g_feat / dW1 columns per half (72, 48, 24: multiples of 8)
     static_assert(TM_W5 + 16 <= TM_COLS, "TMEM column budget");
     static_assert(S::TOTAL <= 227 * 1024, "shared memory budget");
     extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, t = tid;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, t = tid & 127, hf = tid >> 7;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + S::BAR);
     uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + S::BAR + 8);
-    for (uint32_t i = tid * 16; i < W::END; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = __ldg(reinterpret_cast<const uint4*>(wpk + i));
+    for (uint32_t i = tid * 16; i < W::END; i += 256 * 16) *reinterpret_cast<uint4*>(smem + i) = __ldg(reinterpret_cast<const uint4*>(wpk + i));
     if (tid == 0) { mbar_init(bar, 1); mbar_init_fence(); }
     if (warp == 0) tmem_alloc(tslot, TM_COLS);
     fence_async_smem();
@@ -271,7 +287,8 @@ k_mlp_tc_bwd128(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem = *tslot;
-    const uint32_t trow = tmem + ((warp * 32u) << 16) + TM_C;
+    const uint32_t tlane = tmem + (((warp & 3u) * 32u) << 16);   // this warp's lane quarter
+    const uint32_t trow = tlane + TM_C;
     const uint32_t tc = tmem + TM_C;
     const uint32_t sb4 = smem_u32(smem) >> 4;
     const uint32_t W14 = sb4 + (W::W1 >> 4), W24 = sb4 + (W::W2 >> 4), W34 = sb4 + (W::W3 >> 4), W44 = sb4 + (W::W4 >> 4), W54 = sb4 + (W::W5 >> 4);
@@ -292,9 +309,26 @@ k_mlp_tc_bwd128(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat
     }                                      \
     mbar_wait(bar, phase); phase ^= 1;     \
     fence_after_sync()
+    // this thread's 64 of the 128 accumulator columns -> fp16 row chunks of a tile(128, 128)
+#define TNL_EPI_RELU(TILE)                                                                                                   \
+    {                                                                                                                        \
+        float a[64];                                                                                                         \
+        tmem_load_row<64>(trow + hf * 64u, a);                                                                               \
+        _Pragma("unroll") for (int kc = 0; kc < 8; ++kc)                                                                     \
+            *reinterpret_cast<uint4*>(smem + (TILE) + ((hf * 8u + kc) * 128u + t) * 16u) = pack8<true>(a + 8 * kc);         \
+    }
+#define TNL_EPI_MASK(TILE)                                                                                                   \
+    {                                                                                                                        \
+        float a[64];                                                                                                         \
+        tmem_load_row<64>(trow + hf * 64u, a);                                                                               \
+        _Pragma("unroll") for (int kc = 0; kc < 8; ++kc) {                                                                   \
+            uint4* q = reinterpret_cast<uint4*>(smem + (TILE) + ((hf * 8u + kc) * 128u + t) * 16u);                          \
+            *q = mask8(pack8<false>(a + 8 * kc), *q);                                                                        \
+        }                                                                                                                    \
+    }
     if (my_tiles > 0) {
         const uint32_t p0 = blockIdx.x * 128 + t;
-        load_x_async<K1>(smem + S::XR, t, feat, p0, p0 < nvalid);
+        load_x_half_async<K1>(smem + S::XR, t, hf, feat, p0, p0 < nvalid);
     }
     for (uint32_t it = 0; it < my_tiles; ++it) {
         const uint32_t tile = blockIdx.x + it * gridDim.x;
@@ -302,7 +336,7 @@ k_mlp_tc_bwd128(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat
         const bool v = p < nvalid;
         const bool accw = it > 0;          // weight-gradient accumulators: initialised by the first tile's products
         float d[3] = {0.f, 0.f, 0.f}, gr[3] = {0.f, 0.f, 0.f}, gs = 0.f;
-        if (v) {
+        if (v && hf == 0) {                // (the 16-column stages are half 0's)
 #pragma unroll
             for (int j = 0; j < 3; ++j) { d[j] = __ldg(dirs + 3 * (size_t)p + j); gr[j] = __ldg(g_rgb + 3 * (size_t)p + j); }
             gs = __ldg(g_sigma + p);
@@ -310,10 +344,10 @@ k_mlp_tc_bwd128(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat
         cp_async_wait_all();
         // ---- recompute ----
         TNL_STAGE(mma_group<K1 / 16>(tc, op_kmajor(X4, 128, 0, 0), op_kmajor(W14, 128, 0, 0), make_idesc(128, 128, false, false), false));   // h1
-        epi_store<128, true>(trow, smem + S::H1, t);
+        TNL_EPI_RELU(S::H1);
         TNL_STAGE(mma_group<8>(tc, op_kmajor(H14, 128, 0, 0), op_kmajor(W24, 16, 0, 0), make_idesc(128, 16, false, false), false));          // h2
-        float logit;
-        {
+        float logit = 0.f;
+        if (hf == 0) {
             float h2[16];
             tmem_load_row<16>(trow, h2);
 #pragma unroll
@@ -333,11 +367,11 @@ k_mlp_tc_bwd128(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat
             for (int kc = 0; kc < 4; ++kc) *reinterpret_cast<uint4*>(smem + S::I3 + (kc * 128 + t) * 16) = pack8<false>(in3 + 8 * kc);
         }
         TNL_STAGE(mma_group<2>(tc, op_kmajor(I34, 128, 0, 0), op_kmajor(W34, 128, 0, 0), make_idesc(128, 128, false, false), false));        // h3
-        epi_store<128, true>(trow, smem + S::H3, t);
+        TNL_EPI_RELU(S::H3);
         TNL_STAGE(mma_group<8>(tc, op_kmajor(H34, 128, 0, 0), op_kmajor(W44, 128, 0, 0), make_idesc(128, 128, false, false), false));        // h4
-        epi_store<128, true>(trow, smem + S::H4, t);          // (overwrites the feature tile: re-fetched below)
+        TNL_EPI_RELU(S::H4);               // (overwrites the feature tile: re-fetched below)
         TNL_STAGE(mma_group<8>(tc, op_kmajor(H44, 128, 0, 0), op_kmajor(W54, 16, 0, 0), make_idesc(128, 16, false, false), false));          // o5
-        {   // d5 = half(g_rgb) * s * (1 - s), rounded to fp16; columns 3..15 zero
+        if (hf == 0) {   // d5 = half(g_rgb) * s * (1 - s), rounded to fp16; columns 3..15 zero
             float o[8];
             tmem_load_row<8>(trow, o);
             float d5[8];
@@ -354,14 +388,14 @@ k_mlp_tc_bwd128(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat
         // ---- input-gradient chain + weight gradients ----
         TNL_STAGE((mma_group<1>(tc, op_kmajor(D54, 128, 0, 0), op_mnmajor(W54, 16, 0, 0), make_idesc(128, 128, false, true), false),         // dh4 = d5 W5
                    mma_group<8>(tmem + TM_W5, op_mnmajor(H44, 128, 0, 0), op_mnmajor(D54, 128, 0, 0), make_idesc(128, 16, true, true), accw)));   // dW5^T += h4^T d5
-        epi_mask_store<128>(trow, smem + S::H4, t);
+        TNL_EPI_MASK(S::H4);
         TNL_STAGE((mma_group<8>(tc, op_kmajor(H44, 128, 0, 0), op_mnmajor(W44, 128, 0, 0), make_idesc(128, 128, false, true), false),        // dh3 = dh4 W4
                    mma_group<8>(tmem + TM_W4, op_mnmajor(H44, 128, 0, 0), op_mnmajor(H34, 128, 0, 0), make_idesc(128, 128, true, true), accw)));  // dW4 += dh4^T h3
-        load_x_async<K1>(smem + S::XR, t, feat, p, v);        // relu(h4) / dh4 / d5 are dead: bring the feature tile back
-        epi_mask_store<128>(trow, smem + S::H3, t);
+        load_x_half_async<K1>(smem + S::XR, t, hf, feat, p, v);   // relu(h4) / dh4 / d5 are dead: bring the feature tile back
+        TNL_EPI_MASK(S::H3);
         TNL_STAGE((mma_group<8>(tc, op_kmajor(H34, 128, 0, 0), op_mnmajor(W34, 128, 0, 16), make_idesc(128, 16, false, true), false),        // d(in3)[:, 16:32]
                    mma_group<8>(tmem + TM_W3, op_mnmajor(H34, 128, 0, 0), op_mnmajor(I34, 128, 0, 0), make_idesc(128, 32, true, true), accw)));   // dW3 += dh3^T in3
-        {   // dh2: column 0 <- g_sigma * exp(clamp(logit, -15, 15)) (trunc_exp backward), columns 1..15 <- d(geo)
+        if (hf == 0) {   // dh2: column 0 <- g_sigma * exp(clamp(logit, -15, 15)) (trunc_exp backward), columns 1..15 <- d(geo)
             float a[16];
             tmem_load_row<16>(trow, a);
             float dh2[16];
@@ -373,37 +407,35 @@ k_mlp_tc_bwd128(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat
         }
         TNL_STAGE((mma_group<1>(tc, op_kmajor(I34, 128, 0, 0), op_mnmajor(W24, 16, 0, 0), make_idesc(128, 128, false, true), false),         // dh1 = dh2 W2
                    mma_group<8>(tmem + TM_W2, op_mnmajor(H14, 128, 0, 0), op_mnmajor(I34, 128, 0, 0), make_idesc(128, 16, true, true), accw)));   // dW2^T += h1^T dh2
-        epi_mask_store<128>(trow, smem + S::H1, t);
+        TNL_EPI_MASK(S::H1);
         cp_async_wait_all();                                  // the feature tile is back
         TNL_STAGE((mma_group<8>(tc, op_kmajor(H14, 128, 0, 0), op_mnmajor(W14, 128, 0, 0), make_idesc(128, K1, false, true), false),         // g_feat = dh1 W1
                    mma_group<8>(tmem + TM_W1, op_mnmajor(H14, 128, 0, 0), op_mnmajor(X4, 128, 0, 0), make_idesc(128, K1, true, true), accw)));    // dW1 += dh1^T feat
         if (it + 1 < my_tiles) {                              // the feature tile has been consumed: prefetch the next one
             const uint32_t pn = (tile + gridDim.x) * 128 + t;
-            load_x_async<K1>(smem + S::XR, t, feat, pn, pn < nvalid);
+            load_x_half_async<K1>(smem + S::XR, t, hf, feat, pn, pn < nvalid);
         }
         {   // (tcgen05.ld is warp-collective: every lane executes it, the stores are predicated)
-            uint4* dst = reinterpret_cast<uint4*>(g_feat + (size_t)p * K1);
-            const bool st = g_feat != nullptr && p < M;
+            float a[KH];
+            tmem_load_row<KH>(trow + hf * KH, a);
+            if (g_feat != nullptr && p < M) {
+                uint4* dst = reinterpret_cast<uint4*>(g_feat + (size_t)p * K1 + hf * KH);
 #pragma unroll
-            for (int c0 = 0; c0 < K1; c0 += 48) {
-                float a[48];
-                tmem_load_row<48>(trow + c0, a);
-                if (st) {
-#pragma unroll
-                    for (int kc = 0; kc < 6; ++kc) dst[c0 / 8 + kc] = v ? pack8<false>(a + 8 * kc) : make_uint4(0u, 0u, 0u, 0u);
-                }
+                for (int kc = 0; kc < KH / 8; ++kc) dst[kc] = v ? pack8<false>(a + 8 * kc) : make_uint4(0u, 0u, 0u, 0u);
             }
         }
         // the next tile's first product is ordered behind these loads by the stage's __syncthreads
     }
 #undef TNL_STAGE
+#undef TNL_EPI_RELU
+#undef TNL_EPI_MASK
     cp_async_wait_all();
     // rows of g_feat past the last processed tile: defined zeros
     if (g_feat) {
         for (uint32_t p = ntiles * 128 + blockIdx.x * 128 + t; p < M; p += gridDim.x * 128) {
-            uint4* dst = reinterpret_cast<uint4*>(g_feat + (size_t)p * K1);
+            uint4* dst = reinterpret_cast<uint4*>(g_feat + (size_t)p * K1 + hf * KH);
 #pragma unroll
-            for (int kc = 0; kc < K1 / 8; ++kc) dst[kc] = make_uint4(0u, 0u, 0u, 0u);
+            for (int kc = 0; kc < KH / 8; ++kc) dst[kc] = make_uint4(0u, 0u, 0u, 0u);
         }
     }
     fence_before_sync();
@@ -411,37 +443,36 @@ k_mlp_tc_bwd128(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat
     fence_after_sync();
     // ---------------- flush the weight gradients (fp32, one atomicAdd per element per CTA): TMEM lane = row ----------------
     if (my_tiles > 0) {
-        const uint32_t tl = tmem + ((warp * 32u) << 16);
         const uint32_t row = t;
+        {
+            float a[KH];
+            tmem_load_row<KH>(tlane + TM_W1 + hf * KH, a);
 #pragma unroll
-        for (int c0 = 0; c0 < K1; c0 += 48) {
-            float a[48];
-            tmem_load_row<48>(tl + TM_W1 + c0, a);
-#pragma unroll
-            for (int k = 0; k < 48; ++k) atomicAdd(gW1 + (size_t)row * K1 + c0 + k, a[k]);
-        }
-#pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 64) {
-            float a[64];
-            tmem_load_row<64>(tl + TM_W4 + c0, a);
-#pragma unroll
-            for (int k = 0; k < 64; ++k) atomicAdd(gW4 + (size_t)row * 128 + c0 + k, a[k]);
+            for (int k = 0; k < KH; ++k) atomicAdd(gW1 + (size_t)row * K1 + hf * KH + k, a[k]);
         }
         {
-            float a[32];
-            tmem_load_row<32>(tl + TM_W3, a);
+            float a[64];
+            tmem_load_row<64>(tlane + TM_W4 + hf * 64u, a);
 #pragma unroll
-            for (int k = 0; k < 31; ++k) atomicAdd(gW3 + (size_t)row * 31 + k, a[k]);
+            for (int k = 0; k < 64; ++k) atomicAdd(gW4 + (size_t)row * 128 + hf * 64 + k, a[k]);
         }
-        {   // transposed accumulators: lane row = input feature k, column = output row n
+        {
             float a[16];
-            tmem_load_row<16>(tl + TM_W2, a);
+            tmem_load_row<16>(tlane + TM_W3 + hf * 16u, a);
 #pragma unroll
-            for (int n = 0; n < 16; ++n) atomicAdd(gW2 + (size_t)n * 128 + row, a[n]);
-            float b[16];
-            tmem_load_row<16>(tl + TM_W5, b);
+            for (int k = 0; k < 16; ++k)
+                if (hf * 16 + k < 31) atomicAdd(gW3 + (size_t)row * 31 + hf * 16 + k, a[k]);
+        }
+        {   // transposed accumulators: lane row = input feature k, column = output row n; half 0 flushes dW2, half 1 dW5
+            float a[16];
+            tmem_load_row<16>(tlane + (hf == 0 ? TM_W2 : TM_W5), a);
+            if (hf == 0) {
 #pragma unroll
-            for (int n = 0; n < 3; ++n) atomicAdd(gW5 + (size_t)n * 128 + row, b[n]);
+                for (int n = 0; n < 16; ++n) atomicAdd(gW2 + (size_t)n * 128 + row, a[n]);
+            } else {
+#pragma unroll
+                for (int n = 0; n < 3; ++n) atomicAdd(gW5 + (size_t)n * 128 + row, a[n]);
+            }
         }
     }
     fence_before_sync();
@@ -483,7 +514,7 @@ static void launch_bwd128(const void* wpk, const void* feat, const float* dirs, 
     using S = TcBwd128Smem<K1>;
     cudaFuncSetAttribute(k_mlp_tc_bwd128<K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL);
     const uint32_t blocks = min(ceil_div(M, 128u), (uint32_t)kNumSM);   // one CTA per SM: it owns all 512 TMEM columns
-    k_mlp_tc_bwd128<K1><<<blocks, 128, S::TOTAL, s>>>(static_cast<const uint8_t*>(wpk), static_cast<const __half*>(feat), dirs, M, n_valid,
+    k_mlp_tc_bwd128<K1><<<blocks, 256, S::TOTAL, s>>>(static_cast<const uint8_t*>(wpk), static_cast<const __half*>(feat), dirs, M, n_valid,
                                                       g_sigma, g_rgb, static_cast<__half*>(g_feat), gW1, gW2, gW3, gW4, gW5);
 }
 
