@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--no-next-rows", action="store_true", help="skip the extras.next_rows measurements (feeder, render loops)")
     ap.add_argument("--occupancy-radius", type=float, default=0.75,
                     help="radius of the occupied ball (SURVEY.md 8d: 0.75 = the metric's scene, 0.4 = the sparse preset that exposes the plane-bound regime)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: gradient exchange by this package's peer-memory kernels (multimem / P2P) or by NCCL (bf16 dirty tiles)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU work for the cpu_baseline leg")
     return ap.parse_args()
@@ -502,7 +504,7 @@ def main():
     C, R, S, hidden = cfg["C"], cfg["R"], cfg["S"], cfg["hidden"]
     net = _make_net(cfg, dev, args.occupancy_radius)
     opt = trainer.default_opt()
-    ts = trainer.TrainStep(net, opt, optimizer=None, world_size=world)
+    ts = trainer.TrainStep(net, opt, optimizer=None, world_size=world, exchange=args.exchange)
     sc = scene.make_scene()
     gen = torch.Generator().manual_seed(1234 + rank)     # each rank draws its own shard of the global batch
     total = args.warmup + args.steps
@@ -594,6 +596,9 @@ def main():
         ts.world_size = 1          # rank-0-only section: no collectives from here on
         if ts.reducer is not None:
             ts.reducer.world_size = 1
+        exchange_note = ts.exchange_note
+        ts.exch = None             # (the peer exchange's cross-rank barriers would wait for ranks that are done)
+        net.encoder.external_grad_buffer = None
         ts.prefetch_planes = False   # per-kernel events must not overlap kernels of two streams
         _lib.profile_start()
         nprof = min(args.steps, 5)
@@ -673,10 +678,10 @@ def main():
             "config": {"workload": f"{args.config}: C={C} R={R} wavelet_levels={S} ({int(round(math.log2(S)))} IDWT levels), hidden={hidden}, "
                                    f"{n_rays} rays/GPU/step, synthetic 800x800 Blender-shaped scene, ball occupancy r={args.occupancy_radius:g}, random-init",
                        "rays_per_gpu": n_rays, "global_rays": n_rays * world,
-                       "parallelism": (f"ray-sharded dp{world} ({args.scaling} scaling), replicated coefficients; plane gradient exchanged as bf16 dirty tiles "
-                                       "(NCCL all-reduce) between the render backward and the IDWT backward" if world > 1 else "single GPU"),
+                       "parallelism": (f"ray-sharded dp{world} ({args.scaling} scaling), replicated coefficients; dirty tiles of the plane gradient + MLP gradients "
+                                       f"all-reduced between the render backward and the IDWT backward: {exchange_note}" if world > 1 else "single GPU"),
                        "timed_region": "get_planes (work-list IDWT over the occupied tiles) + render + loss + backward (+ gradient exchange); optimizer and density-grid refresh excluded (metric definition), see extras",
-                       "launch": ("one CUDA-graph replay per step" if world == 1 else "two CUDA-graph replays per step around the NCCL exchange") if use_graph else "eager Python launches",
+                       "launch": ("one CUDA-graph replay per step" if (world == 1 or "peer memory" in (exchange_note or "")) else "two CUDA-graph replays per step around the NCCL exchange") if use_graph else "eager Python launches",
                        "l2": f"inputs ({P / 1e9:.2f} GB of coefficients/planes per pass) exceed the 126 MB L2; a different ray batch every step"},
             "clocks": clk, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "extras": extras,

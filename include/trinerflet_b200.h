@@ -299,6 +299,20 @@ int tnl_tiles_pack(const float* planes, const int32_t* tile_ids, uint32_t n_tile
 int tnl_tiles_unpack(const void* compact, const int32_t* tile_ids, uint32_t n_tiles, uint32_t R, uint32_t C, uint32_t T,
                      float scale, int bf16, float* planes, tnl_stream_t stream);
 
+/* The same exchange IN PLACE over peer memory, without pack / unpack and in fp32: the plane-gradient buffers [3][R][R][C] of
+ * all ranks are symmetric allocations (identical size, peer-mapped over NVLink; `multicast` != NULL: additionally mapped
+ * through one NVSwitch multicast address).  Tile k of the (replicated) list is reduced by rank k % world:
+ *   multicast != NULL   multimem.ld_reduce.add (sum formed in the switch) -> x scale -> multimem.st (broadcast by the switch);
+ *   multicast == NULL   loads from every peers[r], sum in rank order, stores to every peers[r]  (peers: HOST array of `world`
+ *                       device pointers, each rank's mapping of the same buffer; world <= 8).
+ * tile_ids / count / capacity as tnl_tiles_zero (count read on the device).  The caller brackets the call with cross-rank
+ * barriers.  tnl_flat_allreduce: the same for a flat fp32 buffer (n_floats % 4 == 0; the MLP weight gradients). */
+int tnl_tiles_allreduce(void* multicast, const void* const* peers, const int32_t* tile_ids, const int32_t* count,
+                        uint32_t capacity, uint32_t R, uint32_t C, uint32_t T, uint32_t rank, uint32_t world, float scale,
+                        tnl_stream_t stream);
+int tnl_flat_allreduce(void* multicast, const void* const* peers, uint32_t n_floats, uint32_t rank, uint32_t world,
+                       float scale, tnl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

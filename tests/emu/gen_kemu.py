@@ -109,6 +109,9 @@ def rewrite_ptx(src):
     n += k
     src, k = _LDSM.subn(lambda m: f"tnl_emu::ldmatrix_trans<{m.group('n')}>(r, p);", src)
     n += k
+    # device-only instruction wrappers that come with a host definition: `#ifdef __CUDACC__ <asm> #else <host> #endif`
+    src, k = re.subn(r'#ifdef __CUDACC__\n(?:(?!#else|#endif).)*?asm volatile.*?#else[^\n]*\n(.*?)#endif', r'\1', src, flags=re.S)
+    n += k
     if "asm" in re.sub(r"//.*", "", src):
         raise RuntimeError("inline PTX the emulator does not know")
     return src, n

@@ -777,3 +777,42 @@ def test_march_train_other_bounds_cascades_and_grid_sizes(bound, Hg, dt_gamma, m
     assert _bits_equal(xyzs, x_o) and _bits_equal(deltas, l_o)
 
 
+
+
+# ------------------------------------------------------------------------------------------------ peer-memory gradient exchange
+def test_peer_memory_allreduce_kernels_p2p_variant():
+    """csrc/tiles.cu tnl_tiles_allreduce / tnl_flat_allreduce, peer (non-multicast) variant, on the host build: the `peers` are three
+    ordinary buffers standing in for three ranks' mappings of the symmetric plane-gradient buffer.  After every rank has run its
+    share (tile k is owned by rank k % world) all buffers hold the average on the listed tiles and are untouched elsewhere."""
+    rng = np.random.default_rng(3)
+    world, R, C, T = 3, 128, 16, 32
+    nt = R // T
+    bufs = [rng.standard_normal((3, R, R, C)).astype(np.float32) for _ in range(world)]
+    orig = [b.copy() for b in bufs]
+    ids = np.sort(rng.permutation(3 * nt * nt)[:17]).astype(np.int32)
+    cap = 32
+    lst = np.zeros(cap, np.int32); lst[:17] = ids
+    cnt = np.array([17], np.int32)
+    peers = (ctypes.c_void_p * world)(*[b.ctypes.data for b in bufs])
+    for r in range(world):
+        rc = kemu.lib().tnl_tiles_allreduce(None, peers, kemu.p(lst), kemu.p(cnt), cap, R, C, T, r, world, ctypes.c_float(1.0 / world), None)
+        assert rc == 0
+    mean = sum(orig) / np.float32(world)
+    mask = np.zeros((3, R, R), bool)
+    for i in ids:
+        p, ty, tx = i // (nt * nt), (i // nt) % nt, i % nt
+        mask[p, ty * T:(ty + 1) * T, tx * T:(tx + 1) * T] = True
+    for b, o in zip(bufs, orig):
+        assert np.allclose(b[mask], mean[mask], rtol=1e-6, atol=1e-7)
+        assert np.array_equal(b[~mask], o[~mask])
+    assert np.array_equal(bufs[0][mask], bufs[1][mask]) and np.array_equal(bufs[0][mask], bufs[2][mask])    # bit-identical replicas
+    # flat buffer (the MLP weight gradients), length a multiple of 4 * world
+    flats = [rng.standard_normal(4 * world * 37).astype(np.float32) for _ in range(world)]
+    want = sum(flats) / np.float32(world)
+    fp = (ctypes.c_void_p * world)(*[f.ctypes.data for f in flats])
+    for r in range(world):
+        assert kemu.lib().tnl_flat_allreduce(None, fp, flats[0].size, r, world, ctypes.c_float(1.0 / world), None) == 0
+    for f in flats:
+        assert np.allclose(f, want, rtol=1e-6, atol=1e-7)
+    assert kemu.lib().tnl_flat_allreduce(None, fp, 6, 0, world, ctypes.c_float(1.0), None) == -1        # length % 4
+    assert kemu.lib().tnl_tiles_allreduce(None, None, kemu.p(lst), kemu.p(cnt), cap, R, C, T, 0, world, ctypes.c_float(1.0), None) == -1

@@ -65,6 +65,8 @@ SIGNATURES = {
     "tnl_mark_dirty_tiles": (_int, [_vp, _u32, _u32, _f32, _u32, _u32, _u32, _vp, _vp]),
     "tnl_tiles_pack": (_int, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _int, _vp]),
     "tnl_tiles_unpack": (_int, [_vp, _vp, _u32, _u32, _u32, _u32, _f32, _int, _vp, _vp]),
+    "tnl_tiles_allreduce": (_int, [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _u32, _u32, _f32, _vp]),
+    "tnl_flat_allreduce": (_int, [_vp, _vp, _u32, _u32, _u32, _f32, _vp]),
     "tnl_grad_nonfinite": (_int, [_vp, ctypes.c_uint64, _vp, _vp]),
     "tnl_adam_prepare": (_int, [_vp, _vp, _f32, _f32, _vp]),
     "tnl_adam_step": (_int, [_vp, _vp, _vp, _vp, ctypes.c_uint64, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _f32, _vp]),

@@ -203,10 +203,12 @@ k_mlp_tc_fwd(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat, c
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward.  CTA = 9 warps: two warpgroups, each working on its own 128-point sub-tile (own shared-memory tiles, own
-// chain accumulator in TMEM), and one MMA-issuer warp.  A warpgroup hands a stage to the issuer through an mbarrier
-// (`ready`, 128 arrivals), the issuer's tcgen05.commit arrives on the warpgroup's `done` barrier.  The issuer serves
-// the warpgroups alternately, so the tensor core works on one sub-tile while the other warpgroup runs its epilogue;
+// backward.  CTA = 17 warps: two 128-point sub-tiles in flight (own shared-memory tiles, own chain accumulator in TMEM), each
+// served by TWO warpgroups that split the accumulator columns of every epilogue (thread (t, hf): point t <-> TMEM lane t,
+// column half hf; warps w and w + 8 share a lane quarter), and one MMA-issuer warp.  The epilogues (tcgen05.ld -> convert ->
+// st.shared) are latency-bound, so twice the threads per tile nearly halves them.  A sub-tile's 256 threads hand a stage to
+// the issuer through an mbarrier (`ready`, 256 arrivals), the issuer's tcgen05.commit arrives on the sub-tile's `done`
+// barrier.  The issuer serves the sub-tiles alternately, so the tensor core works on one while the other runs its epilogue;
 // being the only issuer it also keeps the accumulation order of the shared weight-gradient accumulators defined.
 // ------------------------------------------------------------------------------------------------
 template <int K1>
@@ -235,7 +237,7 @@ __device__ __forceinline__ bool m64_row_of_lane(uint32_t warp, uint32_t lane, ui
 constexpr int kBwdStages = 10;
 
 template <int K1>
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(544, 1)
 k_mlp_tc_bwd(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat, const float* __restrict__ dirs, uint32_t M,
              const int32_t* __restrict__ n_valid_ptr, const float* __restrict__ g_sigma, const float* __restrict__ g_rgb,
              __half* __restrict__ g_feat, float* __restrict__ gW1, float* __restrict__ gW2, float* __restrict__ gW3,
@@ -252,13 +254,13 @@ k_mlp_tc_bwd(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat, c
     uint64_t* ready = reinterpret_cast<uint64_t*>(smem + S::BAR);
     uint64_t* done = reinterpret_cast<uint64_t*>(smem + S::BAR + 16);
     uint32_t* tslot = reinterpret_cast<uint32_t*>(smem + S::BAR + 32);
-    for (uint32_t i = tid * 16; i < W::END; i += 288 * 16) *reinterpret_cast<uint4*>(smem + i) = __ldg(reinterpret_cast<const uint4*>(wpk + i));
+    for (uint32_t i = tid * 16; i < W::END; i += 544 * 16) *reinterpret_cast<uint4*>(smem + i) = __ldg(reinterpret_cast<const uint4*>(wpk + i));
     if (tid == 0) {
-        mbar_init(&ready[0], 128); mbar_init(&ready[1], 128);
+        mbar_init(&ready[0], 256); mbar_init(&ready[1], 256);
         mbar_init(&done[0], 1); mbar_init(&done[1], 1);
         mbar_init_fence();
     }
-    if (warp == 8) tmem_alloc(tslot, TM_COLS);
+    if (warp == 16) tmem_alloc(tslot, TM_COLS);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -273,7 +275,7 @@ k_mlp_tc_bwd(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat, c
     const bool profiling = dbg != nullptr && blockIdx.x == 0;
     if (profiling && tid < 64) sdbg[tid] = 0ull;
     if (profiling) __syncthreads();
-    if (warp == 8) {
+    if (warp == 16) {
         // ============================== MMA issuer (whole warp, converged; one elected lane issues) ==============================
         const uint32_t sb4 = smem_u32(smem) >> 4;
         const uint32_t W14 = sb4 + (W::W1 >> 4), W24 = sb4 + (W::W2 >> 4), W34 = sb4 + (W::W3 >> 4), W44 = sb4 + (W::W4 >> 4),
@@ -330,7 +332,9 @@ k_mlp_tc_bwd(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat, c
         }
     } else {
         // ============================== warpgroups ==============================
-        const uint32_t g = warp >> 2, t = tid & 127;
+        const uint32_t g = (warp >> 2) & 1u, hf = warp >> 3, t = tid & 127;     // sub-tile, column half, point
+        constexpr int XH = K1 / 16;                                             // feature-row chunks per half
+        constexpr int KH = K1 / 2;                                              // g_feat columns per half
         uint8_t* sub = smem + S::SUB0 + g * S::SUB;
         const uint32_t trow = tmem + (((warp & 3u) * 32u) << 16) + TM_C + g * CW;
         uint32_t phase = 0;
@@ -346,22 +350,39 @@ k_mlp_tc_bwd(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat, c
     mbar_wait(&done[g], phase); phase ^= 1;          \
     fence_after_sync();                              \
     if (prof) { const long long c = clock64(); sdbg[stg] += (unsigned long long)(c - tprev); tprev = c; stg = (stg + 1) % kBwdStages; }
+        // this thread's 32 of the 64 accumulator columns -> fp16 row chunks of a tile(128, 64); in place masked by the ReLU output
+#define TNL_EPI_RELU(TILE)                                                                                              \
+    {                                                                                                                   \
+        float a[32];                                                                                                    \
+        tmem_load_row<32>(trow + hf * 32u, a);                                                                          \
+        _Pragma("unroll") for (int kc = 0; kc < 4; ++kc)                                                                \
+            *reinterpret_cast<uint4*>(sub + (TILE) + ((hf * 4u + kc) * 128u + t) * 16u) = pack8<true>(a + 8 * kc);     \
+    }
+#define TNL_EPI_MASK(TILE)                                                                                              \
+    {                                                                                                                   \
+        float a[32];                                                                                                    \
+        tmem_load_row<32>(trow + hf * 32u, a);                                                                          \
+        _Pragma("unroll") for (int kc = 0; kc < 4; ++kc) {                                                              \
+            uint4* q = reinterpret_cast<uint4*>(sub + (TILE) + ((hf * 4u + kc) * 128u + t) * 16u);                      \
+            *q = mask8(pack8<false>(a + 8 * kc), *q);                                                                   \
+        }                                                                                                               \
+    }
         // first tile's feature row
-        uint4 x[K1 / 8];
+        uint4 x[XH];
         {
             const uint32_t p0 = (2 * blockIdx.x + g) * 128 + t;
-            const uint4* src = reinterpret_cast<const uint4*>(feat + (size_t)p0 * K1);
+            const uint4* src = reinterpret_cast<const uint4*>(feat + (size_t)p0 * K1) + hf * XH;
 #pragma unroll
-            for (int kc = 0; kc < K1 / 8; ++kc) x[kc] = (my_pairs > 0 && p0 < nvalid) ? __ldg(src + kc) : make_uint4(0u, 0u, 0u, 0u);
+            for (int kc = 0; kc < XH; ++kc) x[kc] = (my_pairs > 0 && p0 < nvalid) ? __ldg(src + kc) : make_uint4(0u, 0u, 0u, 0u);
         }
         for (uint32_t it = 0; it < my_pairs; ++it) {
             const uint32_t tile = 2 * (blockIdx.x + it * gridDim.x) + g;
             const uint32_t p = tile * 128 + t;
             const bool v = p < nvalid;
 #pragma unroll
-            for (int kc = 0; kc < K1 / 8; ++kc) *reinterpret_cast<uint4*>(sub + S::X + (kc * 128 + t) * 16) = x[kc];
+            for (int kc = 0; kc < XH; ++kc) *reinterpret_cast<uint4*>(sub + S::X + ((hf * XH + kc) * 128 + t) * 16) = x[kc];
             float d[3] = {0.f, 0.f, 0.f}, gr[3] = {0.f, 0.f, 0.f}, gs = 0.f;
-            if (v) {
+            if (v && hf == 0) {            // (the 16-column stages are half 0's)
 #pragma unroll
                 for (int j = 0; j < 3; ++j) { d[j] = __ldg(dirs + 3 * (size_t)p + j); gr[j] = __ldg(g_rgb + 3 * (size_t)p + j); }
                 gs = __ldg(g_sigma + p);
@@ -369,20 +390,15 @@ k_mlp_tc_bwd(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat, c
             TNL_HANDOFF();   // stage 0
             {   // prefetch the next tile's feature row; it is consumed at the top of the next iteration
                 const uint32_t pn = (2 * (blockIdx.x + (it + 1) * gridDim.x) + g) * 128 + t;
-                const uint4* src = reinterpret_cast<const uint4*>(feat + (size_t)pn * K1);
+                const uint4* src = reinterpret_cast<const uint4*>(feat + (size_t)pn * K1) + hf * XH;
                 const bool vn = (it + 1 < my_pairs) && pn < nvalid;
 #pragma unroll
-                for (int kc = 0; kc < K1 / 8; ++kc) x[kc] = vn ? __ldg(src + kc) : make_uint4(0u, 0u, 0u, 0u);
+                for (int kc = 0; kc < XH; ++kc) x[kc] = vn ? __ldg(src + kc) : make_uint4(0u, 0u, 0u, 0u);
             }
-            {
-                float a[64];
-                tmem_load_row<64>(trow, a);
-#pragma unroll
-                for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(sub + S::H1 + (kc * 128 + t) * 16) = pack8<true>(a + 8 * kc);
-            }
+            TNL_EPI_RELU(S::H1);
             TNL_HANDOFF();   // stage 1
-            float logit;
-            {
+            float logit = 0.f;
+            if (hf == 0) {
                 float h2[16];
                 tmem_load_row<16>(trow, h2);
 #pragma unroll
@@ -402,21 +418,11 @@ k_mlp_tc_bwd(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat, c
                 for (int kc = 0; kc < 4; ++kc) *reinterpret_cast<uint4*>(sub + S::I3 + (kc * 128 + t) * 16) = pack8<false>(in3 + 8 * kc);
             }
             TNL_HANDOFF();   // stage 2
-            {
-                float a[64];
-                tmem_load_row<64>(trow, a);
-#pragma unroll
-                for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(sub + S::H3 + (kc * 128 + t) * 16) = pack8<true>(a + 8 * kc);
-            }
+            TNL_EPI_RELU(S::H3);
             TNL_HANDOFF();   // stage 3
-            {
-                float a[64];
-                tmem_load_row<64>(trow, a);
-#pragma unroll
-                for (int kc = 0; kc < 8; ++kc) *reinterpret_cast<uint4*>(sub + S::H4 + (kc * 128 + t) * 16) = pack8<true>(a + 8 * kc);
-            }
+            TNL_EPI_RELU(S::H4);
             TNL_HANDOFF();   // stage 4
-            {   // d5 = half(g_rgb) * s * (1 - s), rounded to fp16; columns 3..15 zero
+            if (hf == 0) {   // d5 = half(g_rgb) * s * (1 - s), rounded to fp16; columns 3..15 zero
                 float o[8];
                 tmem_load_row<8>(trow, o);
                 float d5[8];
@@ -431,27 +437,11 @@ k_mlp_tc_bwd(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat, c
                 *reinterpret_cast<uint4*>(sub + S::D5 + (1 * 128 + t) * 16) = make_uint4(0u, 0u, 0u, 0u);
             }
             TNL_HANDOFF();   // stage 5
-            {
-                float a[64];
-                tmem_load_row<64>(trow, a);
-#pragma unroll
-                for (int kc = 0; kc < 8; ++kc) {
-                    uint4* q = reinterpret_cast<uint4*>(sub + S::H4 + (kc * 128 + t) * 16);
-                    *q = mask8(pack8<false>(a + 8 * kc), *q);
-                }
-            }
+            TNL_EPI_MASK(S::H4);
             TNL_HANDOFF();   // stage 6
-            {
-                float a[64];
-                tmem_load_row<64>(trow, a);
-#pragma unroll
-                for (int kc = 0; kc < 8; ++kc) {
-                    uint4* q = reinterpret_cast<uint4*>(sub + S::H3 + (kc * 128 + t) * 16);
-                    *q = mask8(pack8<false>(a + 8 * kc), *q);
-                }
-            }
+            TNL_EPI_MASK(S::H3);
             TNL_HANDOFF();   // stage 7
-            {   // dh2: column 0 <- g_sigma * exp(clamp(logit, -15, 15)) (trunc_exp backward), columns 1..15 <- d(geo)
+            if (hf == 0) {   // dh2: column 0 <- g_sigma * exp(clamp(logit, -15, 15)) (trunc_exp backward), columns 1..15 <- d(geo)
                 float a[16];
                 tmem_load_row<16>(trow, a);
                 float dh2[16];
@@ -462,28 +452,22 @@ k_mlp_tc_bwd(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat, c
                 *reinterpret_cast<uint4*>(sub + S::I3 + (1 * 128 + t) * 16) = pack8<false>(dh2 + 8);
             }
             TNL_HANDOFF();   // stage 8
-            {
-                float a[64];
-                tmem_load_row<64>(trow, a);
-#pragma unroll
-                for (int kc = 0; kc < 8; ++kc) {
-                    uint4* q = reinterpret_cast<uint4*>(sub + S::H1 + (kc * 128 + t) * 16);
-                    *q = mask8(pack8<false>(a + 8 * kc), *q);
-                }
-            }
+            TNL_EPI_MASK(S::H1);
             TNL_HANDOFF();   // stage 9
             {
-                float a[K1];
-                tmem_load_row<K1>(trow, a);
+                float a[KH];
+                tmem_load_row<KH>(trow + hf * KH, a);
                 if (g_feat && p < M) {
-                    uint4* dst = reinterpret_cast<uint4*>(g_feat + (size_t)p * K1);
+                    uint4* dst = reinterpret_cast<uint4*>(g_feat + (size_t)p * K1 + hf * KH);
 #pragma unroll
-                    for (int kc = 0; kc < K1 / 8; ++kc) dst[kc] = v ? pack8<false>(a + 8 * kc) : make_uint4(0u, 0u, 0u, 0u);
+                    for (int kc = 0; kc < KH / 8; ++kc) dst[kc] = v ? pack8<false>(a + 8 * kc) : make_uint4(0u, 0u, 0u, 0u);
                 }
             }
             // the next sub-tile's stage-0 hand-off is ordered behind these loads, so the issuer cannot overwrite the accumulator early
         }
 #undef TNL_HANDOFF
+#undef TNL_EPI_RELU
+#undef TNL_EPI_MASK
     }
     // every product has completed: each warpgroup waited on the commit that followed its last one
     fence_before_sync();
@@ -495,19 +479,21 @@ k_mlp_tc_bwd(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat, c
         const uint32_t tl = tmem + ((warp * 32u) << 16);
         uint32_t row;
         const bool have = m64_row_of_lane(warp, lane, row);
-        {
-            float a[K1];
-            tmem_load_row<K1>(tl + TM_W1, a);
+#pragma unroll 1
+        for (int c0 = 0; c0 < K1; c0 += 16) {
+            float a[16];
+            tmem_load_row<16>(tl + TM_W1 + c0, a);
             if (have)
 #pragma unroll
-                for (int k = 0; k < K1; ++k) atomicAdd(gW1 + (size_t)row * K1 + k, a[k]);
+                for (int k = 0; k < 16; ++k) atomicAdd(gW1 + (size_t)row * K1 + c0 + k, a[k]);
         }
-        {
-            float a[64];
-            tmem_load_row<64>(tl + TM_W4, a);
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+            float a[16];
+            tmem_load_row<16>(tl + TM_W4 + c0, a);
             if (have)
 #pragma unroll
-                for (int k = 0; k < 64; ++k) atomicAdd(gW4 + (size_t)row * 64 + k, a[k]);
+                for (int k = 0; k < 16; ++k) atomicAdd(gW4 + (size_t)row * 64 + c0 + k, a[k]);
         }
         {
             float a[32];
@@ -531,7 +517,7 @@ k_mlp_tc_bwd(const uint8_t* __restrict__ wpk, const __half* __restrict__ feat, c
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 8) tmem_free(tmem, TM_COLS);
+    if (warp == 16) tmem_free(tmem, TM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -705,7 +691,7 @@ static void launch_bwd(const void* wpk, const void* feat, const float* dirs, uin
     using S = TcBwdSmem<K1>;
     cudaFuncSetAttribute(k_mlp_tc_bwd<K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::TOTAL);
     const uint32_t blocks = min(ceil_div(M, 256u), (uint32_t)kNumSM);   // one CTA per SM: it owns all 512 TMEM columns
-    k_mlp_tc_bwd<K1><<<blocks, 288, S::TOTAL, s>>>(static_cast<const uint8_t*>(wpk), static_cast<const __half*>(feat), dirs, M, n_valid,
+    k_mlp_tc_bwd<K1><<<blocks, 544, S::TOTAL, s>>>(static_cast<const uint8_t*>(wpk), static_cast<const __half*>(feat), dirs, M, n_valid,
                                                    g_sigma, g_rgb, static_cast<__half*>(g_feat), gW1, gW2, gW3, gW4, gW5, g_tc_dbg);
 }
 

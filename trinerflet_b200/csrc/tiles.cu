@@ -109,6 +109,92 @@ k_tiles_zero(float* __restrict__ planes, const int32_t* __restrict__ tile_ids, c
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// All-reduce of the dirty tiles IN PLACE over NVLink / NVSwitch peer memory (no pack / unpack, exact fp32 sums).
+// The plane-gradient buffer of every rank lives in symmetric memory (same size on every rank, peer-mapped; with NVLS also
+// mapped through one multicast address).  Tile k of the (replicated) dirty list is reduced by rank k % world:
+//   MC   multimem.ld_reduce.add.v4.f32 -- the switch reads the 16 bytes from every rank and returns their sum --, scale by
+//        1 / world, multimem.st.v4.f32 -- the switch writes the result into every rank's buffer.  Per rank and direction
+//        1 / world of the dirty bytes cross the link;
+//   P2P  (no multicast object): ld.global from each peer's mapping, sum in rank order, st.global to each peer's mapping.
+// Callers bracket the launch with cross-rank barriers (every rank's scatter done before / every store landed after).
+// ------------------------------------------------------------------------------------------------
+struct PeerPtrs {
+    float* p[8];
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float4 mc_ld_reduce_add(const float* mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st(float* mc, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 peer_ld(const float* p) {
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void peer_st(float* p, float4 v) {
+    asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+#else   // host build of the kernels (tests/emu): peers are ordinary buffers; there is no multicast object
+inline float4 mc_ld_reduce_add(const float*) { abort(); }
+inline void mc_st(float*, float4) { abort(); }
+inline float4 peer_ld(const float* p) { return *reinterpret_cast<const float4*>(p); }
+inline void peer_st(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+#endif
+
+template <bool MC>
+__device__ __forceinline__ void allreduce_chunk(const PeerPtrs& peers, float* mc, size_t off, int world, float scale) {
+    float4 v;
+    if (MC) {
+        v = mc_ld_reduce_add(mc + off);
+    } else {
+        v = peer_ld(peers.p[0] + off);
+        for (int r = 1; r < world; ++r) {
+            const float4 u = peer_ld(peers.p[r] + off);
+            v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+        }
+    }
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    if (MC) mc_st(mc + off, v);
+    else
+        for (int r = 0; r < world; ++r) peer_st(peers.p[r] + off, v);
+}
+
+// planes [3][R][R][C] (symmetric); grid (capacity of the tile list, row groups); the list length is read on the device
+template <bool MC>
+__global__ void __launch_bounds__(256)
+k_tiles_allreduce(PeerPtrs peers, float* mc, const int32_t* __restrict__ tile_ids, const int32_t* __restrict__ count, int R, int C, int T,
+                  int rank, int world, float scale) {
+    const int tile = blockIdx.x;
+    if (tile >= __ldg(count) || tile % world != rank) return;
+    const int id = __ldg(tile_ids + tile);
+    const int nt = R / T;
+    const int p = id / (nt * nt), ty = (id / nt) % nt, tx = id % nt;
+    const int n4 = T * C / 4;
+    const int rows_per_cta = (T + gridDim.y - 1) / gridDim.y;
+    const int row_end = min(T, (int)(blockIdx.y + 1) * rows_per_cta);
+    for (int row = blockIdx.y * rows_per_cta; row < row_end; ++row) {
+        const size_t base = (((size_t)p * R + (size_t)ty * T + row) * R + (size_t)tx * T) * C;
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) allreduce_chunk<MC>(peers, mc, base + 4 * (size_t)i, world, scale);
+    }
+}
+
+// a flat fp32 buffer of n4 16-byte chunks (the MLP weight gradients): rank r reduces the r-th contiguous share
+template <bool MC>
+__global__ void __launch_bounds__(256)
+k_flat_allreduce(PeerPtrs peers, float* mc, uint32_t n4, int rank, int world, float scale) {
+    const uint32_t per = (n4 + world - 1) / world;
+    const uint32_t lo = rank * per, hi = min(n4, lo + per);
+    for (uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x)
+        allreduce_chunk<MC>(peers, mc, 4 * (size_t)i, world, scale);
+}
+
 }  // namespace tnl
 
 using namespace tnl;
@@ -156,6 +242,43 @@ int tnl_tiles_unpack(const void* compact, const int32_t* tile_ids, uint32_t n_ti
     if (bf16) k_tiles_copy<false, true><<<dim3(n_tiles, 4), 256, 0, s>>>(planes, const_cast<void*>(compact), tile_ids, (int)R, (int)C, (int)T, scale);
     else k_tiles_copy<false, false><<<dim3(n_tiles, 4), 256, 0, s>>>(planes, const_cast<void*>(compact), tile_ids, (int)R, (int)C, (int)T, scale);
     return finish_launch("tiles_unpack");
+}
+
+static bool fill_peers(PeerPtrs& pp, const void* const* peers, uint32_t world) {
+    if (world < 1 || world > 8) return false;
+    for (uint32_t r = 0; r < 8; ++r) pp.p[r] = r < world && peers ? static_cast<float*>(const_cast<void*>(peers[r])) : nullptr;
+    return true;
+}
+
+int tnl_tiles_allreduce(void* multicast, const void* const* peers, const int32_t* tile_ids, const int32_t* count, uint32_t capacity,
+                        uint32_t R, uint32_t C, uint32_t T, uint32_t rank, uint32_t world, float scale, tnl_stream_t stream) {
+    if (capacity == 0) return 0;
+    TNL_ARG_CHECK(tile_ids && count && (multicast || peers), "null pointer");
+    TNL_ARG_CHECK(R % T == 0 && (T * C) % 4 == 0 && rank < world, "bad tile geometry / rank");
+    PeerPtrs pp;
+    TNL_ARG_CHECK(fill_peers(pp, peers, world), "world size must be 1..8 (one NVSwitch domain)");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (multicast)
+        k_tiles_allreduce<true><<<dim3(capacity, 4), 256, 0, s>>>(pp, static_cast<float*>(multicast), tile_ids, count, (int)R, (int)C, (int)T,
+                                                               (int)rank, (int)world, scale);
+    else
+        k_tiles_allreduce<false><<<dim3(capacity, 4), 256, 0, s>>>(pp, nullptr, tile_ids, count, (int)R, (int)C, (int)T, (int)rank, (int)world,
+                                                                scale);
+    return finish_launch("tiles_allreduce");
+}
+
+int tnl_flat_allreduce(void* multicast, const void* const* peers, uint32_t n_floats, uint32_t rank, uint32_t world, float scale,
+                       tnl_stream_t stream) {
+    if (n_floats == 0) return 0;
+    TNL_ARG_CHECK((multicast || peers) && n_floats % 4 == 0 && rank < world, "bad argument (the buffer length must be a multiple of 4 floats)");
+    PeerPtrs pp;
+    TNL_ARG_CHECK(fill_peers(pp, peers, world), "world size must be 1..8 (one NVSwitch domain)");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const uint32_t n4 = n_floats / 4;
+    const uint32_t blocks = min(ceil_div(ceil_div(n4, world), 256u), (uint32_t)kNumSM);
+    if (multicast) k_flat_allreduce<true><<<blocks, 256, 0, s>>>(pp, static_cast<float*>(multicast), n4, (int)rank, (int)world, scale);
+    else k_flat_allreduce<false><<<blocks, 256, 0, s>>>(pp, nullptr, n4, (int)rank, (int)world, scale);
+    return finish_launch("flat_allreduce");
 }
 
 }  // extern "C"

@@ -101,6 +101,16 @@ class PlaneGradReducer:
             start += int(cnt)
         self.compact = torch.empty(max(self.n_tiles, 1) * T * T * C, dtype=self.transport, device=flags.device)
         self.fraction = self.n_tiles / float(3 * nt * nt)
+        # the same list with its length on the device (grids sized by the capacity): what kernels inside a captured CUDA graph read,
+        # rewritten in place on refresh; `list_version` moves only when the buffer had to grow (graphs must then be re-captured)
+        cap = getattr(self, "list_cap", 0)
+        if self.n_tiles > cap:
+            self.list_cap = max(64, 2 * self.n_tiles)
+            self.list_ids = torch.zeros(self.list_cap, dtype=torch.int32, device=flags.device)
+            self.list_count = torch.zeros(1, dtype=torch.int32, device=flags.device)
+            self.list_version = getattr(self, "list_version", 0) + 1
+        self.list_ids[:self.n_tiles].copy_(self.tile_ids)
+        self.list_count.fill_(self.n_tiles)
         return self
 
     def reduce_(self, g_planes):
@@ -156,6 +166,90 @@ def _reduce_plane(self, g_planes, plane):
 
 
 PlaneGradReducer.reduce_plane_ = _reduce_plane
+
+
+class PeerGradExchange:
+    """The gradient exchange of a training step over NVLink / NVSwitch peer memory, by this package's own kernels
+    (csrc/tiles.cu: tnl_tiles_allreduce, tnl_flat_allreduce) instead of NCCL:
+
+      * the plane-gradient buffer [3,R,R,C] fp32 every rank's sampling backward scatters into, and a flat buffer for the MLP weight
+        gradients, are SYMMETRIC allocations (torch.distributed._symmetric_memory: same size on every rank, peer-mapped; on an
+        NVSwitch fabric also mapped through one multicast address);
+      * after the scatter: cross-rank barrier, then ONE kernel per buffer reduces the dirty tiles in place -- rank r owns tiles
+        r, r + world, ...: `multimem.ld_reduce.add` lets the switch sum the 16 bytes of all ranks, the result is scaled by
+        1 / world and `multimem.st` broadcasts it into every rank's buffer (without a multicast object: peer loads / peer stores)
+        -- then a second barrier; the IDWT backward reads the averaged gradient where the scatter left it.
+    No pack / unpack, no bf16 rounding (exact fp32 sums), 1 / world of the dirty bytes per rank and direction on the wire, and
+    every launch is a plain kernel on the step's stream, so the whole multi-GPU step is captured in ONE CUDA graph."""
+
+    def __init__(self, model, world_size, reducer, group=None):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm_mem
+        enc = model.encoder
+        self.R, self.C, self.T = enc.plane_resolution, enc.number_of_features, reducer.tile
+        self.world, self.rank = world_size, dist.get_rank()
+        self.reducer = reducer
+        dev = enc.planes_features.device
+        group = group or dist.group.WORLD
+        self.params = [p for n, p in model.named_parameters() if not n.startswith("encoder.")]
+        n_mlp = sum(p.numel() for p in self.params)
+        self.n_mlp = n_mlp
+        self.n_mlp_pad = -(-n_mlp // (4 * world_size)) * 4 * world_size
+        self._flat_planes = symm_mem.empty(3 * self.R * self.R * self.C, dtype=torch.float32, device=dev)
+        self._hdl_p = symm_mem.rendezvous(self._flat_planes, group)
+        self._flat_mlp = symm_mem.empty(self.n_mlp_pad, dtype=torch.float32, device=dev)
+        self._hdl_m = symm_mem.rendezvous(self._flat_mlp, group)
+        self._flat_mlp.zero_()
+        self.g_planes = self._flat_planes.view(3, self.R, self.R, self.C).permute(0, 3, 1, 2)      # logical [3,C,R,R], channels-last
+        self._arr_p, self._mc_p = self._pointers(self._flat_planes, self._hdl_p, ctypes)
+        self._arr_m, self._mc_m = self._pointers(self._flat_mlp, self._hdl_m, ctypes)
+        self.mode = self._self_test()
+
+    def _pointers(self, t, hdl, ctypes):
+        """(host array of every rank's mapping of `t`, multicast address of `t` or None)"""
+        delta = t.data_ptr() - int(hdl.buffer_ptrs[self.rank])       # offset of the tensor inside the symmetric block
+        arr = (ctypes.c_void_p * self.world)(*[int(p) + delta for p in hdl.buffer_ptrs])
+        mc = int(hdl.multicast_ptr) if getattr(hdl, "multicast_ptr", 0) else 0
+        return arr, (ctypes.c_void_p(mc + delta) if mc else None)
+
+    def _flat(self, mc, n, scale=1.0):
+        from ._lib import call, stream
+        call("tnl_flat_allreduce", self._mc_m if mc else None, self._arr_m, n, self.rank, self.world, float(scale), stream())
+
+    def _self_test(self):
+        """One known-answer all-reduce through each transport (every rank contributes rank + 1): 'multimem', else 'p2p'."""
+        n = 4 * self.world
+        want = float(self.world * (self.world + 1) // 2)
+        for mode in (("multimem", "p2p") if self._mc_m is not None else ("p2p",)):
+            self._flat_mlp[:n].fill_(float(self.rank + 1))
+            self._hdl_m.barrier(channel=0)
+            self._flat(mode == "multimem", n)
+            self._hdl_m.barrier(channel=1)
+            ok = torch.tensor([float(bool((self._flat_mlp[:n] == want).all()))], device=self._flat_mlp.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            self._flat_mlp[:n].zero_()
+            if float(ok) == 1.0:
+                return mode
+        raise RuntimeError("PeerGradExchange: neither the multicast nor the peer-mapped all-reduce passed its self-test")
+
+    def exchange_(self):
+        """in place, on the current stream: g_planes (dirty tiles) and the MLP gradients <- average over the ranks"""
+        from ._lib import call, ptr, stream
+        r = self.reducer
+        grads = [p.grad for p in self.params]
+        if all(g is not None for g in grads):
+            torch.cat([_dense_view(g).reshape(-1) for g in grads], out=self._flat_mlp[:self.n_mlp])
+        mc = self.mode == "multimem"
+        self._hdl_p.barrier(channel=0)
+        call("tnl_tiles_allreduce", self._mc_p if mc else None, self._arr_p, ptr(r.list_ids), ptr(r.list_count), r.list_cap, self.R, self.C,
+             self.T, self.rank, self.world, 1.0 / self.world, stream())
+        self._flat(mc, self.n_mlp_pad, 1.0 / self.world)
+        self._hdl_p.barrier(channel=1)
+        if all(g is not None for g in grads):
+            off = 0
+            for p in self.params:
+                p.grad = self._flat_mlp[off:off + p.numel()].view_as(p)
+                off += p.numel()
 
 
 def allreduce_small(params, world_size):

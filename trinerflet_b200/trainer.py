@@ -40,7 +40,7 @@ def wavelet_regulariser(encoder, lam, fused=True):
 
 class TrainStep:
     def __init__(self, model, opt=None, optimizer=None, world_size=1, sparse_allreduce=True, check_sparse=False,
-                 transport=torch.bfloat16):
+                 transport=torch.bfloat16, exchange="auto"):
         self.model = model
         self.opt = opt or default_opt()
         self.optimizer = optimizer
@@ -50,6 +50,22 @@ class TrainStep:
         self.criterion = torch.nn.MSELoss(reduction='none')
         # N > 1: the plane gradient is exchanged between the render backward and the IDWT backward, dirty tiles only
         self.reducer = parallel.PlaneGradReducer(model, world_size, check=check_sparse, transport=transport) if (world_size > 1 and sparse_allreduce) else None
+        # exchange: "peer" = this package's own all-reduce kernels over NVLink peer / NVSwitch multicast memory, in place and in fp32
+        # (parallel.PeerGradExchange); "nccl" = pack -> NCCL all-reduce of the bf16 dirty tiles -> unpack; "auto" = peer where the
+        # symmetric-memory rendezvous and its known-answer self-test succeed on every rank, else nccl (with a note on rank 0)
+        self.exch = None
+        self.exchange_note = "nccl (pack / NCCL all-reduce of bf16 dirty tiles / unpack)" if self.reducer is not None else None
+        if self.reducer is not None and exchange in ("auto", "peer") and not check_sparse and next(model.parameters()).is_cuda:
+            try:
+                self.reducer.refresh()
+                self._reducer_gen = getattr(model, "bitfield_generation", 0)
+                self.exch = parallel.PeerGradExchange(model, world_size, self.reducer)
+                model.encoder.external_grad_buffer = self.exch.g_planes
+                self.exchange_note = f"peer memory, {self.exch.mode} (own kernels: in place, fp32, one CUDA graph per step)"
+            except Exception as ex:  # noqa: BLE001
+                if exchange == "peer":
+                    raise
+                self.exchange_note += f" [peer exchange unavailable: {type(ex).__name__}: {str(ex)[:120]}]"
         # eager-mode option: per-plane exchange on a side stream overlapped with the per-plane IDWT backward.  Measured on
         # 8 x B200 it does not beat the sequential exchange (NCCL and the IDWT kernels contend for SMs / HBM), so it is off.
         self.pipelined_tail = False
@@ -60,7 +76,8 @@ class TrainStep:
         # (idwt_plan.py); steps that refresh the density grid query the field everywhere and stay dense
         self.sparse_idwt = True
         self._plan = None
-        self._plan_gen = self._reducer_gen = None     # model.bitfield_generation the plan / the dirty-tile list were built from
+        self._plan_gen = None     # model.bitfield_generation the plan / the dirty-tile list were built from
+        self._reducer_gen = getattr(self, "_reducer_gen", None)
         self.plan_on_any_device = False   # test hook: the CPU suite runs the work-list step over the host build of the kernels
         self._graphs = None
 
@@ -174,7 +191,7 @@ class TrainStep:
                     torch.cuda.current_stream().wait_stream(self._side)
                 if self._split is not None and have_reg:
                     reg = enc.wavelet_l1(lam, abs_sums)
-                if not capturing:
+                if not capturing or self.exch is not None:    # (the peer exchange is plain kernels: it is captured with the step)
                     self._exchange_and_finish()
             loss = loss.detach() + (reg.detach() if reg is not None else 0.0)
         self.global_step += 1
@@ -209,7 +226,19 @@ class TrainStep:
         return self._plan
 
     def _exchange(self):
+        if self.exch is not None:
+            planes, leaf, reg = self._cut
+            if leaf.grad is not None:       # dense step (grid refresh): the scatter went into an ordinary buffer
+                self.exch.g_planes.copy_(leaf.grad)
+                leaf.grad = None
+            self.exch.exchange_()
+            return
         self._exchange_finish(self._exchange_start())
+
+    def _plane_grad(self):
+        """the plane gradient of this step: leaf.grad, or the persistent symmetric buffer the scatter wrote (peer exchange)"""
+        planes, leaf, reg = self._cut
+        return leaf.grad if (self.exch is None or leaf.grad is not None) else self.exch.g_planes
 
     def _exchange_start(self):
         """pack the dirty tiles of the plane gradient and start their all-reduce (asynchronous: NCCL's own stream)."""
@@ -232,15 +261,15 @@ class TrainStep:
                 sp.run_clean()
             if self._side is not None and self.reducer is None:   # (N > 1: forward_backward has already joined the stream)
                 torch.cuda.current_stream().wait_stream(self._side)
-            sp.run_active(leaf.grad)
+            sp.run_active(self._plane_grad())
             sp.assign()
             return
         if self._side is not None:   # the reconstruction's autograd node runs on the prefetch stream
             self._side.wait_stream(torch.cuda.current_stream())
         if reg is not None:   # identical on every rank: added once, after the exchange
-            torch.autograd.backward([planes, self.scaler.scale(reg)], [leaf.grad, None])
+            torch.autograd.backward([planes, self.scaler.scale(reg)], [self._plane_grad(), None])
         else:
-            torch.autograd.backward([planes], [leaf.grad])
+            torch.autograd.backward([planes], [self._plane_grad()])
 
     def _tail_pipelined(self):
         """N > 1: per-plane gradient exchange on a communication stream, overlapped with the IDWT backward of the previous
@@ -318,7 +347,7 @@ class TrainStep:
         with torch.cuda.graph(gA, stream=side):
             self._static_loss = self.forward_backward(*self._static, update_grid=False)
         gB = None
-        if self.reducer is not None:
+        if self.reducer is not None and self.exch is None:
             gB = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gB, pool=gA.pool(), stream=side):
                 self._idwt_backward()
@@ -346,7 +375,7 @@ class TrainStep:
         if gB is not None:
             self._exchange()
             gB.replay()
-        elif self.world_size > 1:
+        elif self.world_size > 1 and self.reducer is None:
             parallel.allreduce_gradients(self.model, self.world_size)
         for p, g in self._graph_grads:
             p.grad = g

@@ -273,14 +273,17 @@ class _SamplePlanes(Function):
         coords, n_valid, perm = ctx.saved_tensors
         M, R, C, inv, fp16_coords, has_nv, has_perm, half = ctx.meta
         g_feat = g_feat.contiguous().half() if half else g_feat.contiguous().float()
+        external = False
         if ctx.grad_buf is not None:     # zero-filled ahead of time on the prefetch stream (TriPlaneVolume.prefetch_planes)
-            g_planes, ready = ctx.grad_buf
+            g_planes, ready, external = ctx.grad_buf
             ctx.grad_buf = None
             torch.cuda.current_stream().wait_event(ready)
         else:
             g_planes = cl_empty_planes(C, R, device=g_feat.device, zero=True)
         call("tnl_sample_planes_backward", ptr(g_feat), int(half), ptr(coords), M, R, C, inv, fp16_coords,
              ptr(n_valid) if has_nv else None, ptr(perm) if has_perm else None, ptr(g_planes), stream())
+        if external:      # the caller's persistent (symmetric-memory) buffer holds the result; autograd must not clone 1.6 GB of it
+            return None, None, None, None, None, None, None, None
         return g_planes, None, None, None, None, None, None, None
 
 
@@ -365,6 +368,7 @@ class TriPlaneVolume(nn.Module):
         # training hot path only: an idwt_plan.IdwtPlan restricts the next reconstructions to the occupied tiles
         # (see idwt_plan.py); None = dense planes, the reference's semantics
         self.idwt_plan = None
+        self.external_grad_buffer = None      # set by the multi-GPU training step: where the sampling backward scatters (see prefetch_planes)
         self._init_plane_features(planes_features)
 
     # -- parameters (triplane_encoder.py:155-231) --------------------------------------------------
@@ -437,15 +441,19 @@ class TriPlaneVolume(nn.Module):
                 ready.record(side)
             gbuf = None
             if torch.is_grad_enabled() and planes.requires_grad:
+                ext = self.external_grad_buffer     # multi-GPU: the persistent symmetric-memory buffer of parallel.PeerGradExchange
                 if plan is not None and partial_zero:
                     # the work-list backward only reads the tiles around the occupied ones: zero those, leave the rest undefined
-                    gbuf = cl_empty_planes(self.number_of_features, self.plane_resolution, device=planes.device)
+                    gbuf = ext if ext is not None else cl_empty_planes(self.number_of_features, self.plane_resolution, device=planes.device)
                     plan.zero_gradient_tiles(gbuf.permute(0, 2, 3, 1))
+                elif ext is not None:
+                    gbuf = ext
+                    gbuf.zero_()
                 else:
                     gbuf = cl_empty_planes(self.number_of_features, self.plane_resolution, device=planes.device, zero=True)
                 gready = torch.cuda.Event()
                 gready.record(side)
-                gbuf = (gbuf, gready)
+                gbuf = (gbuf, gready, ext is not None)
         self._prefetch = (ready, gbuf)
         return planes
 
