@@ -153,6 +153,43 @@ class DWTForward(torch.nn.Module):
         return ll, yh
 
 
+def _h(t):
+    return t.half().float()
+
+
+def build_planes_fp16_autocast(planes_features, coefs, wave="bior6.8"):
+    """What the reference's RENDER path computes: `get_planes()` is first reached inside
+    `torch.cuda.amp.autocast` + no_grad (nerf/utils.py:850-856), so every conv_transpose2d of the IDWT is an autocast-fp16 op:
+    operands and filter taps rounded to fp16, fp32 accumulation, fp16 result; the sums of two conv results are fp16 + fp16 -> fp16;
+    `2 * x` and F.pad keep the dtype.  Emulated here with fp32 arithmetic on fp16-rounded values.  The result is the fp16 plane
+    stack the reference caches for the whole evaluation run (triplane_encoder.py:409-416), returned as fp32 holding fp16 values."""
+    w = WAVELETS[wave]
+    pad = w["pad"]
+    g0 = [float(torch.tensor(v, dtype=torch.float32).half()) for v in w["rec_lo"]]
+    g1 = [float(torch.tensor(v, dtype=torch.float32).half()) for v in w["rec_hi"]]
+
+    def sfb1d_h(lo, hi, dim):
+        C = lo.shape[1]
+        L = len(g0)
+        w0 = _filt(g0, lo, dim).repeat(C, 1, 1, 1)
+        w1 = _filt(g1, lo, dim).repeat(C, 1, 1, 1)
+        s = (2, 1) if dim == 2 else (1, 2)
+        p = (L - 2, 0) if dim == 2 else (0, L - 2)
+        a = _h(F.conv_transpose2d(_h(lo), w0, stride=s, padding=p, groups=C))
+        b = _h(F.conv_transpose2d(_h(hi), w1, stride=s, padding=p, groups=C))
+        return _h(a + b)
+
+    x = planes_features.float()
+    for yh in coefs:
+        yl = F.pad(2 * x, (pad, pad, pad, pad))
+        yhp = F.pad(yh.float(), (pad, pad, pad, pad))
+        lh, hl, hh = torch.unbind(yhp, dim=2)
+        lo = sfb1d_h(yl, lh, 2)
+        hi = sfb1d_h(hl, hh, 2)
+        x = sfb1d_h(lo, hi, 3)
+    return x
+
+
 def build_planes(planes_features, coefs, wave="bior6.8"):
     """Multilevel reconstruction of the three planes; restates
     TriPlaneVolume.build_planes (triplane_encoder.py:364-405) for the configuration every README

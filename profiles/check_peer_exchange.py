@@ -51,7 +51,34 @@ def main():
         torch.cuda.synchronize(); dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 20
+        extra = {}
         if mode == "peer":
+            from trinerflet_b200._lib import call, ptr, stream
+            ex, r = ts.exch, ts.reducer
+
+            def timed(fn, n=reps):
+                fn(); torch.cuda.synchronize(); dist.barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(n):
+                    fn()
+                b.record(); torch.cuda.synchronize()
+                return round(a.elapsed_time(b) / n, 4)
+
+            extra["ms_two_barriers"] = timed(lambda: (ex._hdl_p.barrier(channel=0), ex._hdl_p.barrier(channel=1)))
+            for mc in ([True, False] if ex._mc_p is not None else [False]):
+                def tiles(mc=mc):
+                    ex._hdl_p.barrier(channel=0)
+                    call("tnl_tiles_allreduce", ex._mc_p if mc else None, ex._arr_p, ptr(r.list_ids), ptr(r.list_count), r.list_cap, ex.R, ex.C, ex.T,
+                         ex.rank, ex.world, 1.0 / ex.world, stream())
+                    ex._hdl_p.barrier(channel=1)
+                extra["ms_tiles_allreduce_" + ("multimem" if mc else "p2p")] = timed(tiles)
+            plain = torch.zeros_like(ex._flat_planes)
+            extra["ms_rmw_1.6GB_symmetric_buffer"] = timed(lambda: ex._flat_planes.add_(1.0), 5)
+            extra["ms_rmw_1.6GB_ordinary_buffer"] = timed(lambda: plain.add_(1.0), 5)
+            del plain
+            extra["dirty_tiles"] = r.n_tiles
+            extra["dirty_MB_fp32"] = round(r.n_tiles * ex.T * ex.T * ex.C * 4 / 1e6, 1)
             e0.record()
             for _ in range(reps):
                 ts.exch.exchange_()
@@ -67,7 +94,7 @@ def main():
             e1.record()
         torch.cuda.synchronize()
         res[mode] = dict(loss=float(loss), loss_graph=float(loss_g), grads=grads, grads_graph=grads_g, ms=e0.elapsed_time(e1) / reps,
-                         note=ts.exchange_note, graphs=1 if ts._graphs[1] is None else 2)
+                         note=ts.exchange_note, graphs=1 if ts._graphs[1] is None else 2, extra=extra)
         del ts, net
         torch.cuda.empty_cache()
     worst = max(rel_l2(a, b) for a, b in zip(res["peer"]["grads"], res["nccl"]["grads"]))
@@ -79,7 +106,7 @@ def main():
         print(json.dumps({"what": "peer_exchange_check", "world": world, "ok_all_ranks": bool(float(t) == 1.0), "max_rel_l2_peer_vs_nccl_fp32": worst,
                           "max_rel_l2_graph_vs_eager": worst_g, "loss_peer": res["peer"]["loss"], "loss_nccl": res["nccl"]["loss"],
                           "exchange_ms_peer_fp32_in_place": round(res["peer"]["ms"], 4), "exchange_ms_nccl_bf16_pack_unpack": round(res["nccl"]["ms"], 4),
-                          "peer": res["peer"]["note"], "graphs_per_step_peer": res["peer"]["graphs"], "graphs_per_step_nccl": res["nccl"]["graphs"]}))
+                          "peer": res["peer"]["note"], "graphs_per_step_peer": res["peer"]["graphs"], "graphs_per_step_nccl": res["nccl"]["graphs"], "detail": res["peer"]["extra"]}))
     dist.barrier()
     dist.destroy_process_group()
 
