@@ -375,8 +375,8 @@ def run_render(args, cfg):
     sc = scene.make_scene()
     frames = [scene.full_frame(sc, i % sc.poses.shape[0]) for i in range(args.warmup + args.steps)]
     N = frames[0][0].shape[0]
-    lo, hi = parallel.shard_range(N, rank, world)
-    host = [tuple(t[lo:hi].contiguous().pin_memory() for t in f) for f in frames]      # this rank's ray tile of every frame
+    n_local = int(parallel.tile_shard_indices(N, rank, world).numel()) if world > 1 else N
+    host = [tuple(t.contiguous().pin_memory() for t in f) for f in frames]      # the frame's rays (every rank takes its tiles of them)
     devf = [tuple(t.to(dev) for t in f) for f in host]
     kw = dict(bg_color=1, max_steps=args.max_steps, dt_gamma=0)
 
@@ -385,11 +385,15 @@ def run_render(args, cfg):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def render_tile(ro, rd):
+    def render_frame(ro, rd):
+        """this rank's round-robin ray tiles through the marching loop + the final gather (the only collective)"""
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
-            return net.render(ro.unsqueeze(0), rd.unsqueeze(0), staged=True, perturb=False, **kw)
+            return parallel.render_frame_sharded(net, ro, rd, rank, world, **kw)
 
     # planes: reconstructed once and cached for the whole run, as in the reference's eval (SURVEY.md 3.3)
+    with torch.no_grad():
+        net.encoder.get_planes()
+        net.encoder.reset_cahce()
     torch.cuda.synchronize()
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record()
@@ -400,7 +404,7 @@ def run_render(args, cfg):
     planes_ms = p0.elapsed_time(p1)
     c0 = _lib.launch_count
     for i in range(args.warmup):
-        render_tile(*devf[i])
+        render_frame(*devf[i])
     launches_per_frame = (_lib.launch_count - c0) / max(args.warmup, 1)
     clocks = ClockSampler(local_rank) if rank == 0 else None
     barrier()
@@ -408,9 +412,8 @@ def run_render(args, cfg):
         clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    outs = None
     for i in range(args.steps):
-        outs = render_tile(*devf[args.warmup + i])
+        render_frame(*devf[args.warmup + i])
     e1.record()
     barrier()
     if rank == 0:
@@ -419,27 +422,19 @@ def run_render(args, cfg):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_frame = float(ms) / args.steps
-    # ---- e2e: host rays in, sharded render, final gather (the only collective), image out, every frame ----
+    # ---- e2e: host rays in, sharded render + gather, frame out on rank 0, every frame ----
     barrier()
     if rank == 0:
         clocks.start()
-    f0, f1, g0, g1 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
-    gather_ms = 0.0
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for i in range(args.steps):
         ro, rd = (t.to(dev, non_blocking=True) for t in host[args.warmup + i])
-        o = render_tile(ro, rd)
-        g0.record()
-        image = parallel.gather_frame(o['image'].reshape(-1, 3), N, rank, world)
-        depth = parallel.gather_frame(o['depth'].reshape(-1), N, rank, world)
-        wsum = parallel.gather_frame(o['weights_sum'].reshape(-1), N, rank, world)
-        g1.record()
+        o = render_frame(ro, rd)
         if rank == 0:
-            img_host = image.cpu()
-            d_host, w_host = depth.cpu(), wsum.cpu()
+            img_host, d_host, w_host = o['image'].cpu(), o['depth'].cpu(), o['weights_sum'].cpu()
         else:
             torch.cuda.synchronize()
-        gather_ms += g0.elapsed_time(g1)
     f1.record()
     barrier()
     clk = clocks.stop() if rank == 0 else None
@@ -458,12 +453,12 @@ def run_render(args, cfg):
             "ms_per_step": ms_frame, "frames_per_s": 1e3 / ms_frame, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f16", "data": "synthetic",
             "config": {"workload": f"full-frame render: {args.config} C={C} R={R}, 800x800 = {N} rays, max_steps={args.max_steps}, perturb=False, ball occupancy r={args.occupancy_radius:g}, random-init",
-                       "parallelism": f"contiguous ray tiles over {world} GPU(s), replicated planes (built once, cached), no collective until the final gather",
+                       "parallelism": f"round-robin tiles of 256 rays over {world} GPU(s) ({n_local} rays on rank 0), replicated planes (built once, cached), no collective until the final gather (inside the timed region)",
                        "loop": (f"device-driven inference loop, {args.infer_chunk} iterations per state read" if args.infer_chunk else "host-driven loop (one 4-byte read per iteration)"),
                        "l2": "a different camera every frame; planes (1.6 GB) exceed the 126 MB L2"},
             "clocks": clk,
-            "e2e": {"value": N / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": (hi - lo) * 24 * world, "d2h_bytes_per_step": N * 20,
-                    "frames_per_s": 1e3 / ms_e2e, "gather_ms_per_frame": round(gather_ms / args.steps, 3)},
+            "e2e": {"value": N / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": N * 24 * world, "d2h_bytes_per_step": N * 20,
+                    "frames_per_s": 1e3 / ms_e2e},
             "gpu_launches": int(launches_per_frame * args.steps),
             "extras": {"planes_build_ms_once": round(planes_ms, 3), "planes_GBps": round(2 * P / 1e9 / (planes_ms * 1e-3), 1),
                        "iterations": (loop.iterations_done if loop else None), "state_reads": (loop.reads if loop else None)},

@@ -62,7 +62,8 @@ int tnl_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* b
  * Same outputs; sample slots are allocated by a deterministic exclusive scan in ray order instead
  * of the reference's atomicAdd race (raymarching.cu:405-406), so rays[n] = (n, offset_n, count_n).
  * counter[0] += total samples, counter[1] += N (as the reference's atomics leave them).
- * xyzs/dirs/deltas must be zero-initialised by the caller (reference: torch.zeros).
+ * xyzs/dirs/deltas may be uninitialised: rows no kept ray owns are zero-filled by the call (the reference zero-initialises
+ * the whole buffers, raymarching.py:205-207; rays are dropped, from the first that does not fit, when offset + count > M).
  * workspace: >= tnl_march_rays_train_workspace(N) bytes of device scratch. */
 size_t tnl_march_rays_train_workspace(uint32_t N);
 int tnl_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
@@ -70,7 +71,9 @@ int tnl_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t
                          const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
                          int32_t* rays, int32_t* counter, const float* noises, void* workspace,
                          size_t workspace_bytes, tnl_stream_t stream);
-/* replaces composite_rays_train_forward / _backward (raymarching.h:14-15, raymarching.cu:580-693) */
+/* replaces composite_rays_train_forward / _backward (raymarching.h:14-15, raymarching.cu:580-693).
+ * backward: grad_sigmas / grad_rgbs may be uninitialised; every row is written (zeros past a ray's termination and in rows no
+ * kept ray owns -- what the reference leaves untouched in its zero-initialised outputs, raymarching.py:283-284). */
 int tnl_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas,
                                      const int32_t* rays, uint32_t M, uint32_t N, float T_thresh,
                                      float* weights_sum, float* depth, float* image, tnl_stream_t stream);

@@ -1,5 +1,5 @@
 """torchrun --nproc-per-node N profiles/check_render_sharded.py [max_steps]
-Full-frame 800x800 render of the base config sharded into contiguous ray tiles over N GPUs (parallel.render_frame_sharded:
+Full-frame 800x800 render of the base config sharded into round-robin ray tiles over N GPUs (parallel.render_frame_sharded:
 replicated planes, device-driven marching loop, no collective until the final NCCL gather) against the same
 frame rendered on rank 0 alone.  Prints one JSON line on rank 0."""
 import json

@@ -25,3 +25,17 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(autouse=True)
+def _autocast_state_does_not_leak():
+    """Some CPU tests answer `torch.is_autocast_enabled` with a monkeypatched True (CUDA autocast cannot be switched on without a
+    device).  torch.autocast.__exit__ restores the state it READ on entry, so such a test leaves the real thread-local flag set;
+    reset it so that the next test starts from the documented default."""
+    yield
+    import torch
+    for dev in ("cuda", "cpu"):
+        try:
+            torch.set_autocast_enabled(dev, False)
+        except Exception:
+            pass

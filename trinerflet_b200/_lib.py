@@ -121,7 +121,7 @@ def check(rc, what):
 
 
 # number of kernels each ABI call launches (for the launch counter the benchmark reports)
-KERNELS_PER_CALL = {"tnl_march_rays_train": 5, "tnl_compact_alive": 3, "tnl_compact_alive_dev": 3, "tnl_cell_sort": 5,
+KERNELS_PER_CALL = {"tnl_march_rays_train": 6, "tnl_composite_rays_train_backward": 2, "tnl_compact_alive": 3, "tnl_compact_alive_dev": 3, "tnl_cell_sort": 5,
                     "tnl_mlp_pack_weights": 2}
 # work-list IDWT calls launch one kernel per requested part (position of the `parts` argument from the end)
 _PARTS_ARG = {"tnl_idwt_level_forward_sparse": -2, "tnl_idwt_level_backward_sparse": -3}

@@ -463,10 +463,15 @@ k_composite_train_bwd(const float* __restrict__ grad_ws, const float* __restrict
     const float tail = grad_ws[index] * (1.0f - weights_sum[index]);
     const float rf = image[3 * (size_t)index], gf = image[3 * (size_t)index + 1], bf = image[3 * (size_t)index + 2];
     float T = 1.0f, r = 0.f, g = 0.f, b = 0.f;  // carried across chunks
+    bool done = false;                          // the ray has terminated: the remaining samples get zero gradient
     for (uint32_t base = 0; base < num; base += 32) {
         const uint32_t k = base + lane;
         const bool act = k < num;
         const size_t i = (size_t)offset + k;
+        if (done) {                             // (the reference relies on zero-initialised outputs; here every row is written)
+            if (act) { grad_rgbs[3 * i] = 0.f; grad_rgbs[3 * i + 1] = 0.f; grad_rgbs[3 * i + 2] = 0.f; grad_sigmas[i] = 0.f; }
+            continue;
+        }
         const float sg = act ? __ldg(sigmas + i) : 0.f;
         const float d0 = act ? __ldg(deltas + 2 * i) : 0.f;
         const float c0 = act ? __ldg(rgbs + 3 * i) : 0.f, c1 = act ? __ldg(rgbs + 3 * i + 1) : 0.f,
@@ -487,12 +492,40 @@ k_composite_train_bwd(const float* __restrict__ grad_ws, const float* __restrict
             grad_rgbs[3 * i + 2] = gi2 * w;
             grad_sigmas[i] = d0 * (gi0 * (T_after * c0 - (rf - ri)) + gi1 * (T_after * c1 - (gf - gi)) +
                                    gi2 * (T_after * c2 - (bf - bi)) + tail);
+        } else if (act) {
+            grad_rgbs[3 * i] = 0.f; grad_rgbs[3 * i + 1] = 0.f; grad_rgbs[3 * i + 2] = 0.f; grad_sigmas[i] = 0.f;
         }
-        if (stop) break;
+        if (stop) { done = true; continue; }
         T = __shfl_sync(0xffffffffu, T_after, 31);
         r = __shfl_sync(0xffffffffu, ri, 31);
         g = __shfl_sync(0xffffffffu, gi, 31);
         b = __shfl_sync(0xffffffffu, bi, 31);
+    }
+}
+
+// Rows of the [M, *] sample buffers that no kept ray owns: [T, M) with T = offset of the first ray that does not fit
+// (offset <= M < offset + count; the slots are allocated in ray order, so every later ray is dropped as well) or, when all rays
+// fit, the total sample count.  The reference gets zeros there from zero-initialised buffers (raymarching.py:205-207, 283-284:
+// about 190 MB of memset per step); here the few rows of the tail are cleared instead.  Up to three buffers of widths wa/wb/wc.
+__global__ void __launch_bounds__(256)
+k_zero_unowned_rows(const int32_t* __restrict__ rays, uint32_t N, uint32_t M, float* __restrict__ a, int wa, float* __restrict__ b, int wb,
+                    float* __restrict__ c, int wc) {
+    __shared__ uint32_t sT;
+    if (threadIdx.x == 0) {
+        uint32_t lo = 0, hi = N;     // first ray whose end exceeds M (ends are non-decreasing in ray order)
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            const uint32_t end = (uint32_t)rays[3 * (size_t)mid + 1] + (uint32_t)rays[3 * (size_t)mid + 2];
+            if (end > M) hi = mid; else lo = mid + 1;
+        }
+        sT = lo < N ? (uint32_t)rays[3 * (size_t)lo + 1] : ((uint32_t)rays[3 * (size_t)(N - 1) + 1] + (uint32_t)rays[3 * (size_t)(N - 1) + 2]);
+    }
+    __syncthreads();
+    const uint32_t T = sT < M ? sT : M;
+    for (uint32_t row = T + blockIdx.x * blockDim.x + threadIdx.x; row < M; row += gridDim.x * blockDim.x) {
+        if (a) for (int j = 0; j < wa; ++j) a[(size_t)row * wa + j] = 0.f;
+        if (b) for (int j = 0; j < wb; ++j) b[(size_t)row * wb + j] = 0.f;
+        if (c) for (int j = 0; j < wc; ++j) c[(size_t)row * wc + j] = 0.f;
     }
 }
 
@@ -785,9 +818,12 @@ int tnl_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t
     k_scan_block_sums<0><<<nb, kScanThreads, 0, S(stream)>>>(rays + 2, N, 3, block_sums);
     k_scan_of_sums<<<1, kScanThreads, 0, S(stream)>>>(block_sums, nb, counter, N, nullptr);
     k_scan_offsets<<<nb, kScanThreads, 0, S(stream)>>>(rays + 2, N, 3, block_sums, rays + 1);
-    if (M > 0)
+    if (M > 0) {
         k_march_train_write<<<ceil_div(N, kT), kT, 0, S(stream)>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N,
                                                                     C, H, M, nears, fars, noises, rays, xyzs, dirs, deltas);
+        // rows no kept ray owns are zeros, as in the reference's zero-initialised buffers: the caller may pass uninitialised memory
+        k_zero_unowned_rows<<<32, 256, 0, S(stream)>>>(rays, N, M, xyzs, 3, dirs, 3, deltas, 2);
+    }
     return finish_launch("march_rays_train");
 }
 
@@ -812,6 +848,8 @@ int tnl_composite_rays_train_backward(const float* grad_weights_sum, const float
                       grad_sigmas && grad_rgbs, "null pointer");
     k_composite_train_bwd<<<ceil_div(N, 8u), 256, 0, S(stream)>>>(grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays,
                                                                    weights_sum, image, M, N, T_thresh, grad_sigmas, grad_rgbs);
+    // every row a kept ray owns has been written (zeros past the ray's termination); the rest of the buffers: the unowned tail
+    k_zero_unowned_rows<<<32, 256, 0, S(stream)>>>(rays, N, M, grad_sigmas, 1, grad_rgbs, 3, nullptr, 0);
     return finish_launch("composite_rays_train_backward");
 }
 

@@ -159,14 +159,16 @@ class _march_rays_train(Function):
             if align > 0:
                 m += align - m % align
             m = min(m, M)
-            xyzs = torch.zeros(m, 3, dtype=rays_o.dtype, device=dev)
-            dirs = torch.zeros(m, 3, dtype=rays_o.dtype, device=dev)
-            deltas = torch.zeros(m, 2, dtype=rays_o.dtype, device=dev)
+            # (torch.empty: the call itself zero-fills the rows no ray owns -- same contents as the reference's zero-initialised
+            #  buffers, raymarching.py:205-207, without 120 MB of memset per step)
+            xyzs = torch.empty(m, 3, dtype=rays_o.dtype, device=dev)
+            dirs = torch.empty(m, 3, dtype=rays_o.dtype, device=dev)
+            deltas = torch.empty(m, 2, dtype=rays_o.dtype, device=dev)
             run(m, xyzs, dirs, deltas)
         else:
-            xyzs = torch.zeros(M, 3, dtype=rays_o.dtype, device=dev)
-            dirs = torch.zeros(M, 3, dtype=rays_o.dtype, device=dev)
-            deltas = torch.zeros(M, 2, dtype=rays_o.dtype, device=dev)
+            xyzs = torch.empty(M, 3, dtype=rays_o.dtype, device=dev)
+            dirs = torch.empty(M, 3, dtype=rays_o.dtype, device=dev)
+            deltas = torch.empty(M, 2, dtype=rays_o.dtype, device=dev)
             run(M, xyzs, dirs, deltas)
         return xyzs, dirs, deltas, rays
 
@@ -201,8 +203,8 @@ class _composite_rays_train(Function):
         grad_image = grad_image.contiguous()
         sigmas, rgbs, deltas, rays, weights_sum, depth, image = ctx.saved_tensors
         M, N, T_thresh = ctx.dims
-        grad_sigmas = torch.zeros_like(sigmas)
-        grad_rgbs = torch.zeros_like(rgbs)
+        grad_sigmas = torch.empty_like(sigmas)      # every row is written by the call (zeros where the reference leaves its
+        grad_rgbs = torch.empty_like(rgbs)          # zero-initialised buffers untouched, raymarching.py:283-284)
         call("tnl_composite_rays_train_backward", ptr(grad_weights_sum), ptr(grad_image), ptr(sigmas), ptr(rgbs),
              ptr(deltas), ptr(rays), ptr(weights_sum), ptr(image), M, N, float(T_thresh), ptr(grad_sigmas),
              ptr(grad_rgbs), stream())
@@ -283,7 +285,8 @@ class DeviceRayLoop:
                 break
     """
 
-    def __init__(self, rays_o, rays_d, nears, fars, bound, density_bitfield, C, H, dt_gamma=0, max_steps=1024, perturb=False):
+    def __init__(self, rays_o, rays_d, nears, fars, bound, density_bitfield, C, H, dt_gamma=0, max_steps=1024, perturb=False,
+                 row_budget=0):
         self.rays_o = _cuda_f32(rays_o).view(-1, 3)
         self.rays_d = _cuda_f32(rays_d).view(-1, 3)
         dev = self.rays_o.device
@@ -296,7 +299,11 @@ class DeviceRayLoop:
         self.n_valid = self.ctrl[3:4]                      # n_alive * n_step of the running iteration, on the device
         self.lists = [torch.arange(N, dtype=torch.int32, device=dev), torch.empty(N, dtype=torch.int32, device=dev)]
         self.rays_t = self.nears.clone()
-        rows = N + 128 - N % 128                           # n_alive * n_step <= N always; same padding rule as march_rays
+        # rows marched per iteration: n_alive * n_step <= budget.  The reference's budget is the N of the call (renderer.py:352:
+        # n_step = max(min(N // n_alive, 8), 1)); a ray-tile shard of a frame passes the frame's ray count instead, so that it
+        # marches as many samples per ray and iteration as the unsharded frame would (per-ray results do not depend on n_step)
+        self.budget = B = max(N, int(row_budget))
+        rows = B + 128 - B % 128                           # n_alive * n_step <= budget always; same padding rule as march_rays
         self.xyzs = torch.zeros(rows, 3, dtype=torch.float32, device=dev)
         self.dirs = torch.zeros(rows, 3, dtype=torch.float32, device=dev)
         self.deltas = torch.zeros(rows, 2, dtype=torch.float32, device=dev)
@@ -307,14 +314,14 @@ class DeviceRayLoop:
         self.reads = 0
 
     def _rows_cap(self):
-        m = min(self.N, 8 * self.cap)
+        m = min(self.budget, 8 * self.cap)
         return min(m + 128 - m % 128, self.xyzs.shape[0])
 
     def begin_iteration(self):
         """plan + march -> views of the sample buffers the field has to evaluate (rows >= *n_valid are stale: skip them)"""
         if self.cap <= 0:
             raise RuntimeError("DeviceRayLoop: the loop has finished")
-        call("tnl_infer_plan", ptr(self.ctrl), self.N, self.max_steps, stream())
+        call("tnl_infer_plan", ptr(self.ctrl), self.budget, self.max_steps, stream())
         noises = self.noises if self.iterations_issued == 0 else None
         call("tnl_march_rays_dev", ptr(self.ctrl), self.cap, ptr(self.lists[0]), ptr(self.rays_t), ptr(self.rays_o), ptr(self.rays_d),
              self.bound, self.dt_gamma, self.max_steps, self.C, self.H, ptr(self.bitfield), ptr(self.fars), ptr(self.xyzs),

@@ -113,11 +113,12 @@ class NeRFRenderer(nn.Module):
             depth = torch.zeros(N, dtype=torch.float32, device=device)
             image = torch.zeros(N, 3, dtype=torch.float32, device=device)
             chunk = int(getattr(self, "infer_chunk", 0))
+            budget = max(N, int(getattr(self, "infer_row_budget", 0)))   # rows per iteration (reference: N; see DeviceRayLoop)
             if chunk > 0 and N > 0:
                 # device-driven loop: `chunk` iterations are issued per read of the loop state; sample
                 # buffers live for the whole frame; identical per-ray results (opt-in: model.infer_chunk = 8)
                 loop = raymarching.DeviceRayLoop(rays_o, rays_d, nears, fars, self.bound, self.density_bitfield, self.cascade,
-                                                 self.grid_size, dt_gamma, max_steps, perturb)
+                                                 self.grid_size, dt_gamma, max_steps, perturb, row_budget=budget)
                 # every live iteration marches >= 1 sample per ray, so the loop needs at most max_steps iterations
                 for _ in range(-(-int(max_steps) // chunk) + 1):
                     for _ in range(chunk):
@@ -137,7 +138,7 @@ class NeRFRenderer(nn.Module):
             rays_t = nears.clone()
             step = 0
             while step < max_steps and n_alive > 0:
-                n_step = max(min(N // n_alive, 8), 1)
+                n_step = max(min(budget // n_alive, 8), 1)
                 xyzs, dirs, deltas = raymarching.march_rays(
                     n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound, self.density_bitfield, self.cascade,
                     self.grid_size, nears, fars, 128, perturb if step == 0 else False, dt_gamma, max_steps)
