@@ -184,6 +184,11 @@ int tnl_sample_planes_forward(const float* planes, const float* xyz, uint32_t M,
 int tnl_sample_planes_backward(const void* g_feat, int feat_fp16, const float* xyz, uint32_t M, uint32_t R, uint32_t C,
                                float inv_bound, int fp16_coords, const int32_t* n_valid, const int32_t* perm,
                                float* g_planes, tnl_stream_t stream);
+/* The same scatter for ONE plane (plane = 0, 1, 2; C in {16, 32, 48}): three calls equal tnl_sample_planes_backward.  The
+ * multi-GPU training step issues them one by one and starts the exchange of a plane's gradient while the next plane scatters. */
+int tnl_sample_planes_backward_plane(const void* g_feat, int feat_fp16, const float* xyz, uint32_t M, uint32_t R, uint32_t C,
+                                     float inv_bound, int fp16_coords, const int32_t* n_valid, const int32_t* perm,
+                                     float* g_planes, uint32_t plane, tnl_stream_t stream);
 
 /* Spatial binning of sample points: perm[i] = row of the i-th point in the order of a G^3 Morton grid over
  * [-bound, bound]^3 (rows >= *n_valid last).  Kernels taking `perm` visit points in that order, which makes the

@@ -232,6 +232,18 @@ def test_sampling_forward_backward(C, R, fp16, use_perm):
     pl.grad = None
     (of.sample_planes(pl, xyz, BOUND, fp16=fp16) * torch.from_numpy(Gh.astype(np.float32))).sum().backward()
     assert np.abs(gp_h - _cl(pl.grad)).max() <= 1e-4 * np.abs(want).max()
+    # plane by plane (the multi-GPU step overlaps the exchange of one plane with the scatter of the next): same per-plane sums,
+    # and plane p's call touches plane p only
+    if C in (16, 32, 48):
+        gp_p = np.zeros((3, R, R, C), np.float32)
+        for p in range(3):
+            before = gp_p.copy()
+            kemu.call("tnl_sample_planes_backward_plane", Gh, 1, xyz.numpy(), M, R, C, inv_bound, int(fp16), nv, perm, gp_p, p, None)
+            others = [q for q in range(3) if q != p]
+            assert np.array_equal(gp_p[others], before[others])
+        assert np.abs(gp_p - gp_h).max() <= 1e-5 * np.abs(want).max()
+        assert kemu.lib().tnl_sample_planes_backward_plane(kemu.p(Gh), 1, kemu.p(xyz.numpy()), M, R, C, ctypes.c_float(inv_bound), int(fp16),
+                                                           None, None, kemu.p(gp_p), 3, None) == -1
 
 
 def test_cell_sort_orders_by_cell():

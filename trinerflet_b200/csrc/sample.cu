@@ -195,6 +195,36 @@ k_sample_bwd4(const void* __restrict__ g_feat_, const float* __restrict__ xyz, u
     if (t.x1ok && t.y1ok) red_add_v4(base + dy + dx, g, t.se);
 }
 
+// the same scatter restricted to ONE plane (thread <-> (point, 4 channels); 24 points per block): the multi-GPU step scatters plane
+// by plane so that the exchange of plane p overlaps the scatter of plane p + 1 (parallel.PeerGradExchange)
+template <int TPP4, bool HALF>
+__global__ void __launch_bounds__(ScatterCfg<TPP4>::NT)
+k_sample_bwd4_plane(const void* __restrict__ g_feat_, const float* __restrict__ xyz, uint32_t M, int R, float inv_bound,
+                    int fp16_coords, const int32_t* __restrict__ n_valid, const int32_t* __restrict__ perm,
+                    float* __restrict__ g_planes, int p) {
+    using Cfg = ScatterCfg<TPP4>;
+    constexpr int C = Cfg::C;
+    const int tid = threadIdx.x;
+    const int cq = tid % TPP4, lp = tid / TPP4;
+    uint32_t m = blockIdx.x * (3 * Cfg::PPB) + lp;
+    if (m >= M) return;
+    if (perm) m = (uint32_t)__ldg(perm + m);
+    if (n_valid && (int32_t)m >= *n_valid) return;
+    const size_t q4 = ((size_t)m * 3 + p) * TPP4 + cq;
+    const float4 g = HALF ? unpack4h(__ldg(reinterpret_cast<const uint2*>(g_feat_) + q4))
+                          : __ldg(reinterpret_cast<const float4*>(g_feat_) + q4);
+    if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) return;
+    float gx, gy;
+    plane_coords(xyz, m, p, inv_bound, fp16_coords, gx, gy);
+    const Tap t = make_tap(gx, gy, R);
+    float* base = g_planes + (((size_t)p * R + t.y0) * R + t.x0) * C + 4 * cq;
+    const size_t dx = (size_t)C, dy = (size_t)R * C;
+    red_add_v4(base, g, t.nw);
+    if (t.x1ok) red_add_v4(base + dx, g, t.ne);
+    if (t.y1ok) red_add_v4(base + dy, g, t.sw);
+    if (t.x1ok && t.y1ok) red_add_v4(base + dy + dx, g, t.se);
+}
+
 template <int TPP>
 static void launch_fwd8(const float* planes, const float* xyz, uint32_t M, uint32_t R, float inv_bound, int fp16_coords,
                         const int32_t* n_valid, const int32_t* perm, void* feat, int half, cudaStream_t s) {
@@ -210,6 +240,15 @@ static void launch_bwd4(const void* g_feat, int half, const float* xyz, uint32_t
     const unsigned blocks = ceil_div(M, (uint32_t)Cfg::PPB);
     if (half) k_sample_bwd4<TPP4, true><<<blocks, Cfg::NT, 0, s>>>(g_feat, xyz, M, (int)R, inv_bound, fp16_coords, n_valid, perm, g_planes);
     else k_sample_bwd4<TPP4, false><<<blocks, Cfg::NT, 0, s>>>(g_feat, xyz, M, (int)R, inv_bound, fp16_coords, n_valid, perm, g_planes);
+}
+
+template <int TPP4>
+static void launch_bwd4_plane(const void* g_feat, int half, const float* xyz, uint32_t M, uint32_t R, float inv_bound, int fp16_coords,
+                              const int32_t* n_valid, const int32_t* perm, float* g_planes, int plane, cudaStream_t s) {
+    using Cfg = ScatterCfg<TPP4>;
+    const unsigned blocks = ceil_div(M, (uint32_t)(3 * Cfg::PPB));
+    if (half) k_sample_bwd4_plane<TPP4, true><<<blocks, Cfg::NT, 0, s>>>(g_feat, xyz, M, (int)R, inv_bound, fp16_coords, n_valid, perm, g_planes, plane);
+    else k_sample_bwd4_plane<TPP4, false><<<blocks, Cfg::NT, 0, s>>>(g_feat, xyz, M, (int)R, inv_bound, fp16_coords, n_valid, perm, g_planes, plane);
 }
 
 }  // namespace tnl
@@ -264,6 +303,20 @@ int tnl_sample_planes_backward(const void* g_feat, int feat_fp16, const float* x
         k_sample_bwd<false><<<(unsigned)ceil_div(total, (uint64_t)256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
             g_feat, xyz, M, (int)R, (int)C, inv_bound, fp16_coords, n_valid, perm, g_planes);
     return finish_launch("sample_planes_backward");
+}
+
+int tnl_sample_planes_backward_plane(const void* g_feat, int feat_fp16, const float* xyz, uint32_t M, uint32_t R, uint32_t C,
+                                     float inv_bound, int fp16_coords, const int32_t* n_valid, const int32_t* perm,
+                                     float* g_planes, uint32_t plane, tnl_stream_t stream) {
+    if (M == 0) return 0;
+    TNL_ARG_CHECK(g_feat && xyz && g_planes && plane < 3, "null pointer / plane index");
+    TNL_ARG_CHECK(C == 16 || C == 32 || C == 48, "per-plane scatter: C in {16, 32, 48}");
+    TNL_ARG_CHECK(((uintptr_t)g_planes & 15) == 0 && ((uintptr_t)g_feat & 15) == 0, "g_planes/g_feat must be 16-byte aligned");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (C == 16) launch_bwd4_plane<4>(g_feat, feat_fp16, xyz, M, R, inv_bound, fp16_coords, n_valid, perm, g_planes, (int)plane, st);
+    else if (C == 32) launch_bwd4_plane<8>(g_feat, feat_fp16, xyz, M, R, inv_bound, fp16_coords, n_valid, perm, g_planes, (int)plane, st);
+    else launch_bwd4_plane<12>(g_feat, feat_fp16, xyz, M, R, inv_bound, fp16_coords, n_valid, perm, g_planes, (int)plane, st);
+    return finish_launch("sample_planes_backward_plane");
 }
 
 }  // extern "C"

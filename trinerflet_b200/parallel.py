@@ -113,6 +113,18 @@ class PlaneGradReducer:
             self.list_version = getattr(self, "list_version", 0) + 1
         self.list_ids[:self.n_tiles].copy_(self.tile_ids)
         self.list_count.fill_(self.n_tiles)
+        # ... and one list per plane (the peer exchange of plane p overlaps the scatter of plane p + 1)
+        pcap = getattr(self, "plane_cap", 0)
+        need = max(cnt for _, cnt in self.plane_ranges) if self.plane_ranges else 0
+        if need > pcap:
+            self.plane_cap = max(64, 2 * need)
+            self.plane_ids = [torch.zeros(self.plane_cap, dtype=torch.int32, device=flags.device) for _ in range(3)]
+            self.plane_count = torch.zeros(3, dtype=torch.int32, device=flags.device)
+            self.list_version = getattr(self, "list_version", 0) + 1
+        for p, (start, cnt) in enumerate(self.plane_ranges):
+            if cnt:
+                self.plane_ids[p][:cnt].copy_(self.tile_ids[start:start + cnt])
+        self.plane_count.copy_(torch.tensor([cnt for _, cnt in self.plane_ranges], dtype=torch.int32))
         return self
 
     def reduce_(self, g_planes):
@@ -239,6 +251,31 @@ class PeerGradExchange:
             if float(ok) == 1.0:
                 return mode
         raise RuntimeError("PeerGradExchange: neither the multicast nor the peer-mapped all-reduce passed its self-test")
+
+    def exchange_plane_(self, plane):
+        """in place, on the current stream: the dirty tiles of ONE plane of g_planes <- average over the ranks"""
+        from ._lib import call, ptr, stream
+        r = self.reducer
+        mc = self.mode == "multimem"
+        self._hdl_p.barrier(channel=0)
+        call("tnl_tiles_allreduce", self._mc_p if mc else None, self._arr_p, ptr(r.plane_ids[plane]), ptr(r.plane_count[plane:plane + 1]), r.plane_cap,
+             self.R, self.C, self.T, self.rank, self.world, 1.0 / self.world, stream())
+        self._hdl_p.barrier(channel=1)
+
+    def exchange_mlp_(self):
+        """in place, on the current stream: the MLP weight gradients <- average over the ranks (they become views of one flat buffer)"""
+        grads = [p.grad for p in self.params]
+        lo, hi = self._flat_mlp.data_ptr(), self._flat_mlp.data_ptr() + 4 * self.n_mlp_pad
+        if not all(g is not None for g in grads) or any(lo <= g.data_ptr() < hi for g in grads):
+            return      # (nothing new: gradients that already are views of the flat buffer have been exchanged)
+        torch.cat([_dense_view(g).reshape(-1) for g in grads], out=self._flat_mlp[:self.n_mlp])
+        self._hdl_m.barrier(channel=0)
+        self._flat(self.mode == "multimem", self.n_mlp_pad, 1.0 / self.world)
+        self._hdl_m.barrier(channel=1)
+        off = 0
+        for p in self.params:
+            p.grad = self._flat_mlp[off:off + p.numel()].view_as(p)
+            off += p.numel()
 
     def exchange_(self):
         """in place, on the current stream: g_planes (dirty tiles) and the MLP gradients <- average over the ranks"""

@@ -61,6 +61,8 @@ class TrainStep:
                 self._reducer_gen = getattr(model, "bitfield_generation", 0)
                 self.exch = parallel.PeerGradExchange(model, world_size, self.reducer)
                 model.encoder.external_grad_buffer = self.exch.g_planes
+                model.encoder.scatter_plane_hook = self._exchange_plane_async
+                self._comm = torch.cuda.Stream()
                 self.exchange_note = f"peer memory, {self.exch.mode} (own kernels: in place, fp32, one CUDA graph per step)"
             except Exception as ex:  # noqa: BLE001
                 if exchange == "peer":
@@ -97,6 +99,7 @@ class TrainStep:
         enc = model.encoder
         model.train()
         enc.reset_cahce()
+        self._planes_exchanged = 0
         do_update = (self.global_step % opt.update_extra_interval == 0) if update_grid is None else update_grid
         enc.idwt_plan = None
         use_plan = (self.sparse_idwt and not do_update and (rays_o.is_cuda or self.plan_on_any_device) and model.cuda_ray
@@ -236,9 +239,21 @@ class TrainStep:
         self._plan_gen = getattr(self.model, "bitfield_generation", 0)
         return self._plan
 
+    def _exchange_plane_async(self, plane):
+        """called by the sampling backward right after it has launched the scatter of `plane`: that plane's exchange starts on the
+        communication stream while the next plane scatters on the main stream"""
+        self._comm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._comm):
+            self.exch.exchange_plane_(plane)
+        self._planes_exchanged += 1
+
     def _exchange(self):
         if self.exch is not None:
             planes, leaf, reg = self._cut
+            if self._planes_exchanged == 3 and leaf.grad is None:
+                self.exch.exchange_mlp_()                                   # (small: 54 KB) on the main stream ...
+                torch.cuda.current_stream().wait_stream(self._comm)         # ... while the last plane finishes on the other
+                return
             if leaf.grad is not None:       # dense step (grid refresh): the scatter went into an ordinary buffer
                 self.exch.g_planes.copy_(leaf.grad)
                 leaf.grad = None

@@ -275,13 +275,21 @@ class _SamplePlanes(Function):
         g_feat = g_feat.contiguous().half() if half else g_feat.contiguous().float()
         external = False
         if ctx.grad_buf is not None:     # zero-filled ahead of time on the prefetch stream (TriPlaneVolume.prefetch_planes)
-            g_planes, ready, external = ctx.grad_buf
+            g_planes, ready, external, plane_hook = ctx.grad_buf
             ctx.grad_buf = None
             torch.cuda.current_stream().wait_event(ready)
         else:
             g_planes = cl_empty_planes(C, R, device=g_feat.device, zero=True)
-        call("tnl_sample_planes_backward", ptr(g_feat), int(half), ptr(coords), M, R, C, inv, fp16_coords,
-             ptr(n_valid) if has_nv else None, ptr(perm) if has_perm else None, ptr(g_planes), stream())
+            plane_hook = None
+        if plane_hook is not None and C in (16, 32, 48):
+            # multi-GPU step: plane by plane, so that the caller can start exchanging plane p while plane p + 1 scatters
+            for p in range(3):
+                call("tnl_sample_planes_backward_plane", ptr(g_feat), int(half), ptr(coords), M, R, C, inv, fp16_coords,
+                     ptr(n_valid) if has_nv else None, ptr(perm) if has_perm else None, ptr(g_planes), p, stream())
+                plane_hook(p)
+        else:
+            call("tnl_sample_planes_backward", ptr(g_feat), int(half), ptr(coords), M, R, C, inv, fp16_coords,
+                 ptr(n_valid) if has_nv else None, ptr(perm) if has_perm else None, ptr(g_planes), stream())
         if external:      # the caller's persistent (symmetric-memory) buffer holds the result; autograd must not clone 1.6 GB of it
             return None, None, None, None, None, None, None, None
         return g_planes, None, None, None, None, None, None, None
@@ -369,6 +377,7 @@ class TriPlaneVolume(nn.Module):
         # (see idwt_plan.py); None = dense planes, the reference's semantics
         self.idwt_plan = None
         self.external_grad_buffer = None      # set by the multi-GPU training step: where the sampling backward scatters (see prefetch_planes)
+        self.scatter_plane_hook = None        # ... and a callback after each plane's scatter (starts that plane's exchange)
         self._init_plane_features(planes_features)
 
     # -- parameters (triplane_encoder.py:155-231) --------------------------------------------------
@@ -453,7 +462,7 @@ class TriPlaneVolume(nn.Module):
                     gbuf = cl_empty_planes(self.number_of_features, self.plane_resolution, device=planes.device, zero=True)
                 gready = torch.cuda.Event()
                 gready.record(side)
-                gbuf = (gbuf, gready, ext is not None)
+                gbuf = (gbuf, gready, ext is not None, self.scatter_plane_hook if ext is not None else None)
         self._prefetch = (ready, gbuf)
         return planes
 
