@@ -342,6 +342,9 @@ def gather_frame(local, n_total, rank, world_size):
     return torch.cat([o[:hi - lo] for o, (lo, hi) in zip(out, sizes)], dim=0)
 
 
+_TILE_SHARDS = {}
+
+
 def tile_shard_indices(n, rank, world_size, tile=256):
     """Ray ids of `rank` when the n rays of a frame are dealt out as round-robin tiles of `tile` consecutive rays (tile k goes to
     rank k % world_size).  Interleaving balances the work: contiguous bands give the ranks that see the object every hit ray
@@ -351,16 +354,30 @@ def tile_shard_indices(n, rank, world_size, tile=256):
     return ids[t % world_size == rank]
 
 
+def _tile_shards(n, world_size, tile, device):
+    """cached per frame geometry: (ray ids of every rank on `device`, their counts, inverse permutation of the concatenation)"""
+    key = (n, world_size, tile, str(device))
+    hit = _TILE_SHARDS.get(key)
+    if hit is None:
+        ids = [tile_shard_indices(n, r, world_size, tile) for r in range(world_size)]
+        inv = torch.empty(n, dtype=torch.long)
+        inv[torch.cat(ids)] = torch.arange(n)
+        hit = ([i.to(device) for i in ids], [int(i.numel()) for i in ids], inv.to(device))
+        _TILE_SHARDS[key] = hit
+    return hit
+
+
 def render_frame_sharded(model, rays_o, rays_d, rank, world_size, tile=256, **render_kwargs):
     """Full-frame inference sharded by ray tiles (renderer.py:549-576 path; BASELINE.json configs[4]): every rank
     renders its round-robin tiles from replicated planes with the device-driven marching loop and no collective until the final
     gather.  The shard marches with the FRAME's row budget (model.infer_row_budget), i.e. as many samples per ray and iteration as
-    the unsharded frame; per-ray results are independent of that schedule, so the gathered frame is bit-identical."""
+    the unsharded frame; per-ray results are independent of that schedule, so the gathered frame equals the single-GPU frame."""
     n = rays_o.shape[0]
     if world_size <= 1:
         out = model.render(rays_o.unsqueeze(0), rays_d.unsqueeze(0), staged=True, perturb=False, **render_kwargs)
         return {'image': out['image'].reshape(-1, 3), 'depth': out['depth'].reshape(-1), 'weights_sum': out['weights_sum'].reshape(-1)}
-    mine = tile_shard_indices(n, rank, world_size, tile).to(rays_o.device)
+    ids, counts, inv = _tile_shards(n, world_size, tile, rays_o.device)
+    mine = ids[rank]
     saved = getattr(model, "infer_row_budget", 0)
     model.infer_row_budget = n
     try:
@@ -369,12 +386,10 @@ def render_frame_sharded(model, rays_o, rays_d, rank, world_size, tile=256, **re
         model.infer_row_budget = saved
     # final gather (the only collective): one padded all-gather of [image | depth | weights_sum], then the tiles go back in place
     local = torch.cat([out['image'].reshape(-1, 3), out['depth'].reshape(-1, 1), out['weights_sum'].reshape(-1, 1)], dim=1)
-    counts = [int(tile_shard_indices(n, r, world_size, tile).numel()) for r in range(world_size)]
     pad = torch.zeros(max(counts), 5, dtype=local.dtype, device=local.device)
     pad[:local.shape[0]] = local
-    parts = [torch.empty_like(pad) for _ in range(world_size)]
-    dist.all_gather(parts, pad)
-    frame = torch.empty(n, 5, dtype=local.dtype, device=local.device)
-    for r in range(world_size):
-        frame[tile_shard_indices(n, r, world_size, tile).to(local.device)] = parts[r][:counts[r]]
+    gathered = torch.empty(world_size, max(counts), 5, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(gathered, pad) if hasattr(dist, "all_gather_into_tensor") and local.is_cuda else \
+        dist.all_gather(list(gathered.unbind(0)), pad)
+    frame = torch.cat([gathered[r, :counts[r]] for r in range(world_size)], dim=0)[inv]
     return {'image': frame[:, :3].contiguous(), 'depth': frame[:, 3].contiguous(), 'weights_sum': frame[:, 4].contiguous()}
