@@ -66,6 +66,10 @@ int tnl_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* b
  * the whole buffers, raymarching.py:205-207; rays are dropped, from the first that does not fit, when offset + count > M).
  * workspace: >= tnl_march_rays_train_workspace(N) bytes of device scratch. */
 size_t tnl_march_rays_train_workspace(uint32_t N);
+/* >= this many bytes of workspace (one float per ray and step on top of the scan scratch) let the call record every sample's ray
+ * parameter during the counting traversal and emit the rows from it, warp per ray and coalesced, instead of traversing the
+ * occupancy grid a second time; bit-identical outputs. */
+size_t tnl_march_rays_train_workspace_fast(uint32_t N, uint32_t max_steps);
 int tnl_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
                          float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
                          const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,

@@ -72,10 +72,18 @@ def test_march_rays_train_bitexact(max_steps, dt_gamma):
     M = N * 256
     xyzs = torch.zeros(M, 3, device="cuda"); dirs = torch.zeros(M, 3, device="cuda"); deltas = torch.zeros(M, 2, device="cuda")
     rays = torch.empty(N, 3, dtype=torch.int32, device="cuda")
-    ws = torch.empty(lib.tnl_march_rays_train_workspace(N), dtype=torch.uint8, device="cuda")
-    _lib.call("tnl_march_rays_train", _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(bf), BOUND, dt_gamma, max_steps, N, CAS, H, M,
-              _lib.ptr(nears), _lib.ptr(fars), _lib.ptr(xyzs), _lib.ptr(dirs), _lib.ptr(deltas), _lib.ptr(rays),
-              _lib.ptr(counter), _lib.ptr(noises), _lib.ptr(ws), ws.numel(), _lib.stream())
+    # both forms of the second pass: re-traversal (small workspace) first, then emission from the recorded sample parameters;
+    # the outputs start as NaN (the call zero-fills the rows no ray owns) and must come out bit-identical
+    outs = []
+    for wsz in (lib.tnl_march_rays_train_workspace(N), lib.tnl_march_rays_train_workspace_fast(N, max_steps)):
+        xyzs.fill_(float("nan")); dirs.fill_(float("nan")); deltas.fill_(float("nan")); counter.zero_()
+        ws = torch.empty(wsz, dtype=torch.uint8, device="cuda")
+        _lib.call("tnl_march_rays_train", _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(bf), BOUND, dt_gamma, max_steps, N, CAS, H, M,
+                  _lib.ptr(nears), _lib.ptr(fars), _lib.ptr(xyzs), _lib.ptr(dirs), _lib.ptr(deltas), _lib.ptr(rays),
+                  _lib.ptr(counter), _lib.ptr(noises), _lib.ptr(ws), ws.numel(), _lib.stream())
+        outs.append([t.clone() for t in (xyzs, dirs, deltas, rays, counter)])
+    for a, b in zip(*outs):
+        assert torch.equal(a.view(torch.int32) if a.dtype == torch.float32 else a, b.view(torch.int32) if b.dtype == torch.float32 else b)
     x_o, d_o, l_o, r_o, c_o = orc.march_rays_train(o, d, BOUND, bits.numpy(), CAS, H, nears.cpu().numpy(),
                                                    fars.cpu().numpy(), noises.cpu().numpy(), M, dt_gamma, max_steps)
     assert np.array_equal(counter.cpu().numpy(), c_o)

@@ -31,6 +31,7 @@ SIGNATURES = {
     "tnl_morton3d_invert": (_int, [_vp, _u32, _vp, _vp]),
     "tnl_packbits": (_int, [_vp, _u32, _f32, _vp, _vp]),
     "tnl_march_rays_train_workspace": (_sz, [_u32]),
+    "tnl_march_rays_train_workspace_fast": (_sz, [_u32, _u32]),
     "tnl_march_rays_train": (_int, [_vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp,
                                     _vp, _vp, _vp, _vp, _sz, _vp]),
     "tnl_composite_rays_train_forward": (_int, [_vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp, _vp]),

@@ -216,7 +216,7 @@ __global__ void k_march_train_count(const float* __restrict__ rays_o, const floa
                                     const uint8_t* __restrict__ grid, float bound, float dt_gamma, uint32_t max_steps,
                                     uint32_t N, uint32_t C, uint32_t H, const float* __restrict__ nears,
                                     const float* __restrict__ fars, const float* __restrict__ noises,
-                                    int32_t* __restrict__ rays) {
+                                    int32_t* __restrict__ rays, float* __restrict__ ts) {
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     const MarchParams p = make_params(bound, dt_gamma, max_steps, C, H, grid);
@@ -226,8 +226,10 @@ __global__ void k_march_train_count(const float* __restrict__ rays_o, const floa
     t = __fmaf_rn(clampf(__fmul_rn(t, dt_gamma), p.dt_min, p.dt_max), noises[n], t);
     uint32_t num = 0;
     float x, y, z, dt;
+    float* tn = ts ? ts + (size_t)n * max_steps : nullptr;    // optional: the parameter of every sample, for k_march_train_emit
     while (t < far && num < max_steps) {
         if (march_probe(p, r, t, x, y, z, dt)) {
+            if (tn) tn[num] = t;
             ++num;
             t = __fadd_rn(t, dt);
         }
@@ -270,6 +272,43 @@ __global__ void k_march_train_write(const float* __restrict__ rays_o, const floa
             px += 3; pd += 3; pl += 2;
             ++step;
         }
+    }
+}
+
+// pass 2 without a second traversal: pass 1 recorded the parameter t of every sample (ts[n][k]); one warp per ray turns them into
+// positions / directions / deltas with the very operations of the traversal (same roundings => bit-identical rows) and writes
+// the ray's rows coalesced.  The occupancy grid is not touched again.
+__global__ void __launch_bounds__(256)
+k_march_train_emit(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                   uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* __restrict__ nears, const float* __restrict__ noises,
+                   const int32_t* __restrict__ rays, const float* __restrict__ ts, float* __restrict__ xyzs, float* __restrict__ dirs,
+                   float* __restrict__ deltas) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const uint32_t offset = (uint32_t)rays[3 * (size_t)n + 1];
+    const uint32_t num = (uint32_t)rays[3 * (size_t)n + 2];
+    if (num == 0 || offset + num > M) return;  // overflowing rays are dropped silently, as the reference (:416)
+    const MarchParams p = make_params(bound, dt_gamma, max_steps, C, H, nullptr);
+    const MarchRay r = load_ray(rays_o + 3 * (size_t)n, rays_d + 3 * (size_t)n);
+    float t0 = nears[n];
+    t0 = __fmaf_rn(clampf(__fmul_rn(t0, dt_gamma), p.dt_min, p.dt_max), noises[n], t0);      // last_t before the first sample
+    const float* tn = ts + (size_t)n * max_steps;
+    for (uint32_t k = lane; k < num; k += 32) {
+        const float t = tn[k];
+        const float dt = clampf(__fmul_rn(t, p.dt_gamma), p.dt_min, p.dt_max);
+        float last_t = t0;
+        if (k > 0) {
+            const float tp = tn[k - 1];
+            last_t = __fadd_rn(tp, clampf(__fmul_rn(tp, p.dt_gamma), p.dt_min, p.dt_max));
+        }
+        const size_t i = (size_t)offset + k;
+        xyzs[3 * i] = clampf(__fmaf_rn(t, r.dx, r.ox), -p.bound, p.bound);
+        xyzs[3 * i + 1] = clampf(__fmaf_rn(t, r.dy, r.oy), -p.bound, p.bound);
+        xyzs[3 * i + 2] = clampf(__fmaf_rn(t, r.dz, r.oz), -p.bound, p.bound);
+        dirs[3 * i] = r.dx; dirs[3 * i + 1] = r.dy; dirs[3 * i + 2] = r.dz;
+        deltas[2 * i] = dt;
+        deltas[2 * i + 1] = __fsub_rn(__fadd_rn(t, dt), last_t);
     }
 }
 
@@ -799,6 +838,12 @@ int tnl_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* b
 
 size_t tnl_march_rays_train_workspace(uint32_t N) { return sizeof(uint32_t) * (ceil_div(N, (uint32_t)kScanThreads) + 1); }
 
+// with room for one float per (ray, step) the second traversal is replaced by k_march_train_emit
+static size_t march_scan_bytes(uint32_t N) { return (tnl_march_rays_train_workspace(N) + 255) & ~(size_t)255; }
+size_t tnl_march_rays_train_workspace_fast(uint32_t N, uint32_t max_steps) {
+    return march_scan_bytes(N) + sizeof(float) * (size_t)N * max_steps;
+}
+
 int tnl_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound, float dt_gamma,
                          uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float* nears,
                          const float* fars, float* xyzs, float* dirs, float* deltas, int32_t* rays, int32_t* counter,
@@ -813,14 +858,20 @@ int tnl_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t
     }
     uint32_t* block_sums = static_cast<uint32_t*>(workspace);
     const uint32_t nb = ceil_div(N, (uint32_t)kScanThreads);
+    const bool fast = M > 0 && workspace_bytes >= tnl_march_rays_train_workspace_fast(N, max_steps);
+    float* ts = fast ? reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + march_scan_bytes(N)) : nullptr;
     k_march_train_count<<<ceil_div(N, kT), kT, 0, S(stream)>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H,
-                                                                nears, fars, noises, rays);
+                                                                nears, fars, noises, rays, ts);
     k_scan_block_sums<0><<<nb, kScanThreads, 0, S(stream)>>>(rays + 2, N, 3, block_sums);
     k_scan_of_sums<<<1, kScanThreads, 0, S(stream)>>>(block_sums, nb, counter, N, nullptr);
     k_scan_offsets<<<nb, kScanThreads, 0, S(stream)>>>(rays + 2, N, 3, block_sums, rays + 1);
     if (M > 0) {
-        k_march_train_write<<<ceil_div(N, kT), kT, 0, S(stream)>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N,
-                                                                    C, H, M, nears, fars, noises, rays, xyzs, dirs, deltas);
+        if (fast)
+            k_march_train_emit<<<ceil_div(N, 8u), 256, 0, S(stream)>>>(rays_o, rays_d, bound, dt_gamma, max_steps, N, C, H, M, nears, noises,
+                                                                       rays, ts, xyzs, dirs, deltas);
+        else
+            k_march_train_write<<<ceil_div(N, kT), kT, 0, S(stream)>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N,
+                                                                        C, H, M, nears, fars, noises, rays, xyzs, dirs, deltas);
         // rows no kept ray owns are zeros, as in the reference's zero-initialised buffers: the caller may pass uninitialised memory
         k_zero_unowned_rows<<<32, 256, 0, S(stream)>>>(rays, N, M, xyzs, 3, dirs, 3, deltas, 2);
     }

@@ -141,7 +141,9 @@ class _march_rays_train(Function):
             noises = torch.zeros(N, dtype=rays_o.dtype, device=dev)
         rays = torch.empty(N, 3, dtype=torch.int32, device=dev)
         lib = _lib.load()
-        ws = _workspace(lib.tnl_march_rays_train_workspace(N), dev)
+        # (one float per ray and step of scratch lets the call skip the second traversal; beyond 1 GiB the plain two-pass march)
+        need = lib.tnl_march_rays_train_workspace_fast(N, int(max_steps))
+        ws = _workspace(need if need <= (1 << 30) else lib.tnl_march_rays_train_workspace(N), dev)
 
         def run(M_, xyzs, dirs, deltas):
             call("tnl_march_rays_train", ptr(rays_o), ptr(rays_d), ptr(density_bitfield), float(bound), float(dt_gamma),
