@@ -207,11 +207,8 @@ template <typename Cfg>
 static int launch_fwd_sparse(const float* x, const float* yh, float* out, uint32_t n, uint32_t C, float* abs_sum, const int32_t* active,
                              const int32_t* clean, const int32_t* counts, uint32_t max_active, uint32_t max_clean, uint32_t parts,
                              cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_idwt_fwd<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_F);
-        attr_set = true;
-    }
+    // (per device, cheap: no process-wide "already set" flag -- a process may drive several devices)
+    cudaFuncSetAttribute(k_idwt_fwd<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_F);
     if (max_active > 0 && (parts & 1u))
         k_idwt_fwd<Cfg><<<max_active * (C / Cfg::CG), Cfg::NT, Cfg::SMEM_F, stream>>>(x, yh, out, (int)n, (int)C, 0, abs_sum,
                                                                                      reinterpret_cast<const int4*>(active), counts);
@@ -225,11 +222,8 @@ template <typename Cfg>
 static int launch_bwd_sparse(const float* g, float* g_x, float* g_yh, uint32_t n, uint32_t C, const float* yh, const float* reg_grad,
                              float reg_coef, const int32_t* active, const int32_t* clean, const int32_t* counts, uint32_t max_active,
                              uint32_t max_clean, uint32_t parts, float* abs_sum, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_idwt_bwd<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_B);
-        attr_set = true;
-    }
+    // (per device, cheap: no process-wide "already set" flag -- a process may drive several devices)
+    cudaFuncSetAttribute(k_idwt_bwd<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_B);
     if (max_active > 0 && (parts & 1u))
         k_idwt_bwd<Cfg><<<max_active * (C / Cfg::CG), Cfg::NT, Cfg::SMEM_B, stream>>>(g, g_x, g_yh, (int)n, (int)C, 0, yh, reg_grad, reg_coef,
                                                                                      0, reinterpret_cast<const int4*>(active), counts);
@@ -243,11 +237,8 @@ static int launch_bwd_sparse(const float* g, float* g_x, float* g_yh, uint32_t n
 template <typename Cfg>
 static int launch_fwd(const float* x, const float* yh, float* out, uint32_t n, uint32_t C, float* abs_sum,
                       cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_idwt_fwd<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_F);
-        attr_set = true;
-    }
+    // (per device, cheap: no process-wide "already set" flag -- a process may drive several devices)
+    cudaFuncSetAttribute(k_idwt_fwd<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_F);
     unsigned gx, gy, gz, rows;
     idwt_grid<Cfg>(n, C, kNumSM, gx, gy, gz, rows);
     k_idwt_fwd<Cfg><<<dim3(gx, gy, gz), Cfg::NT, Cfg::SMEM_F, stream>>>(x, yh, out, (int)n, (int)C, (int)rows, abs_sum, nullptr, nullptr);
@@ -257,11 +248,8 @@ static int launch_fwd(const float* x, const float* yh, float* out, uint32_t n, u
 template <typename Cfg>
 static int launch_bwd(const float* g, float* g_x, float* g_yh, uint32_t n, uint32_t C, const float* yh,
                       const float* reg_grad, float reg_coef, uint32_t plane0, uint32_t nplanes, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_idwt_bwd<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_B);
-        attr_set = true;
-    }
+    // (per device, cheap: no process-wide "already set" flag -- a process may drive several devices)
+    cudaFuncSetAttribute(k_idwt_bwd<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_B);
     unsigned gx, gy, gz, rows;
     idwt_grid<Cfg>(n, C, kNumSM, gx, gy, gz, rows);
     gz = nplanes;
