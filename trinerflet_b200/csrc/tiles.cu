@@ -184,35 +184,42 @@ __device__ __forceinline__ void allreduce_batch(const PeerPtrs& peers, float* mc
     }
 }
 
-// planes [3][R][R][C] (symmetric); grid (capacity of the tile list, row groups); the list length is read on the device
+// planes [3][R][R][C] (symmetric).  Work item w = (tile, group of T / 4 rows); a persistent grid strides over the items of the
+// tiles this rank owns (the list length is read on the device), so the kernel needs few SM slots and slips in beside the
+// scatter of the next plane (its stream has high priority).
 template <bool MC>
 __global__ void __launch_bounds__(256)
 k_tiles_allreduce(PeerPtrs peers, float* mc, const int32_t* __restrict__ tile_ids, const int32_t* __restrict__ count, int R, int C, int T,
                   int rank, int world, float scale) {
-    constexpr int U = 8;
-    const int tile = blockIdx.x;
-    if (tile >= __ldg(count) || tile % world != rank) return;
-    const int id = __ldg(tile_ids + tile);
+    constexpr int U = 8, GROUPS = 4;
+    const int n_tiles = __ldg(count);
     const int nt = R / T;
-    const int p = id / (nt * nt), ty = (id / nt) % nt, tx = id % nt;
     const int n4 = T * C / 4;                                   // 16-byte chunks per tile row
-    const int rows_per_cta = (T + gridDim.y - 1) / gridDim.y;
-    const int row0 = blockIdx.y * rows_per_cta;
-    const int nrows = min(T, row0 + rows_per_cta) - row0;
-    const int total = nrows * n4;
-    const size_t base = (((size_t)p * R + (size_t)ty * T + row0) * R + (size_t)tx * T) * C;
+    const int rows_per_group = (T + GROUPS - 1) / GROUPS;
     const size_t row_stride = (size_t)R * C;
-    for (int i0 = threadIdx.x; i0 < total; i0 += U * blockDim.x) {
-        size_t off[U];
-        bool ok[U];
+    // owned tiles: rank, rank + world, ...; item index over (owned tile, row group)
+    const int n_owned = n_tiles > rank ? (n_tiles - rank + world - 1) / world : 0;
+    for (int w = blockIdx.x; w < n_owned * GROUPS; w += gridDim.x) {
+        const int tile = rank + (w / GROUPS) * world;
+        const int grp = w % GROUPS;
+        const int id = __ldg(tile_ids + tile);
+        const int p = id / (nt * nt), ty = (id / nt) % nt, tx = id % nt;
+        const int row0 = grp * rows_per_group;
+        const int nrows = min(T, row0 + rows_per_group) - row0;
+        const int total = nrows * n4;
+        const size_t base = (((size_t)p * R + (size_t)ty * T + row0) * R + (size_t)tx * T) * C;
+        for (int i0 = threadIdx.x; i0 < total; i0 += U * blockDim.x) {
+            size_t off[U];
+            bool ok[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = i0 + u * blockDim.x;
-            ok[u] = i < total;
-            const int row = ok[u] ? i / n4 : 0, c4 = ok[u] ? i % n4 : 0;
-            off[u] = base + (size_t)row * row_stride + 4 * (size_t)c4;
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * blockDim.x;
+                ok[u] = i < total;
+                const int row = ok[u] ? i / n4 : 0, c4 = ok[u] ? i % n4 : 0;
+                off[u] = base + (size_t)row * row_stride + 4 * (size_t)c4;
+            }
+            allreduce_batch<MC, U>(peers, mc, off, ok, world, scale);
         }
-        allreduce_batch<MC, U>(peers, mc, off, ok, world, scale);
     }
 }
 
@@ -299,12 +306,12 @@ int tnl_tiles_allreduce(void* multicast, const void* const* peers, const int32_t
     PeerPtrs pp;
     TNL_ARG_CHECK(fill_peers(pp, peers, world), "world size must be 1..8 (one NVSwitch domain)");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const uint32_t blocks = min(ceil_div(capacity, world) * 4u, (uint32_t)kNumSM * 3u);      // persistent: a few CTAs per SM
     if (multicast)
-        k_tiles_allreduce<true><<<dim3(capacity, 4), 256, 0, s>>>(pp, static_cast<float*>(multicast), tile_ids, count, (int)R, (int)C, (int)T,
-                                                               (int)rank, (int)world, scale);
+        k_tiles_allreduce<true><<<blocks, 256, 0, s>>>(pp, static_cast<float*>(multicast), tile_ids, count, (int)R, (int)C, (int)T,
+                                                    (int)rank, (int)world, scale);
     else
-        k_tiles_allreduce<false><<<dim3(capacity, 4), 256, 0, s>>>(pp, nullptr, tile_ids, count, (int)R, (int)C, (int)T, (int)rank, (int)world,
-                                                                scale);
+        k_tiles_allreduce<false><<<blocks, 256, 0, s>>>(pp, nullptr, tile_ids, count, (int)R, (int)C, (int)T, (int)rank, (int)world, scale);
     return finish_launch("tiles_allreduce");
 }
 

@@ -63,7 +63,9 @@ class TrainStep:
                 self.exch = parallel.PeerGradExchange(model, world_size, self.reducer)
                 model.encoder.external_grad_buffer = self.exch.g_planes
                 model.encoder.scatter_plane_hook = self._exchange_plane_async
-                self._comm = torch.cuda.Stream()
+                # high priority: when SM slots free up the (small, persistent) exchange kernels are placed before the next wave of
+                # the scatter's CTAs, so the exchange of plane p really runs under the scatter of plane p + 1
+                self._comm = torch.cuda.Stream(priority=-1)
                 self.exchange_note = f"peer memory, {self.exch.mode} (own kernels: in place, fp32, one CUDA graph per step)"
             except Exception as ex:  # noqa: BLE001
                 if exchange == "peer":
