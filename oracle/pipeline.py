@@ -137,42 +137,3 @@ def cpu_config_benchmark(points=65536, C=16, R=512, S=8, hidden=64, iters=5, war
     return dict(points=points, points_per_s=points / med[0], fwd_bwd_seconds=med[0], idwt_fwd_seconds=med[1],
                 idwt_fwd_GBps=2 * P / med[1] / 1e9, sample_fwd_seconds=med[2], mlp_fwd_seconds=med[3], backward_seconds=med[4],
                 iters=iters, warmup=warmup, config=f"C={C} R={R} S={S} hidden={hidden} fp32")
-
-
-def timed_components(C, R, S, hidden, n_rays_full, scene_batch, bitfield, planes_sub, r_div, n_small, n_large, seed=0):
-    """Bounded-sample timing of one reference training step (fwd+bwd) on the CPU, extrapolated to the full workload:
-      (a) multilevel IDWT forward+backward on planes_sub of the 3 planes (batch entries are independent: exact x3/planes_sub)
-          at resolution R/r_div with the same number of levels (cost is proportional to the pixel count: x r_div^2);
-      (b) march + sample + MLP + composite + loss, forward+backward down to the plane gradients, on n_small and
-          n_large rays against full-size planes; a linear fit t = a + b*n gives the time at n_rays_full.
-    Returns dict(step_seconds, idwt_seconds, rays_seconds, detail...)."""
-    g = torch.Generator().manual_seed(seed)
-    L = int(round(np.log2(S)))
-    n0 = R // S
-    n0 = max(n0 // r_div, 8)
-    pf = (0.1 * torch.randn(planes_sub, C, n0, n0, generator=g)).requires_grad_(True)
-    coefs = [(0.05 * torch.randn(planes_sub, C, 3, n0 * 2 ** l, n0 * 2 ** l, generator=g)).requires_grad_(True) for l in range(L)]
-    t0 = time.perf_counter()
-    planes = ow.build_planes(pf, coefs)
-    planes.backward(torch.ones_like(planes))
-    t_idwt_sub = time.perf_counter() - t0
-    t_idwt = t_idwt_sub * (3.0 / planes_sub) * (R // S / n0) ** 2
-    del planes, pf, coefs
-    planes = torch.randn(3, C, R, R, generator=g).mul_(0.1).requires_grad_(True)
-    weights = [w.requires_grad_(True) for w in of.init_mlp_weights(C, hidden, hidden, gen=g)]
-    rays_o, rays_d, target = scene_batch
-    times, Ms = [], []
-    for n in (n_small, n_large):
-        noises = torch.rand(n, generator=g).numpy()
-        planes.grad = None
-        t0 = time.perf_counter()
-        image, ws, depth, M = render_train(planes, weights, rays_o[:n], rays_d[:n], bitfield, noises)
-        loss = ((image - target[:n]) ** 2).mean(-1).mean()
-        loss.backward()
-        times.append(time.perf_counter() - t0)
-        Ms.append(M)
-    b = (times[1] - times[0]) / max(n_large - n_small, 1)
-    a = max(times[0] - b * n_small, 0.0)
-    t_rays = a + b * n_rays_full
-    return dict(step_seconds=t_idwt + t_rays, idwt_seconds=t_idwt, rays_seconds=t_rays, idwt_sub_seconds=t_idwt_sub,
-                planes_sub=planes_sub, r_div=R // S // n0, n_small=n_small, n_large=n_large, t_small=times[0], t_large=times[1], M_small=Ms[0], M_large=Ms[1])
