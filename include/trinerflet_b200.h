@@ -194,6 +194,15 @@ int tnl_sample_planes_backward_plane(const void* g_feat, int feat_fp16, const fl
                                      float inv_bound, int fp16_coords, const int32_t* n_valid, const int32_t* perm,
                                      float* g_planes, uint32_t plane, tnl_stream_t stream);
 
+/* Gradient with respect to the sample positions (grid_sampler_2d_backward w.r.t. the grid, chained through u = xyz * inv_bound):
+ * g_xyz [M][3] = d(sum g_feat * feat)/d(xyz), written (not accumulated).  The derivative is zero along an axis whose projected
+ * coordinate lies on or beyond the plane border (ATen's clip_coordinates_set_grad), and the fp16 rounding of fp16_coords is
+ * passed straight through, as autograd does for a dtype cast.  fp32 features only.  Replaces what autograd derives from the
+ * F.grid_sample call of super_resolution/threestudio/models/triplaneencoder/triplane_encoder.py:262 when the positions
+ * require grad (analytic normals, super_resolution/threestudio/models/geometry/implicit_volume.py:218-226). */
+int tnl_sample_planes_backward_coords(const float* g_feat, const float* planes, const float* xyz, uint32_t M, uint32_t R,
+                                      uint32_t C, float inv_bound, int fp16_coords, float* g_xyz, tnl_stream_t stream);
+
 /* Spatial binning of sample points: perm[i] = row of the i-th point in the order of a G^3 Morton grid over
  * [-bound, bound]^3 (rows >= *n_valid last).  Kernels taking `perm` visit points in that order, which makes the
  * plane gathers / gradient scatters of neighbouring threads hit the same texels (L2 locality); per-point results

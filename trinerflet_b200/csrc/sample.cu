@@ -225,6 +225,67 @@ k_sample_bwd4_plane(const void* __restrict__ g_feat_, const float* __restrict__ 
     if (t.x1ok && t.y1ok) red_add_v4(base + dy + dx, g, t.se);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Gradient with respect to the sample POSITIONS: grid_sampler_2d_backward w.r.t. the grid, chained through the projection
+// u = xyz * inv_bound.  Callers that differentiate the field in space need it (the super_resolution application's analytic
+// normals, super_resolution/threestudio/models/geometry/implicit_volume.py:218-226, through the F.grid_sample call of
+// super_resolution/threestudio/models/triplaneencoder/triplane_encoder.py:262); the NeRF training step never does.
+// Block = 32 points x 3 planes.  Thread (point, plane) walks the C channels of its four corner texels (contiguous 4*C-byte
+// runs, every sector fully used) with the term order of ATen's kernel; the three planes of a point meet in shared memory
+// and thread (point, axis) writes one component, so the result is deterministic and needs no atomics.
+// ------------------------------------------------------------------------------------------------
+constexpr int XG_PPB = 32;
+
+__device__ __forceinline__ float dot4(const float4 a, const float4 b) {
+    return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
+}
+
+__global__ void __launch_bounds__(3 * XG_PPB)
+k_sample_xyz_grad(const float* __restrict__ g_feat, const float* __restrict__ planes, const float* __restrict__ xyz,
+                  uint32_t M, int R, int C, float inv_bound, int fp16_coords, float* __restrict__ g_xyz) {
+    __shared__ float s_uv[XG_PPB][3][2];
+    const int p = threadIdx.x % 3, lp = threadIdx.x / 3;
+    const uint32_t m = blockIdx.x * XG_PPB + lp;
+    float gu = 0.f, gv = 0.f;
+    if (m < M) {
+        float gx, gy, mx, my;
+        plane_coords(xyz, m, p, inv_bound, fp16_coords, gx, gy);
+        const float ix = to_pixel_grad(gx, R, mx), iy = to_pixel_grad(gy, R, my);
+        const float fx = floorf(ix), fy = floorf(iy);
+        const int x0 = (int)fx, y0 = (int)fy;
+        const bool x1ok = x0 + 1 <= R - 1, y1ok = y0 + 1 <= R - 1;
+        const float wx0 = (fx + 1.0f) - ix, wx1 = ix - fx, wy0 = (fy + 1.0f) - iy, wy1 = iy - fy;
+        const int cq_per = C >> 2;
+        const float4* base = reinterpret_cast<const float4*>(planes + (((size_t)p * R + y0) * R + x0) * C);
+        const float4* go = reinterpret_cast<const float4*>(g_feat + ((size_t)m * 3 + p) * C);
+        const size_t dx = (size_t)cq_per, dy = (size_t)R * cq_per;
+        for (int q = 0; q < cq_per; ++q) {
+            const float4 g = __ldg(go + q);
+            const float nw = dot4(__ldg(base + q), g);
+            const float ne = x1ok ? dot4(__ldg(base + dx + q), g) : 0.f;
+            const float sw = y1ok ? dot4(__ldg(base + dy + q), g) : 0.f;
+            const float se = (x1ok && y1ok) ? dot4(__ldg(base + dy + dx + q), g) : 0.f;
+            gu -= nw * wy0; gv -= nw * wx0;
+            gu += ne * wy0; gv -= ne * wx1;
+            gu -= sw * wy1; gv += sw * wx0;
+            gu += se * wy1; gv += se * wx1;
+        }
+        gu *= mx;
+        gv *= my;
+    }
+    s_uv[lp][p][0] = gu;
+    s_uv[lp][p][1] = gv;
+    __syncthreads();
+    if (m < M) {
+        // axis a = p of this thread: x <- u of planes 0, 1;  y <- v of plane 1, u of plane 2;  z <- v of planes 0, 2
+        const float s = (p == 0) ? s_uv[lp][0][0] + s_uv[lp][1][0]
+                      : (p == 1) ? s_uv[lp][1][1] + s_uv[lp][2][0]
+                                 : s_uv[lp][0][1] + s_uv[lp][2][1];
+        g_xyz[3 * (size_t)m + p] = s * inv_bound;
+    }
+}
+
 template <int TPP>
 static void launch_fwd8(const float* planes, const float* xyz, uint32_t M, uint32_t R, float inv_bound, int fp16_coords,
                         const int32_t* n_valid, const int32_t* perm, void* feat, int half, cudaStream_t s) {
@@ -317,6 +378,17 @@ int tnl_sample_planes_backward_plane(const void* g_feat, int feat_fp16, const fl
     else if (C == 32) launch_bwd4_plane<8>(g_feat, feat_fp16, xyz, M, R, inv_bound, fp16_coords, n_valid, perm, g_planes, (int)plane, st);
     else launch_bwd4_plane<12>(g_feat, feat_fp16, xyz, M, R, inv_bound, fp16_coords, n_valid, perm, g_planes, (int)plane, st);
     return finish_launch("sample_planes_backward_plane");
+}
+
+int tnl_sample_planes_backward_coords(const float* g_feat, const float* planes, const float* xyz, uint32_t M, uint32_t R,
+                                      uint32_t C, float inv_bound, int fp16_coords, float* g_xyz, tnl_stream_t stream) {
+    if (M == 0) return 0;
+    TNL_ARG_CHECK(g_feat && planes && xyz && g_xyz, "null pointer");
+    TNL_ARG_CHECK(C >= 4 && C % 4 == 0 && R >= 2, "C must be a multiple of 4, R >= 2");
+    TNL_ARG_CHECK(((uintptr_t)planes & 15) == 0 && ((uintptr_t)g_feat & 15) == 0, "planes/g_feat must be 16-byte aligned");
+    k_sample_xyz_grad<<<ceil_div(M, (uint32_t)XG_PPB), 3 * XG_PPB, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        g_feat, planes, xyz, M, (int)R, (int)C, inv_bound, fp16_coords, g_xyz);
+    return finish_launch("sample_planes_backward_coords");
 }
 
 }  // extern "C"

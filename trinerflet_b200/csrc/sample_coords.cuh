@@ -18,6 +18,17 @@ __device__ __forceinline__ float to_pixel(float g, int R) {
     return fminf((float)(R - 1), fmaxf(v, 0.0f));
 }
 
+// to_pixel plus d(pixel)/d(g): ATen's clip_coordinates_set_grad -- the derivative is (R-1)/2 strictly inside the plane and 0
+// on or beyond its border (grid_sampler_2d_backward, padding_mode='border', align_corners=True).
+__device__ __forceinline__ float to_pixel_grad(float g, int R, float& dg) {
+    const float hi = (float)(R - 1);
+    const float v = ((g + 1.0f) * 0.5f) * hi;
+    if (!(v > 0.0f)) { dg = 0.0f; return 0.0f; }   // also NaN, which to_pixel maps to texel 0
+    if (v >= hi) { dg = 0.0f; return hi; }
+    dg = 0.5f * hi;
+    return v;
+}
+
 __device__ __forceinline__ Tap make_tap(float gx, float gy, int R) {
     const float ix = to_pixel(gx, R), iy = to_pixel(gy, R);
     const float fx = floorf(ix), fy = floorf(iy);
