@@ -1,5 +1,5 @@
 """CPU: host-side logic -- channels-last parameter storage with reference-compatible logical shapes / state-dict keys,
-loading a reference-layout checkpoint, shard arithmetic, synthetic scene determinism, and the ray-sharded gradient
+loading a reference-layout checkpoint and a Trainer checkpoint file, shard arithmetic, synthetic scene determinism, and the ray-sharded gradient
 all-reduce on world_size = 2 (gloo)."""
 import os
 
@@ -52,6 +52,59 @@ def test_load_reference_layout_checkpoint_keeps_channels_last():
     opt.step()
     assert is_cl_coefs(net.encoder.planes_features_wavelet_coefs[1])            # optimizer keeps the strides
     assert len(net.get_params(1e-2)) == 4
+
+
+def test_trainer_checkpoint_file_round_trip(tmp_path):
+    """the file Trainer.save_checkpoint(full=True) writes and the sequence Trainer.load_checkpoint reads it with
+    (reconstruction/nerf/utils.py:1390-1430, :1466-1532): model state dict, mean_count / mean_density, optimizer and scaler
+    state, through torch.save / torch.load; plus the 'best' flavour, which drops density_grid (:1450-1452)"""
+    from trinerflet_b200.optim import FusedAdam
+    g = torch.Generator().manual_seed(3)
+    src = _net(C=16, R=64, S=2)
+    with torch.no_grad():
+        for p in src.parameters():
+            p.copy_(0.1 * torch.randn(p.shape, generator=g))
+        src.density_grid.copy_(torch.rand(src.density_grid.shape, generator=g))
+        src.density_bitfield.copy_(torch.randint(0, 256, src.density_bitfield.shape, generator=g, dtype=torch.uint8))
+        src.step_counter.copy_(torch.randint(0, 4096, src.step_counter.shape, generator=g, dtype=torch.int32))
+    src.mean_count, src.mean_density = 1234, 0.0625
+    opt = torch.optim.Adam(src.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15)
+    for p in src.parameters():
+        p.grad = torch.randn(p.shape, generator=g)
+    opt.step()
+    scaler_state = {"scale": 32768.0, "growth_factor": 2.0, "backoff_factor": 0.5, "growth_interval": 2000, "_growth_tracker": 7}
+    state = {"epoch": 3, "global_step": 1200, "stats": {"loss": [0.1], "checkpoints": []},
+             "mean_count": src.mean_count, "mean_density": src.mean_density,
+             "optimizer": opt.state_dict(), "scaler": scaler_state, "model": src.state_dict()}
+    path = tmp_path / "ngp_ep0003.pth"
+    torch.save(state, path)
+
+    ckpt = torch.load(path, map_location="cpu", weights_only=False)
+    dst = _net(C=16, R=64, S=2)
+    gen0 = dst.bitfield_generation
+    missing, unexpected = dst.load_state_dict(ckpt["model"], strict=False)          # :1482
+    assert not missing and not unexpected
+    dst.mean_count, dst.mean_density = ckpt["mean_count"], ckpt["mean_density"]     # :1491-1495
+    assert dst.bitfield_generation > gen0                # a loaded occupancy grid invalidates work-lists built from the old one
+    assert dst.mean_count == 1234 and dst.mean_density == 0.0625
+    for (k, a), (_, b) in zip(src.state_dict().items(), dst.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert is_cl_planes(dst.encoder.planes_features) and all(is_cl_coefs(p) for p in dst.encoder.planes_features_wavelet_coefs)
+    # the optimizer the fast path uses accepts the torch.optim.Adam state of the file (:1512)
+    fused = FusedAdam(dst.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15)
+    fused.load_state_dict(ckpt["optimizer"])
+    st_src, st_dst = opt.state_dict()["state"], fused.state_dict()["state"]
+    assert st_src.keys() == st_dst.keys()
+    for k in st_src:
+        assert torch.equal(st_src[k]["exp_avg"], st_dst[k]["exp_avg"]) and float(st_src[k]["step"]) == float(st_dst[k]["step"])
+
+    best = dict(state, model={k: v for k, v in src.state_dict().items() if k != "density_grid"})
+    torch.save(best, tmp_path / "best.pth")
+    ckpt = torch.load(tmp_path / "best.pth", map_location="cpu", weights_only=False)
+    dst = _net(C=16, R=64, S=2)
+    missing, unexpected = dst.load_state_dict(ckpt["model"], strict=False)
+    assert missing == ["density_grid"] and not unexpected
+    assert torch.equal(dst.density_bitfield, src.density_bitfield) and float(dst.density_grid.abs().sum()) == 0.0
 
 
 def test_unsupported_options_fail_loudly():
