@@ -28,7 +28,7 @@ def test_state_dict_contract(golden_dir):
     assert enc.planes_features.shape == (3, 16, 32, 32) and is_cl_planes(enc.planes_features)
     assert [tuple(p.shape) for p in enc.planes_features_wavelet_coefs] == [(3, 16, 3, 32, 32), (3, 16, 3, 64, 64)]
     assert all(is_cl_coefs(p) for p in enc.planes_features_wavelet_coefs)
-    assert all(float(p.abs().sum()) == 0 for p in enc.planes_features_wavelet_coefs)   # zero-init (:220)
+    assert all(float(p.detach().abs().sum()) == 0 for p in enc.planes_features_wavelet_coefs)   # zero-init (:220)
     assert net.cascade == 2 and net.density_grid.shape == (2, 128 ** 3) and net.density_bitfield.shape == (2 * 128 ** 3 // 8,)
     assert enc.output_dim == 48 and net.in_dim == 48 and net.sigma_net[0].weight.shape == (64, 48)
     assert net.color_net[0].weight.shape == (64, 31) and net.color_net[2].weight.shape == (3, 64)
