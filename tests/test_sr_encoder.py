@@ -129,6 +129,12 @@ def test_against_the_reference_module_live(emu):
     with torch.no_grad():
         assert tuple(ours.get_planes().shape) == tuple(theirs.get_planes().shape) == (3, 8, 32, 32)
         assert rel_l2(ours(x), theirs(x)) <= sr_cases.TOL
+    # get_grid_features (:371-413): the lattice, its axis permutation and the features on it
+    with torch.no_grad():
+        lb_a, feat_a, grid_a = theirs.get_grid_features(6)
+        lb_b, feat_b, grid_b = ours.get_grid_features(6)
+    assert lb_a == lb_b and torch.equal(grid_a, grid_b) and tuple(feat_a.shape) == tuple(feat_b.shape) == (6, 6, 6, 24)
+    assert rel_l2(feat_b, feat_a) <= sr_cases.TOL
     G.randomise_(ours, gen)
     theirs.load_state_dict(ours.state_dict(), strict=True)
     with torch.no_grad():
