@@ -3,7 +3,6 @@ reference's own fp32 results (tests/golden/sr_encoder_fp32.npz) and the oracle (
 sizes, fp32 at the plane size of the reference's configs (super_resolution/configs/triplane-sr100_400_2.yaml: 16 channels, 1024^2, wavelet scale 16,
 low_res_scale 4)).  The same checks run on CPU over the host build of the kernels in tests/test_sr_encoder.py."""
 import pytest
-import torch
 
 from tests import sr_cases
 
