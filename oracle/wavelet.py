@@ -206,6 +206,30 @@ def build_planes(planes_features, coefs, wave="bior6.8"):
     return x
 
 
+def build_planes_limited(planes_features, coefs, max_res=-1, max_scale=-1, get_all_resolutions=False, wave="bior6.8"):
+    """TriPlaneVolume.build_planes (triplane_encoder.py:364-405) with its optional arguments, as the reference's tooling calls it
+    (save_triplane, nerf/utils.py:1649; get_grid_features, triplane_encoder.py:500): the level loop STOPS at the first level
+    whose input side has reached max_res or whose accumulated scale has reached max_scale (:380-383; the zero-coefficient
+    continuation is commented out there), so the planes come back at that coarser side; get_all_resolutions collects the input
+    of every level visited and the final planes (:377-378, :397-398 -- after a stop the last entry appears twice).
+    -> (planes, all_res)"""
+    pad = WAVELETS[wave]["pad"]
+    x, all_res, current_scale = planes_features, [], 1
+    for yh in coefs:
+        if get_all_resolutions:
+            all_res.append(x)
+        yl = 2 * x
+        if (max_res > 0 and min(x.shape[2:]) >= max_res) or (max_scale > 0 and current_scale >= max_scale):
+            break
+        yl = F.pad(yl, (pad, pad, pad, pad))
+        yh = F.pad(yh, (pad, pad, pad, pad))
+        x = sfb2d(yl, yh, wave)
+        current_scale *= 2
+    if get_all_resolutions:
+        all_res.append(x)
+    return x, all_res
+
+
 def idwt_level_closed_form_1d(x, d, g0, g1):
     """Closed form of one padded 1-D synthesis step, pure Python, tiny inputs:
     y[i] = sum_m 2*x[m]*g0[i+8-2m] + d[m]*g1[i+8-2m],  0 <= i+8-2m < 18,  i in [0, 2n)."""

@@ -486,13 +486,40 @@ class TriPlaneVolume(nn.Module):
         return planes
 
     def get_planes(self, max_res=-1, max_scale=-1, get_all_resolutions=False):
-        if max_res > 0 or max_scale > 0 or get_all_resolutions:
-            raise NotImplementedError("partial-resolution plane queries are not on the training/render hot path")
         if self.last_used_planes is not None:
-            return self.last_used_planes
+            return self.last_used_planes               # whatever the arguments, as the reference (:409-410)
+        if max_res > 0 or max_scale > 0 or get_all_resolutions:
+            return self._get_planes_limited(max_res, max_scale, get_all_resolutions)
         planes = self.build_planes()
+        if isinstance(planes, nn.Parameter):           # no wavelet levels: cache an alias (assigning a Parameter would register it)
+            planes = planes.view_as(planes)
         self.last_used_planes = planes
         return planes
+
+    def _get_planes_limited(self, max_res, max_scale, get_all_resolutions):
+        """The coarser / per-level readings of build_planes (:376-398), used by the reference's tooling (save_triplane,
+        nerf/utils.py:1649; get_grid_features, :500), not by a training step: the level loop stops at the first level whose input
+        side has reached `max_res` or whose accumulated upscale factor has reached `max_scale`, and the planes come back at that
+        side; `get_all_resolutions` returns the input of every level visited and the final planes (after a stop the last entry
+        appears twice, as in the reference).  Dense, level by level."""
+        x, all_res, scale = self.planes_features, [], 1
+        if self.inner_wavelet_scale > 1:
+            for yh in self.planes_features_wavelet_coefs:
+                if get_all_resolutions:
+                    all_res.append(x)
+                if (max_res > 0 and min(x.shape[2:]) >= max_res) or (max_scale > 0 and scale >= max_scale):
+                    break
+                x = build_planes(x, [yh])
+                scale *= 2
+            if get_all_resolutions:
+                all_res.append(x)
+        if isinstance(x, nn.Parameter):                # stopped before the first level: cache an alias, not the Parameter itself
+            x = x.view_as(x)
+            if get_all_resolutions:
+                all_res[-1] = x
+        self.last_used_planes = x
+        self._last_abs_sums = None
+        return all_res if get_all_resolutions else x
 
     def wavelet_l1(self, lam, abs_sums=None):
         """lam * (sum_l mean|yh_l| * numel_l / numel_all) / L -- the regulariser of nerf/utils.py:640-655 (unweighted
@@ -507,6 +534,8 @@ class TriPlaneVolume(nn.Module):
             if self.last_used_planes is None or getattr(self, "_last_abs_sums", None) is None:
                 self.get_planes()
             abs_sums = self._last_abs_sums
+            if abs_sums is None:      # the cached planes came from a band-limited query, which keeps no |yh| sums
+                abs_sums = torch.stack([v.abs().sum() for v in feats])
         total = sum(v.numel() for v in feats)
         return lam * abs_sums.sum() / (total * len(feats))
 
@@ -517,6 +546,23 @@ class TriPlaneVolume(nn.Module):
             lbound = self.lbound
         feat = sample_planes(plane_features, coordinates, lbound, n_valid=n_valid)
         return feat.view(feat.shape[0], 3, self.number_of_features)
+
+    def get_grid_features(self, grid_res, plane_features=None, grid=None):
+        """:485-512 -- features on a regular grid_res^3 lattice of [-lbound, lbound]^3 (axes permuted to (z, x, y) as the
+        reference does); the planes default to the first level whose side reaches 2 * grid_res."""
+        if grid is None:
+            axis = torch.arange(grid_res)
+            gx, gy, gz = torch.meshgrid(axis, axis, axis, indexing='xy')
+            grid = torch.stack([gx, gy, gz], dim=-1) / (grid_res - 1)
+        assert grid.max() <= 1 and grid.min() >= 0
+        grid = 2 * self.lbound * grid - self.lbound
+        grid = grid[..., [2, 0, 1]]
+        if plane_features is None:
+            plane_features = self.get_planes(2 * grid_res)
+        grid = grid.to(device=plane_features.device, dtype=plane_features.dtype)
+        shape = grid.shape
+        feats = self.sample_from_planes(grid.reshape(-1, 3), plane_features=plane_features)
+        return self.lbound, feats.reshape(*shape[:-1], -1), grid
 
     def forward(self, coordinates, bound, n_valid=None, perm=None, half_out=False):
         """coordinates [M,3] in [-bound, bound] -> features [M, 3C] (index p*C + c); fp32 as the reference's
