@@ -149,3 +149,75 @@ def test_reference_update_extra_state_and_mark_untrained_grid_over_the_dropin_mo
         m.density_grid.zero_()
         m.mark_untrained_grid(poses, sc.intrinsics)
     assert torch.equal(ref.density_grid, ours.density_grid) and int((ours.density_grid < 0).sum()) > 0
+
+
+# one stage of the README command (/root/reference/README.md:46), scaled down and without --fp16 (the host build computes fp32)
+CLI = ("main_nerf.py --path data --workspace out --cuda_ray --bound 1.5 --scale 1 --dt_gamma 0 --iters 1000 --num_rays 300 "
+       "--background_color 0 --triplane_wavelet --triplane_channels 16 --triplane_wavelet_levels 2 --triplane_resolution 128 "
+       "--wavelet_regularization 0.2 --downscale 1 --ckpt latest_model --ema_decay -1 --training_evaluate_test --warmup_steps 0 "
+       "--fast_training --max_steps 256")
+STAGED = ['iters', 'num_rays', 'triplane_resolution', 'triplane_wavelet_levels', 'downscale', 'warmup_steps', 'lr',
+          'wavelet_regularization', 'upscale_ratio_bound', 'upscale_levels']                     # main_nerf.py:168-170
+PASSED_TO_NERF = ['triplane_channels', 'triplane_resolution', 'triplane_wavelet_levels', 'wavelet_type', 'hidden_dim',
+                  'hidden_dim_color', 'hidden_dim_bg', 'learn_rotation_axis', 'dropout', 'inner_bound', 'lbound_auto_scale',
+                  'upscale_ratio_bound', 'upscale_levels', 'density_blob_scale', 'density_blob_std', 'mlp_weight_decay',
+                  'wavelet_base_resolution', 'nerfacc_renderer']                                  # main_nerf.py:44-58
+
+
+def test_reference_trainer_train_step_from_its_own_command_line(ref_modules, monkeypatch):
+    """The reference's option parser (run_utils.get_params) on a README-shaped command line, its model construction
+    (main_nerf.py:44-72) and its Trainer.train_step (nerf/utils.py:532-679: render with **vars(opt), MSE, the wavelet
+    regulariser expression) -- all unmodified -- over (a) the reference NeRFNetwork on the drop-in modules and (b) this
+    package's NeRFNetwork built from the SAME keyword arguments; then the fast path INTEGRATION.md offers in its place,
+    TrainStep.forward_backward, on the same rays.  Loss and every parameter gradient must agree."""
+    import argparse
+    from trinerflet_b200 import scene, trainer as our_trainer
+    from trinerflet_b200.network import NeRFNetwork as OurNet
+    renderer, network = ref_modules
+    run_utils = importlib.import_module("run_utils")
+    utils = importlib.import_module("nerf.utils")
+    assert run_utils.__file__.startswith(REF) and utils.__file__.startswith(REF)
+    monkeypatch.setattr(sys, "argv", CLI.split())
+    opt = run_utils.get_params()
+    for key in STAGED:                                                   # run(): one stage (main_nerf.py:190-199)
+        vars(opt)[key] = vars(opt)[key][0]
+    assert opt.triplane_wavelet and opt.cuda_ray and opt.wavelet_regularization == 0.2 and opt.patch_size == 1
+    extra = {k: vars(opt)[k] for k in PASSED_TO_NERF}
+    build = dict(encoding="triplane_wavelet", bound=opt.bound, cuda_ray=opt.cuda_ray, density_scale=opt.density_scale,
+                 min_near=opt.min_near, density_thresh=opt.density_thresh, bg_radius=opt.bg_radius, **extra)
+    ref, ours, fast = network.NeRFNetwork(**build), OurNet(**build), OurNet(**build)
+    scene.init_model_(ours, seed=0)
+    with torch.no_grad():
+        for p in ours.encoder.planes_features_wavelet_coefs:            # non-zero detail coefficients: the regulariser has a gradient
+            p.copy_(0.05 * torch.randn(p.shape, generator=torch.Generator().manual_seed(5)))
+    grid = scene.ball_density_grid(1.5, 0.75)
+    for m in (ref, ours, fast):
+        if m is not ours:
+            m.load_state_dict(ours.state_dict(), strict=True)
+        m.density_grid.copy_(grid)
+        m.density_bitfield.copy_(scene.packbits_cpu(grid, 0.5))
+        m.mean_density = float(grid.clamp(min=0).mean())
+        m.iter_density = 16
+        m.train()
+    sc = scene.make_scene()
+    ro, rd, tgt = scene.sample_batch(sc, opt.num_rays, torch.Generator().manual_seed(0))
+    data = {"rays_o": ro.unsqueeze(0), "rays_d": rd.unsqueeze(0), "images": tgt.unsqueeze(0)}
+    results = []
+    for m in (ref, ours):
+        me = argparse.Namespace(model=m, opt=opt, criterion=torch.nn.MSELoss(reduction='none'), error_map=None, nerfacc_renderer=None)
+        torch.manual_seed(11)
+        pred, gt, loss, aux = utils.Trainer.train_step(me, {k: v.clone() for k, v in data.items()})
+        loss.backward()
+        results.append((pred.detach(), float(loss.detach()), aux, [p.grad.clone() for p in m.parameters()]))
+    (pred_r, loss_r, aux_r, g_r), (pred_o, loss_o, aux_o, g_o) = results
+    assert aux_r.keys() == aux_o.keys() == {"mse", "wavelet_reg"} and aux_r["wavelet_reg"] > 0
+    assert torch.equal(pred_r, pred_o) and loss_r == loss_o
+    for a, b in zip(g_r, g_o):
+        assert torch.equal(a, b)
+    # the replacement for train_step + backward: same rays, same jitter draw
+    step = our_trainer.TrainStep(fast, opt, None)
+    torch.manual_seed(11)
+    loss_f = step.forward_backward(ro, rd, tgt, update_grid=False)
+    assert abs(float(loss_f) - loss_r) <= 1e-6 * abs(loss_r)
+    for p, g in zip(fast.parameters(), g_r):
+        assert float((p.grad - g).norm() / g.norm().clamp_min(1e-30)) <= 1e-5
