@@ -36,9 +36,10 @@ def install(monkeypatch):
             monkeypatch.setattr(mod, "ptr", _ptr)
         if getattr(mod, "stream", None) is real_stream:
             monkeypatch.setattr(mod, "stream", _stream)
-    from trinerflet_b200 import raymarching, triplane_encoder
+    from trinerflet_b200 import optim, raymarching, triplane_encoder
     monkeypatch.setattr(raymarching, "_cuda_f32", lambda t: t.contiguous().float())
     monkeypatch.setattr(triplane_encoder, "_require_cuda_f32", lambda t, what: None)
+    monkeypatch.setattr(optim, "_require_cuda_f32", lambda p: None)
     monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)      # wrappers that move stray CPU inputs
     monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)   # needs a driver otherwise
     return so

@@ -221,3 +221,73 @@ def test_reference_trainer_train_step_from_its_own_command_line(ref_modules, mon
     assert abs(float(loss_f) - loss_r) <= 1e-6 * abs(loss_r)
     for p, g in zip(fast.parameters(), g_r):
         assert float((p.grad - g).norm() / g.norm().clamp_min(1e-30)) <= 1e-5
+
+
+def test_reference_epoch_loop_against_the_fast_path(ref_modules, monkeypatch):
+    """Four optimizer steps of the reference's Trainer.train_one_epoch2 (nerf/utils.py:1115-1177: shuffle_data, select_batch,
+    reset_cahce / get_planes, train_step, scaler.scale(loss).backward(), scaler.step(optimizer), LambdaLR(decay_function)),
+    unmodified, over this package's NeRFNetwork -- against the loop INTEGRATION.md describes: the same batches through
+    TrainStep.step with FusedAdam and the same schedule.  The two parameter trajectories must stay together."""
+    import argparse
+    import functools
+    from trinerflet_b200 import scene, trainer as our_trainer
+    from trinerflet_b200.network import NeRFNetwork as OurNet
+    from trinerflet_b200.optim import FusedAdam
+    run_utils = importlib.import_module("run_utils")
+    utils = importlib.import_module("nerf.utils")
+    monkeypatch.setattr(sys, "argv", (CLI + " --update_extra_interval 1000 --warmup_steps 2").split())
+    opt = run_utils.get_params()
+    for key in STAGED:
+        vars(opt)[key] = vars(opt)[key][-1]
+    build = dict(encoding="triplane_wavelet", bound=opt.bound, cuda_ray=opt.cuda_ray, density_scale=opt.density_scale,
+                 min_near=opt.min_near, density_thresh=opt.density_thresh, bg_radius=opt.bg_radius,
+                 **{k: vars(opt)[k] for k in PASSED_TO_NERF})
+    theirs_loop, fast = OurNet(**build), OurNet(**build)
+    scene.init_model_(theirs_loop, seed=0)
+    fast.load_state_dict(theirs_loop.state_dict(), strict=True)
+    grid = scene.ball_density_grid(1.5, 0.75)
+    for m in (theirs_loop, fast):
+        m.density_grid.copy_(grid)
+        m.density_bitfield.copy_(scene.packbits_cpu(grid, 0.5))
+        m.mean_density = float(grid.clamp(min=0).mean())
+        m.iter_density = 16
+        m.mark_bitfield_changed()
+    sc = scene.make_scene()
+    n_steps = 4
+    ro, rd, tgt = scene.sample_batch(sc, n_steps * opt.num_rays, torch.Generator().manual_seed(2))
+    all_data = {"rays_o": ro.view(1, -1, 3), "rays_d": rd.view(1, -1, 3), "images": tgt.view(1, -1, 3)}    # collate_all layout [B, N, C]
+    sched = lambda optimizer: torch.optim.lr_scheduler.LambdaLR(optimizer, lambda it: utils.decay_function(it, opt))   # main_nerf.py:131
+
+    # (a) the reference's loop, its own optimizer construction (main_nerf.py:119)
+    optimizer = torch.optim.Adam(theirs_loop.get_params(opt.lr), betas=(0.9, 0.99), eps=1e-15)
+    me = argparse.Namespace(model=theirs_loop, opt=opt, criterion=torch.nn.MSELoss(reduction='none'), error_map=None, nerfacc_renderer=None,
+                            log=lambda *a, **k: None, epoch=1, optimizer=optimizer, local_rank=1, report_metric_at_train=False, metrics=[],
+                            local_step=0, global_step=1, device=torch.device("cpu"), fp16=False, use_tensorboardX=False,
+                            scaler=torch.amp.GradScaler("cuda", enabled=False), scheduler_update_every_step=True,
+                            lr_scheduler=sched(optimizer), stats={"loss": []}, ema=None)
+    me.train_step = functools.partial(utils.Trainer.train_step, me)
+    me.clear_grad = functools.partial(utils.Trainer.clear_grad, me)
+    torch.manual_seed(21)
+    utils.Trainer.train_one_epoch2(me, {k: v.clone() for k, v in all_data.items()})
+    assert me.global_step == 1 + n_steps and len(me.stats["loss"]) == 1
+
+    # (b) the fast path on the same shuffled batches and jitter draws
+    fused = FusedAdam(fast.get_params(opt.lr), betas=(0.9, 0.99), eps=1e-15)
+    lr_sched = sched(fused)
+    step = our_trainer.TrainStep(fast, opt, fused)
+    fast.train()
+    torch.manual_seed(21)
+    shuffled = utils.shuffle_data({k: v.clone() for k, v in all_data.items()})
+    losses = []
+    for b in range(n_steps):
+        d = utils.select_batch(shuffled, b, opt.num_rays, torch.device("cpu"))
+        losses.append(float(step.step(d["rays_o"][0], d["rays_d"][0], d["images"][0], update_grid=False)))
+        lr_sched.step()
+    assert abs(sum(losses) / n_steps - me.stats["loss"][0]) <= 1e-5 * me.stats["loss"][0]
+    assert optimizer.param_groups[0]["lr"] == fused.param_groups[0]["lr"] != opt.lr            # the warm-up schedule moved both
+    start = OurNet(**build)
+    scene.init_model_(start, seed=0)
+    for (name, a), b, a0 in zip(theirs_loop.named_parameters(), fast.parameters(), start.parameters()):
+        travelled = float((a - a0).norm())
+        assert travelled > 0.0, name                                              # four Adam steps moved every tensor ...
+        assert float((a - b).norm()) <= 1e-4 * travelled, name      # ... and both loops moved it to the same place (measured: 2e-7)

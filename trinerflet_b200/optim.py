@@ -30,6 +30,11 @@ def _dense_storage(t):
     return True
 
 
+def _require_cuda_f32(p):
+    if not p.is_cuda or p.dtype != torch.float32:
+        raise RuntimeError("trinerflet_b200.FusedAdam: parameters must be fp32 CUDA tensors (no CPU fallback)")
+
+
 class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1 and 0 <= betas[1] < 1) or weight_decay < 0:
@@ -55,8 +60,7 @@ class FusedAdam(torch.optim.Optimizer):
             for p in group["params"]:
                 if p.grad is None:
                     continue
-                if not p.is_cuda or p.dtype != torch.float32:
-                    raise RuntimeError("trinerflet_b200.FusedAdam: parameters must be fp32 CUDA tensors (no CPU fallback)")
+                _require_cuda_f32(p)
                 if not _dense_storage(p):
                     raise RuntimeError("FusedAdam needs dense parameter storage")
                 dev = p.device
