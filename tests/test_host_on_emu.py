@@ -598,3 +598,50 @@ def test_full_frame_render_sharded_world2_gloo():
     out = mgr.dict()
     mp.spawn(_render_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+def test_fused_adam_resumes_from_torch_adam_checkpoint_host_logic(emu):
+    """FusedAdam's host logic over the host build of csrc/optim.cu (the device run is tests/test_gpu_train.py): moments restored
+    from a torch.optim.Adam checkpoint arrive NCHW-contiguous with a per-parameter `step`; the resumed update must pair every
+    element with its own moments (channels-last parameters!) and continue the bias correction from the saved count, then keep
+    tracking torch.optim.Adam step for step."""
+    import copy
+    from trinerflet_b200.optim import FusedAdam
+    g = torch.Generator().manual_seed(5)
+    net_a, net_b = _model(), _model()
+    net_b.load_state_dict(net_a.state_dict())
+    adam = torch.optim.Adam(net_a.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15)
+
+    def grads():
+        return [torch.randn(p.shape, generator=g) * (1 + i) for i, p in enumerate(net_a.parameters())]
+
+    for _ in range(3):
+        for p, gr in zip(net_a.parameters(), grads()):
+            p.grad = gr
+        adam.step()
+    sd = copy.deepcopy(adam.state_dict())
+    for st in sd["state"].values():
+        for k in ("exp_avg", "exp_avg_sq"):
+            st[k] = st[k].contiguous()                     # logical NCHW order, dense: NOT the channels-last storage order
+    with torch.no_grad():
+        for pa, pb in zip(net_a.parameters(), net_b.parameters()):
+            pb.copy_(pa)
+    fused = FusedAdam(net_b.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15)
+    fused.load_state_dict(sd)
+    for k in range(2):
+        for pa, pb, gr in zip(net_a.parameters(), net_b.parameters(), grads()):
+            pa.grad, pb.grad = gr, gr.clone()
+        adam.step()
+        fused.step()
+        assert float(fused.param_groups[0]["_tnl_state"][0]) == 4.0 + k
+        for (n, pa), pb in zip(net_a.named_parameters(), net_b.parameters()):
+            assert rel_l2(pb, pa) <= 1e-6, (n, k, rel_l2(pb, pa))
+    # its own state dict round-trips too
+    fused2 = FusedAdam(net_b.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15)
+    fused2.load_state_dict(copy.deepcopy(fused.state_dict()))
+    for pa, pb, gr in zip(net_a.parameters(), net_b.parameters(), grads()):
+        pa.grad, pb.grad = gr, gr.clone()
+    adam.step()
+    fused2.step()
+    for (n, pa), pb in zip(net_a.named_parameters(), net_b.parameters()):
+        assert rel_l2(pb, pa) <= 1e-6, n
