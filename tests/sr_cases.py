@@ -191,3 +191,60 @@ def check_low_resolution_phase_cost(device, R):
     full_launches = _lib.launch_count - before
     assert tuple(planes.shape) == (3, 16, R // 4, R // 4) and tuple(full.shape) == (3, 16, R, R)
     assert low_launches == 2 and full_launches == 4
+
+
+def _bilinear_any_order(planes, xyz, bound):
+    """plain-torch tri-plane bilinear sampling (align_corners, border clamp) written with index arithmetic, so that autograd can
+    differentiate it any number of times w.r.t. the planes -- the ground truth for the high-order op"""
+    R = planes.shape[-1]
+    u = xyz / bound
+    out = []
+    for p, (a, b) in enumerate(((0, 2), (0, 1), (1, 2))):
+        ix = (((u[:, a] + 1) / 2) * (R - 1)).clamp(0, R - 1)
+        iy = (((u[:, b] + 1) / 2) * (R - 1)).clamp(0, R - 1)
+        x0, y0 = ix.floor().long(), iy.floor().long()
+        x1, y1 = (x0 + 1).clamp(max=R - 1), (y0 + 1).clamp(max=R - 1)
+        wx1, wy1 = ix - x0, iy - y0
+        wx0, wy0 = 1 - wx1, 1 - wy1
+        pl = planes[p]                                          # [C, R, R]
+        v = (pl[:, y0, x0] * (wx0 * wy0) + pl[:, y0, x1] * (wx1 * wy0) + pl[:, y1, x0] * (wx0 * wy1) + pl[:, y1, x1] * (wx1 * wy1))
+        out.append(v.t())                                       # [M, C]
+    return torch.cat(out, dim=-1)
+
+
+def check_high_order_gradients(device):
+    """high_order_gradients = True (the capability of the reference's grid_backward.py): a loss on the GRADIENT w.r.t. the planes
+    (gradient-penalty shape) back-propagates through the sampling backward; first and second order against plain torch in fp64"""
+    from trinerflet_b200 import sr_encoder
+    gen = torch.Generator().manual_seed(9)
+    C, R, M = 8, 16, 200
+    enc = sr_encoder.TriPlaneVolume(number_of_features=C, plane_resolution=R, inner_multi_res_scale=1, input_pts_in_unit_cube=False,
+                                    lbound=1.5)
+    G.randomise_(enc, gen, 1.0)
+    enc = enc.to(device)
+    enc.high_order_gradients = True
+    x = (torch.rand(M, 3, generator=gen) * 2 - 1) * 1.6          # some outside the cube: border clamp
+    w = torch.randn(M, 3 * C, generator=gen)
+
+    def penalty(sample, planes, xs, ws):
+        y = sample(planes, xs)
+        s = (y ** 2 * ws).sum()
+        g, = torch.autograd.grad(s, planes, create_graph=True)
+        return s + (g ** 2).sum(), y, g
+
+    planes = enc.planes_features
+    loss, y, g = penalty(lambda pl, xs: enc(xs, bound=1.5), planes, x.to(device), w.to(device))
+    loss.backward()
+    pd = planes.detach().cpu().double().contiguous().requires_grad_(True)
+    loss_d, y_d, g_d = penalty(lambda pl, xs: _bilinear_any_order(pl, xs, 1.5), pd, x.double(), w.double())
+    loss_d.backward()
+    assert rel_l2(y, y_d) <= TOL and rel_l2(g, g_d) <= TOL
+    assert abs(float(loss.detach()) - float(loss_d.detach())) <= TOL * abs(float(loss_d.detach()))
+    assert rel_l2(planes.grad, pd.grad) <= 10 * TOL              # second order: two more passes of fp32 sampling / scatter
+    # third order exists as well (the ops alternate); the default op refuses the second
+    enc.zero_grad()
+    y = enc(x.to(device), bound=1.5)
+    g1, = torch.autograd.grad((y ** 3).sum(), planes, create_graph=True)
+    g2, = torch.autograd.grad((g1 ** 2).sum(), planes, create_graph=True)
+    (g2 ** 2).sum().backward()
+    assert torch.isfinite(planes.grad).all() and float(planes.grad.abs().max()) > 0

@@ -67,6 +67,10 @@ def test_position_gradient_properties(emu):
     sr_cases.check_position_gradient_properties("cpu")
 
 
+def test_high_order_gradients_like_grid_backward(emu):
+    sr_cases.check_high_order_gradients("cpu")
+
+
 def test_low_resolution_phase_runs_coarse_levels_only(emu):
     sr_cases.check_low_resolution_phase_cost("cpu", R=128)
 

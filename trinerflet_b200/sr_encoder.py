@@ -16,8 +16,9 @@ reconstruction encoder (triplane_encoder.py in this package):
     shared coarse levels).  With `enable_cache` both readings are kept until `reset_cahce()`.
   * positions arrive in the unit cube (`input_pts_in_unit_cube`) and are mapped to [-lbound, lbound] first.
   * the positions may require grad (analytic normals, threestudio/models/geometry/implicit_volume.py:218-226): the sampling
-    node returns d/d(xyz) from tnl_sample_planes_backward_coords.  As with the reference's F.grid_sample (:262; the
-    double-backward wrapper of grid_backward.py is commented out at :263), that gradient is not differentiable again.
+    node returns d/d(xyz) from tnl_sample_planes_backward_coords.  As with the reference's F.grid_sample (:262), the backward
+    is not differentiable again by default; `high_order_gradients = True` switches to an op with the capability of the
+    reference's grid_backward.py (whose call is commented out at :263): gradients of any order between planes and features.
   * an empty batch returns zeros(0, 3C) (:431-434).
 
 Storage is channels-last as everywhere in this package (see triplane_encoder.py); reference checkpoints load unchanged.
@@ -66,8 +67,58 @@ class _SamplePlanesXyz(Function):
         return g_planes, g_xyz, None
 
 
-def sample_planes_xyz(planes, coords, bound):
-    """planes logical [3,C,R,R], coords [M,3] in [-bound, bound] -> features [M, 3C]; differentiable in both."""
+class _SampleHighOrder(Function):
+    """The sampling op with gradients of arbitrary order between the planes and the output -- the capability of the reference's
+    grid_backward.py (:41-99, NVIDIA's grid_sample_gradfix; present in the reference but switched off at triplane_encoder.py:263):
+    the backward pass is itself an autograd node whose derivative w.r.t. the incoming feature gradient is this op again, applied
+    to the plane-shaped cotangent.  As there (:84-97), second-order terms through the positions are not provided."""
+
+    @staticmethod
+    def forward(ctx, planes, coords, bound):
+        feat = _SamplePlanesXyz.forward(ctx, planes, coords, bound)
+        ctx.bound = bound
+        return feat
+
+    @staticmethod
+    def backward(ctx, g_feat):
+        planes_cl, xyz = ctx.saved_tensors
+        g_planes, g_xyz = _SampleHighOrderBackward.apply(g_feat, planes_cl, xyz, ctx.bound, ctx.meta, ctx.needs_input_grad[0],
+                                                        ctx.needs_input_grad[1])
+        return g_planes, g_xyz, None
+
+
+class _SampleHighOrderBackward(Function):
+    @staticmethod
+    def forward(ctx, g_feat, planes_cl, xyz, bound, meta, need_planes, need_xyz):
+        M, R, C, inv, coords_dtype = meta
+        g_feat = g_feat.detach().contiguous().float()
+        g_planes = g_xyz = None
+        if need_planes:
+            g_planes = cl_empty_planes(C, R, device=g_feat.device, zero=True)
+            call("tnl_sample_planes_backward", ptr(g_feat), 0, ptr(xyz), M, R, C, inv, 0, None, None, ptr(g_planes), stream())
+        if need_xyz:
+            g_xyz = torch.empty(M, 3, device=g_feat.device, dtype=torch.float32)
+            call("tnl_sample_planes_backward_coords", ptr(g_feat), ptr(planes_cl), ptr(xyz), M, R, C, inv, 0, ptr(g_xyz), stream())
+            g_xyz = g_xyz.to(coords_dtype)
+        ctx.save_for_backward(xyz)
+        ctx.bound = bound
+        ctx.set_materialize_grads(False)
+        return g_planes, g_xyz
+
+    @staticmethod
+    def backward(ctx, gg_planes, gg_xyz):
+        xyz, = ctx.saved_tensors
+        gg_feat = None
+        if ctx.needs_input_grad[0] and gg_planes is not None:
+            gg_feat = _SampleHighOrder.apply(gg_planes, xyz, ctx.bound)
+        return gg_feat, None, None, None, None, None, None
+
+
+def sample_planes_xyz(planes, coords, bound, high_order=False):
+    """planes logical [3,C,R,R], coords [M,3] in [-bound, bound] -> features [M, 3C]; differentiable in both.  high_order:
+    gradients of any order between planes and features (see _SampleHighOrder); default: once, like F.grid_sample."""
+    if high_order:
+        return _SampleHighOrder.apply(planes, coords, float(bound))
     return _SamplePlanesXyz.apply(planes, coords, float(bound))
 
 
@@ -109,6 +160,9 @@ class TriPlaneVolume(_te.TriPlaneVolume):
         self.enable_cache = False
         self.enable_grid_acc = False
         self.init_fn = init_fn
+        # True: sample through the op that can be differentiated repeatedly w.r.t. the planes -- what the reference's
+        # grid_backward.grid_sample offers (its call is commented out there, triplane_encoder.py:263, so the default is off)
+        self.high_order_gradients = False
 
     # -- the two readings of the coefficient pyramid (:268-340) ----------------------------------------
     def _level_split(self):
@@ -170,7 +224,7 @@ class TriPlaneVolume(_te.TriPlaneVolume):
             lbound = self.lbound
         if self.input_pts_in_unit_cube:
             coordinates = (coordinates * 2 - 1) * lbound
-        feat = sample_planes_xyz(plane_features, coordinates, lbound)
+        feat = sample_planes_xyz(plane_features, coordinates, lbound, high_order=self.high_order_gradients)
         return feat.view(feat.shape[0], 3, plane_features.shape[1])
 
     def forward(self, coordinates, bound=None):
